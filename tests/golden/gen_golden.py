@@ -1,0 +1,184 @@
+"""Generate golden vectors by running the LIVE reference (uma-pi1/kge) in the build container.
+
+    python tests/golden/gen_golden.py          # writes tests/golden/*.npz
+
+The reference holds no golden vectors of its own for the scoring path, so
+these files — outputs of the unmodified reference on seeded inputs — are what pins the
+oracle (tests/test_oracle_golden.py) and, through it and directly, the CUDA path
+(tests/test_gpu_*.py).  /root/reference does not exist on the GPU box; the committed .npz
+files travel instead.  Inputs are stored with the outputs so replay needs no RNG parity.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import kge_oracle as orc  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+S, P, O = 0, 1, 2
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def gen_scores(model, E, R, D, n, l_norm, sigma, tag):
+    ent, rel = orc.make_tables(model, E, R, D, sigma=sigma, seed=1234)
+    tri = orc.make_triples(E, R, n, seed=0)
+    m, _, _ = ref_shim.make_reference_model(
+        model, E, R, D, ent, rel, l_norm=l_norm if model in ("transe", "rotate") else None
+    )
+    s, p, o = tri[:, S], tri[:, P], tri[:, O]
+    g = torch.Generator().manual_seed(7)
+    subset = torch.randperm(E, generator=g)[: max(3, E // 3)]
+    psub = torch.randperm(R, generator=g)[: max(2, R // 2)]
+    with torch.no_grad():
+        out = dict(
+            ent=_np(ent), rel=_np(rel), triples=_np(tri), subset=_np(subset), psub=_np(psub),
+            l_norm=np.float64(l_norm),
+            spo=_np(m.score_spo(s, p, o)),
+            sp=_np(m.score_sp(s, p)),
+            po=_np(m.score_po(p, o)),
+            sp_subset=_np(m.score_sp(s, p, subset)),
+            po_subset=_np(m.score_po(p, o, subset)),
+            so=_np(m.score_so(s, o)),
+            so_subset=_np(m.score_so(s, o, psub)),
+            sp_po=_np(m.score_sp_po(s, p, o)),
+            sp_po_subset=_np(m.score_sp_po(s, p, o, subset)),
+        )
+    np.savez_compressed(os.path.join(HERE, f"scores_{tag}.npz"), **out)
+    print("wrote", tag, {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
+
+
+def gen_losses():
+    ref_shim.import_reference()
+    from kge import Config
+    from kge.util.loss import KgeLoss
+
+    g = torch.Generator().manual_seed(11)
+    n, E = 9, 57
+    scores = torch.randn((n, E), generator=g) * 3.0
+    idx = torch.randint(0, E, (n,), generator=g)
+    multi = (torch.rand((n, E), generator=g) < 0.08).float()
+    multi[torch.arange(n), idx] = 1.0
+    smooth = (1.0 - 0.1) * multi + 1.0 / E  # train_KvsAll.py:260-266
+    out = dict(scores=_np(scores), idx=_np(idx), multi=_np(multi), smooth=_np(smooth))
+
+    def make(loss, arg=float("nan")):
+        c = Config()
+        c.folder = None
+        c.set("console.quiet", True)
+        c.set("job.device", "cpu")
+        c.set("train.loss", loss)
+        c.set("train.loss_arg", arg)
+        return KgeLoss.create(c)
+
+    out["bce_idx"] = _np(make("bce")(scores, idx))
+    out["bce_idx_off2"] = _np(make("bce", 2.0)(scores, idx))
+    out["bce_multi"] = _np(make("bce")(scores, multi))
+    out["bce_smooth"] = _np(make("bce")(scores, smooth))
+    out["kl_idx"] = _np(make("kl")(scores, idx))
+    out["kl_multi"] = _np(make("kl")(scores, multi))
+    out["kl_smooth"] = _np(make("kl")(scores, smooth))
+    np.savez_compressed(os.path.join(HERE, "losses.npz"), **out)
+    print("wrote losses")
+
+
+def gen_ranks():
+    ref_shim.import_reference()
+    from kge.job import EntityRankingJob
+
+    class _Self:
+        tie_rtol = 1e-4
+        tie_atol = 1e-5
+        tie_handling = "rounded_mean_rank"
+
+    me = _Self()
+    me._get_ranks_and_num_ties = lambda a, b: EntityRankingJob._get_ranks_and_num_ties(me, a, b)
+    g = torch.Generator().manual_seed(13)
+    n, E = 11, 83
+    sp = torch.randn((n, E), generator=g) * 2.0
+    po = torch.randn((n, E), generator=g) * 2.0
+    # exercise ties, near-ties, NaN, +-inf
+    sp[0, 3] = sp[0, 5]
+    sp[1, 7] = sp[1, 9] * (1 + 5e-5)
+    sp[2, 4] = float("nan")
+    sp[3, 6] = float("inf")
+    po[4, 2] = float("-inf")
+    po[5, :] = 1.25
+    true_o_idx = torch.randint(0, E, (n,), generator=g)
+    true_s_idx = torch.randint(0, E, (n,), generator=g)
+    true_o_idx[0], true_o_idx[1], true_o_idx[2] = 5, 9, 4  # true answer is the tied / NaN one
+    o_true = sp[torch.arange(n), true_o_idx].clone()
+    s_true = po[torch.arange(n), true_s_idx].clone()
+    labels = torch.zeros((n, 2 * E))
+    mask = torch.rand((n, 2 * E), generator=g) < 0.05
+    labels[mask] = float("inf")
+    labels[torch.arange(n), true_o_idx] = 0.0  # own answer zeroed :287-290
+    labels[torch.arange(n), E + true_s_idx] = 0.0
+    out = dict(sp=_np(sp), po=_np(po), labels=_np(labels), o_true=_np(o_true), s_true=_np(s_true),
+               true_o_idx=_np(true_o_idx), true_s_idx=_np(true_s_idx))
+    r, t = EntityRankingJob._get_ranks_and_num_ties(me, sp, o_true)
+    out["raw_o_rank"], out["raw_o_ties"] = _np(r), _np(t)
+    r, t = EntityRankingJob._get_ranks_and_num_ties(me, po, s_true)
+    out["raw_s_rank"], out["raw_s_ties"] = _np(r), _np(t)
+    s_rank, s_ties, o_rank, o_ties, _, _ = EntityRankingJob._filter_and_rank(
+        me, sp, po, labels, o_true, s_true
+    )
+    out.update(filt_s_rank=_np(s_rank), filt_s_ties=_np(s_ties),
+               filt_o_rank=_np(o_rank), filt_o_ties=_np(o_ties))
+    out["final_o"] = _np(EntityRankingJob._get_ranks(me, o_rank, o_ties))
+    np.savez_compressed(os.path.join(HERE, "ranks.npz"), **out)
+    print("wrote ranks")
+
+
+def gen_ns(model, E, R, D, n, K, l_norm, tag):
+    ref_shim.import_reference()
+    from kge.util.sampler import DefaultBatchNegativeSample
+
+    ent, rel = orc.make_tables(model, E, R, D, sigma=1.0, seed=1234)
+    tri = orc.make_triples(E, R, n, seed=3)
+    m, config, _ = ref_shim.make_reference_model(
+        model, E, R, D, ent, rel, l_norm=l_norm if model in ("transe", "rotate") else None
+    )
+    g = torch.Generator().manual_seed(5)
+    out = dict(ent=_np(ent), rel=_np(rel), triples=_np(tri), l_norm=np.float64(l_norm))
+    with torch.no_grad():
+        out["pos"] = _np(m.score_spo(tri[:, S], tri[:, P], tri[:, O]))
+        for slot, nm in ((S, "s"), (P, "p"), (O, "o")):
+            hi = R if slot == P else E
+            neg = torch.randint(0, hi, (n, K), generator=g)
+            out[f"neg_{nm}"] = _np(neg)
+            for impl in ("triple", "batch"):
+                config.set("negative_sampling.implementation", impl)
+                bns = DefaultBatchNegativeSample(config, "negative_sampling", tri, slot, K, neg)
+                out[f"ns_{nm}_{impl}"] = _np(bns.score(m))
+    np.savez_compressed(os.path.join(HERE, f"ns_{tag}.npz"), **out)
+    print("wrote ns", tag)
+
+
+def main():
+    torch.manual_seed(0)
+    E, R, n = 97, 7, 13
+    for model in orc.MODELS:
+        D = 16 if model == "rescal" else 32
+        gen_scores(model, E, R, D, n, 1.0, 1.0, model)
+    gen_scores("transe", E, R, 32, n, 2.0, 1.0, "transe_l2")
+    gen_scores("rotate", E, R, 32, n, 2.0, 1.0, "rotate_l2")
+    gen_scores("complex", 301, 5, 64, 33, 1.0, 0.1, "complex_sigma01")
+    gen_losses()
+    gen_ranks()
+    for model in ("complex", "rotate", "transe", "rescal"):
+        gen_ns(model, 61, 5, 16 if model == "rescal" else 32, 6, 10, 1.0, model)
+
+
+if __name__ == "__main__":
+    main()

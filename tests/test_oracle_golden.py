@@ -1,0 +1,100 @@
+"""Pin the CPU oracle against golden vectors produced by the live reference
+(tests/golden/gen_golden.py).  CPU only."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kge_oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+S, P, O = 0, 1, 2
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    return {k: torch.from_numpy(z[k]) if z[k].ndim else z[k].item() for k in z.files}
+
+
+def _model_of(tag):
+    return tag.split("_")[0]
+
+
+SCORE_FILES = sorted(os.path.basename(f) for f in glob.glob(os.path.join(GOLDEN, "scores_*.npz")))
+
+
+def _close(a, b, what):
+    # the oracle mirrors the reference's own op sequence: agreement is fp32 round-off
+    scale = max(1.0, float(b.abs().max()))
+    err = float((a - b).abs().max())
+    assert err <= 2e-6 * scale, f"{what}: max|d|={err} scale={scale}"
+
+
+@pytest.mark.parametrize("fname", SCORE_FILES)
+def test_scores_match_reference(fname):
+    g = _load(fname)
+    model = _model_of(fname[len("scores_"):-4])
+    ent, rel, tri, ln = g["ent"], g["rel"], g["triples"], float(g["l_norm"])
+    s, p, o = tri[:, S], tri[:, P], tri[:, O]
+    _close(orc.score_spo(model, ent, rel, s, p, o, ln), g["spo"], "spo")
+    _close(orc.score_sp(model, ent, rel, s, p, None, ln), g["sp"], "sp")
+    _close(orc.score_po(model, ent, rel, p, o, None, ln), g["po"], "po")
+    _close(orc.score_sp(model, ent, rel, s, p, g["subset"], ln), g["sp_subset"], "sp_subset")
+    _close(orc.score_po(model, ent, rel, p, o, g["subset"], ln), g["po_subset"], "po_subset")
+    _close(orc.score_so(model, ent, rel, s, o, None, ln), g["so"], "so")
+    _close(orc.score_so(model, ent, rel, s, o, g["psub"], ln), g["so_subset"], "so_subset")
+    _close(orc.score_sp_po(model, ent, rel, s, p, o, None, ln), g["sp_po"], "sp_po")
+    _close(orc.score_sp_po(model, ent, rel, s, p, o, g["subset"], ln), g["sp_po_subset"], "sp_po_subset")
+
+
+def test_losses_match_reference():
+    g = _load("losses.npz")
+    x = g["scores"]
+    rel = lambda a, b: abs(float(a) - float(b)) <= 2e-6 * max(1.0, abs(float(b)))
+    assert rel(orc.bce_loss(x, g["idx"]), g["bce_idx"])
+    assert rel(orc.bce_loss(x, g["idx"], 2.0), g["bce_idx_off2"])
+    assert rel(orc.bce_loss(x, g["multi"]), g["bce_multi"])
+    assert rel(orc.bce_loss(x, g["smooth"]), g["bce_smooth"])
+    assert rel(orc.kl_loss(x, g["idx"]), g["kl_idx"])
+    assert rel(orc.kl_loss(x, g["multi"]), g["kl_multi"])
+    assert rel(orc.kl_loss(x, g["smooth"]), g["kl_smooth"])
+    assert rel(orc.kvsall_smooth_labels(g["multi"], 0.1).sum(), g["smooth"].sum())
+
+
+def test_ranks_match_reference_bit_exact():
+    g = _load("ranks.npz")
+    r, t = orc.ranks_and_ties(g["sp"], g["o_true"])
+    assert torch.equal(r, g["raw_o_rank"]) and torch.equal(t, g["raw_o_ties"])
+    r, t = orc.ranks_and_ties(g["po"], g["s_true"])
+    assert torch.equal(r, g["raw_s_rank"]) and torch.equal(t, g["raw_s_ties"])
+    sr, st, orank, ot = orc.filter_and_rank(g["sp"], g["po"], g["labels"], g["o_true"], g["s_true"])
+    assert torch.equal(sr, g["filt_s_rank"]) and torch.equal(st, g["filt_s_ties"])
+    assert torch.equal(orank, g["filt_o_rank"]) and torch.equal(ot, g["filt_o_ties"])
+    assert torch.equal(orc.final_ranks(orank, ot), g["final_o"])
+
+
+@pytest.mark.parametrize("model", ["complex", "rotate", "transe", "rescal"])
+def test_ns_match_reference(model):
+    g = _load(f"ns_{model}.npz")
+    ent, rel, tri, ln = g["ent"], g["rel"], g["triples"], float(g["l_norm"])
+    _close(orc.score_spo(model, ent, rel, tri[:, S], tri[:, P], tri[:, O], ln), g["pos"], "pos")
+    for slot, nm in ((S, "s"), (P, "p"), (O, "o")):
+        for impl in ("triple", "batch"):
+            got = orc.ns_score(model, ent, rel, tri, g[f"neg_{nm}"], slot, impl, ln)
+            _close(got, g[f"ns_{nm}_{impl}"], f"ns {nm} {impl}")
+    full = orc.ns_scores_with_positive(model, ent, rel, tri, g["neg_o"], O, "triple", ln)
+    _close(full[:, 0], g["pos"], "assembled col0")
+    _close(full[:, 1:], g["ns_o_triple"], "assembled negs")
+
+
+def test_fp64_mode_is_consistent():
+    for model in orc.MODELS:
+        D = 16 if model == "rescal" else 32
+        ent, rel = orc.make_tables(model, 50, 4, D)
+        tri = orc.make_triples(50, 4, 8)
+        a = orc.score_sp_po(model, ent, rel, tri[:, 0], tri[:, 1], tri[:, 2])
+        b = orc.score_sp_po(model, ent.double(), rel.double(), tri[:, 0], tri[:, 1], tri[:, 2])
+        rms = float(b.pow(2).mean().sqrt())
+        assert float((a.double() - b).abs().max()) <= 1e-5 * max(rms, 1.0)
