@@ -1,0 +1,203 @@
+/*
+ * b200kge.h — C ABI of the B200-native KGE scoring engine (libb200kge.so).
+ *
+ * This is the drop-in boundary for ONE path of uma-pi1/kge (LibKGE): embedding-row gather +
+ * relational scorer forward (+ fused BCE/KL loss, rank/tie counting, negative-sample scoring)
+ * behind KgeModel.score_spo/score_sp/score_po/score_sp_po and RelationalScorer.score_emb.
+ * The reference has no FFI for this path (it is PyTorch tensor expressions); every entry point
+ * below names the reference function (file:line under /root/reference) whose arithmetic it
+ * replaces.  INTEGRATION.md shows the ctypes binding a LibKGE maintainer would add.
+ *
+ * Conventions
+ *  - Plain C: raw device pointers, sizes, a cudaStream_t passed as void*.  No torch types.
+ *  - All float data is fp32, row-major.  Index arrays are int64 (LibKGE collates `.long()`,
+ *    train_1vsAll.py:34) and live on the device unless the name says `_host`.
+ *  - A "rows view" (b200kge_rows_t) is how an embedding operand is passed: row i of the operand is
+ *        base + (idx ? idx[i] : i) * ld
+ *    so the same entry point serves KgeModel.score_* (base = embedding table, idx = batch indexes:
+ *    the LookupEmbedder gather lookup_embedder.py:96-97 is fused) and RelationalScorer.score_emb
+ *    (base = already-gathered [n,D] matrix, idx = NULL).  idx == NULL with rows == vocab is
+ *    "embed_all" (lookup_embedder.py:99-112) without the table copy.
+ *  - Outputs and workspace are caller-allocated; nothing is retained across calls; the library
+ *    keeps no global device state and is re-entrant per stream.
+ *  - Every function returns 0 on success or a negative b200kge_status; b200kge_last_error() gives a
+ *    thread-local message.  CUDA allocation failures are reported with the literal text
+ *    "CUDA out of memory" so LibKGE's sub-batch auto-tuner (train.py:384-413) keeps working.
+ */
+#ifndef B200KGE_H_
+#define B200KGE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200KGE_VERSION 100
+
+typedef void* b200kge_stream_t; /* cudaStream_t */
+
+typedef enum {
+  B200KGE_OK = 0,
+  B200KGE_ERR_INVALID = -1,     /* bad argument (ValueError on the Python side)            */
+  B200KGE_ERR_UNSUPPORTED = -2, /* valid but not handled by this build (e.g. D % 4 != 0)   */
+  B200KGE_ERR_CUDA = -3,        /* CUDA runtime error; message holds cudaGetErrorString    */
+  B200KGE_ERR_WORKSPACE = -4,   /* workspace too small; see b200kge_workspace_bytes        */
+  B200KGE_ERR_NO_DEVICE = -5    /* no sm_100 device: the library never falls back to a CPU */
+} b200kge_status;
+
+/* Scorers on the path (kge/model/<name>.py). */
+typedef enum {
+  B200KGE_COMPLEX = 0,  /* complex.py:18-43   */
+  B200KGE_DISTMULT = 1, /* distmult.py:13-25  */
+  B200KGE_SIMPLE = 2,   /* simple.py:13-33    */
+  B200KGE_CP = 3,       /* cp.py:13-30        */
+  B200KGE_RESCAL = 4,   /* rescal.py:14-52    */
+  B200KGE_TRANSE = 5,   /* transe.py:15-37    */
+  B200KGE_ROTATE = 6    /* rotate.py:20-69    */
+} b200kge_model;
+
+/* `combine` of RelationalScorer.score_emb (kge_model.py:151-181) for the 1-vs-N forms. */
+typedef enum {
+  B200KGE_SP_ = 0, /* "sp_": out[i,j] = score(s_i, p_i, cand_j) */
+  B200KGE__PO = 1  /* "_po": out[i,j] = score(cand_j, p_i, o_i) */
+} b200kge_combine;
+
+/* Which kernel family computes dot-product scorers. */
+typedef enum {
+  B200KGE_PREC_AUTO = 0,   /* tcgen05 3xTF32 when the shape allows it, else fp32 SIMT           */
+  B200KGE_PREC_FP32 = 1,   /* CUDA-core fp32 FFMA (bit-for-bit fp32 products)                    */
+  B200KGE_PREC_3XTF32 = 2, /* tcgen05 tensor cores, hi/lo split, fp32-equivalent (~3e-6 of rms)  */
+  B200KGE_PREC_TF32 = 3    /* tcgen05 single pass (~1e-3 of rms; does NOT meet the 1e-4 bar)     */
+} b200kge_precision;
+
+typedef enum {
+  B200KGE_LOSS_BCE = 1, /* BCEWithLogitsKgeLoss, reduction sum, + offset  loss.py:153-159 */
+  B200KGE_LOSS_KL = 2   /* KLDivWithSoftmaxKgeLoss (CE for index labels)   loss.py:198-213 */
+} b200kge_loss;
+
+typedef struct {
+  const float* base;  /* device */
+  const int64_t* idx; /* device, may be NULL */
+  int64_t rows;       /* number of rows of the operand (length of idx, or table rows) */
+  int64_t ld;         /* row stride in floats */
+  int32_t dim;        /* row width in floats */
+} b200kge_rows_t;
+
+/* Labels of a 1-vs-N loss: exactly one of idx / dense is non-NULL.
+ * idx   [n]     position of the single 1 per row (1vsAll; loss.py:105-117 makes it one-hot)
+ * dense [n,ldl] label matrix (KvsAll multi-hot incl. label smoothing train_KvsAll.py:242-266,
+ *               negative sampling [1,0,...] train_negative_sampling.py:128-137)            */
+typedef struct {
+  const int64_t* idx;
+  const float* dense;
+  int64_t ldl;
+} b200kge_labels_t;
+
+/* Library / device ---------------------------------------------------------------------------- */
+int b200kge_version(void);
+const char* b200kge_last_error(void);
+/* 0 if the current device is sm_100 (B200), else B200KGE_ERR_NO_DEVICE. */
+int b200kge_device_ok(void);
+/* Number of kernel launches issued by this library on the calling thread since the last reset
+ * (bench.py reports it as gpu_launches). */
+int64_t b200kge_launch_count(int reset);
+
+/* Bytes of device workspace sufficient for any call below with n query rows (per direction), m
+ * candidate rows and entity width D.  cand_has_idx != 0 reserves room to gather an index subset
+ * of candidates for the tensor-core path. */
+size_t b200kge_workspace_bytes(int model, int64_t n, int64_t m, int32_t D, int cand_has_idx);
+
+/* Row-wise triples ---------------------------------------------------------------------------- */
+/* out[i] = score(s_i, p_i, o_i).  Replaces KgeModel.score_spo kge_model.py:663-680 and
+ * score_emb(combine="spo") of every in-scope scorer.  TransE adds eps=1e-6 to the difference like
+ * F.pairwise_distance (transe.py:18). */
+int b200kge_score_spo(int model, float l_norm, const b200kge_rows_t* s, const b200kge_rows_t* p,
+                      const b200kge_rows_t* o, int64_t n, float* out, b200kge_stream_t stream);
+
+/* 1-vs-N ---------------------------------------------------------------------------------------
+ * out[i*ldo + j], i < n, j < cand->rows.  `q` are the per-row entity operands (subjects for sp_,
+ * objects for _po), `p` the per-row relation operands, `cand` the candidate entities (all of them,
+ * a contiguous chunk, or an index subset).  Replaces KgeModel.score_sp / score_po
+ * kge_model.py:682-725 and score_emb(combine in {"sp_","_po"}). */
+int b200kge_score_1vsN(int model, int combine, float l_norm, int precision,
+                       const b200kge_rows_t* q, const b200kge_rows_t* p,
+                       const b200kge_rows_t* cand, int64_t n, float* out, int64_t ldo,
+                       void* workspace, size_t workspace_bytes, b200kge_stream_t stream);
+
+/* out is [n, 2m] = [sp_ scores | _po scores], m = cand->rows.  Replaces KgeModel.score_sp_po
+ * kge_model.py:749-789 (one launch sequence, no torch.cat copy). */
+int b200kge_score_sp_po(int model, float l_norm, int precision, const b200kge_rows_t* s,
+                        const b200kge_rows_t* p, const b200kge_rows_t* o,
+                        const b200kge_rows_t* cand, int64_t n, float* out, int64_t ldo,
+                        void* workspace, size_t workspace_bytes, b200kge_stream_t stream);
+
+/* Fused 1-vs-N score + loss: the [n,m] scores never reach HBM.
+ * loss_out[0] (device float) receives the SUM-reduced loss of the block exactly as
+ * KgeLoss.__call__ returns it (the caller divides by batch size, train_1vsAll.py:65);
+ * row_loss_out (optional, [n]) receives the per-row terms.  Replaces score_sp/score_po followed by
+ * BCEWithLogitsKgeLoss / KLDivWithSoftmaxKgeLoss (train_1vsAll.py:64-65,75-76,
+ * train_KvsAll.py:275-289). */
+int b200kge_score_1vsN_loss(int model, int combine, float l_norm, int precision,
+                            const b200kge_rows_t* q, const b200kge_rows_t* p,
+                            const b200kge_rows_t* cand, int64_t n, const b200kge_labels_t* labels,
+                            int loss_kind, float offset, float* loss_out, float* row_loss_out,
+                            void* workspace, size_t workspace_bytes, b200kge_stream_t stream);
+
+/* Fused 1-vs-N score + rank/tie counting against a chunk of candidates (additive over chunks,
+ * eval_entity_ranking.py:222-229,310-313).  true_score[i] is the score of row i's true answer;
+ * filter (optional) is the reference's dense label chunk [n, ldf] holding +inf at known-true
+ * columns (own answer zeroed, :287-290) and is SUBTRACTED from the scores before comparing
+ * (:561-566).  rank/ties are int64 [n] and are ACCUMULATED INTO (caller zeroes them before the
+ * first chunk).  Replaces score_sp_po + _filter_and_rank + _get_ranks_and_num_ties :533-596. */
+int b200kge_score_1vsN_rank(int model, int combine, float l_norm, int precision,
+                            const b200kge_rows_t* q, const b200kge_rows_t* p,
+                            const b200kge_rows_t* cand, int64_t n, const float* true_score,
+                            const float* filter, int64_t ldf, float rtol, float atol,
+                            int64_t* rank, int64_t* ties, void* workspace, size_t workspace_bytes,
+                            b200kge_stream_t stream);
+
+/* Dense-score epilogues (for callers that already hold a score matrix) ------------------------ */
+/* KgeLoss on a dense [n,m] score matrix: loss.py:153-159 (BCE) / :198-213 (KL). */
+int b200kge_loss_dense(const float* scores, int64_t lds, int64_t n, int64_t m,
+                       const b200kge_labels_t* labels, int loss_kind, float offset,
+                       float* loss_out, float* row_loss_out, void* workspace,
+                       size_t workspace_bytes, b200kge_stream_t stream);
+
+/* _get_ranks_and_num_ties on a dense [n,m] score matrix (eval_entity_ranking.py:571-596), with the
+ * optional filter subtraction of _filter_and_rank (:561-566).  Bit-exact integer outputs;
+ * ACCUMULATES INTO rank/ties. */
+int b200kge_rank_dense(const float* scores, int64_t lds, int64_t n, int64_t m,
+                       const float* true_score, const float* filter, int64_t ldf, float rtol,
+                       float atol, int64_t* rank, int64_t* ties, b200kge_stream_t stream);
+
+/* Negative sampling -----------------------------------------------------------------------------
+ * out[i*ldo + k] = score of triple i with slot `slot` (0=S,1=P,2=O) replaced by neg[i*K + k].
+ * The gather of the sampled rows is fused with the per-negative dot/distance.  If
+ * with_positive != 0, column 0 of out receives score_spo of the positive triple and negatives go
+ * to columns 1..K (the [n,1+K] assembly of train_negative_sampling.py:139-148).
+ * Replaces BatchNegativeSample.score sampler.py:263-344 (both `triple` and `batch`
+ * implementations give the same numbers; this computes them directly). */
+int b200kge_ns_score(int model, float l_norm, const b200kge_rows_t* s, const b200kge_rows_t* p,
+                     const b200kge_rows_t* o, const b200kge_rows_t* slot_table, int slot,
+                     const int64_t* neg, int64_t n, int64_t K, int with_positive, float* out,
+                     int64_t ldo, b200kge_stream_t stream);
+
+/* Host-buffer entry point (end-to-end measurement and simple embedding use) --------------------
+ * One 1vsAll forward step (train_1vsAll.py:48-82) for a batch of triples held in HOST memory:
+ * copies triples_host [n,3] int64 to the device, runs fused score_sp+loss and score_po+loss
+ * against the whole entity table, copies the scalar
+ *     (loss(score_sp, o) + loss(score_po, s)) / n
+ * back to *loss_host and synchronises the stream.  `ent`/`rel` are the device-resident tables
+ * (idx must be NULL). */
+int b200kge_train_1vsall_forward_host(int model, float l_norm, int precision,
+                                      const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+                                      const int64_t* triples_host, int64_t n, int loss_kind,
+                                      float offset, float* loss_host, void* workspace,
+                                      size_t workspace_bytes, b200kge_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200KGE_H_ */

@@ -1,0 +1,437 @@
+// capi.cu — extern "C" entry points of libb200kge (see include/b200kge.h for the contract).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "fold.cuh"
+
+namespace b200kge {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  if (e == cudaErrorMemoryAllocation)
+    set_error("CUDA out of memory (%s)", what);  // literal matched by LibKGE train.py:384-413
+  else
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return B200KGE_ERR_CUDA;
+}
+
+namespace {
+
+// bump allocator over the caller's workspace
+struct Arena {
+  uint8_t* base;
+  size_t cap, off;
+  void* take(size_t bytes) {
+    size_t a = (off + 255) & ~size_t(255);
+    if (a + bytes > cap) return nullptr;
+    off = a + bytes;
+    return base + a;
+  }
+};
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+int validate_model(int model, const Rows& ent_like, const Rows& rel_like) {
+  if (model < 0 || model > B200KGE_ROTATE) { set_error("unknown model %d", model); return B200KGE_ERR_INVALID; }
+  const int D = ent_like.dim;
+  if (D <= 0) { set_error("entity dim must be positive"); return B200KGE_ERR_INVALID; }
+  if ((model == B200KGE_COMPLEX || model == B200KGE_SIMPLE || model == B200KGE_CP || model == B200KGE_ROTATE) && (D & 1)) {
+    set_error("model %d requires embeddings of even dimensionality (got %d)", model, D);
+    return B200KGE_ERR_INVALID;
+  }
+  const int want = relation_dim(model, D);
+  if (rel_like.dim != want) {
+    set_error("relation dim %d does not match model %d with entity dim %d (expected %d)", rel_like.dim, model, D, want);
+    return B200KGE_ERR_INVALID;
+  }
+  return 0;
+}
+
+int validate_norm(int model, float l_norm) {
+  if ((model == B200KGE_TRANSE || model == B200KGE_ROTATE) && !(l_norm > 0.f && l_norm < 1e30f)) {
+    set_error("l_norm must be a positive finite number (got %g)", (double)l_norm);
+    return B200KGE_ERR_INVALID;
+  }
+  return 0;
+}
+
+// One direction (or the stacked sp+po pair) of a 1-vs-N problem, with any epilogue.
+struct Block {
+  int model, combine;     // combine of the first n rows; stacked => second n rows use the other one
+  const Rows* q0; const Rows* q1;  // per-row entity operands of the two halves (q1 null if not stacked)
+  const Rows* p;
+  const Rows* cand;
+  int64_t n;
+};
+
+int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiParams P, Arena& ws,
+              cudaStream_t st, int* nchunks_out) {
+  const int64_t n = B.n, nq = B.q1 ? 2 * n : n, m = B.cand->rows;
+  const int D = B.q0->dim;
+  Folded f0 = folded_problem(B.model, B.combine, D, l_norm);
+  Folded f1 = f0;
+  if (B.q1) f1 = folded_problem(B.model, 1 - B.combine, D, l_norm);
+  const bool cols_differ = B.q1 && (f0.col_off != f1.col_off);   // CP: halves read different columns
+  const int K = f0.K;
+  const int64_t ldq = round_up(K, 32);
+
+  bool use_tc = false;
+  if (f0.pair_op == PAIR_DOT && precision != B200KGE_PREC_FP32 && !cols_differ) {
+    Rows c = *B.cand;
+    bool ok = (K >= 32) && (c.ld % 4 == 0) && (f0.col_off % 4 == 0) &&
+              ((reinterpret_cast<uintptr_t>(c.base) & 15) == 0) && (m < (1ll << 31));
+    if (precision == B200KGE_PREC_AUTO) use_tc = ok && nq >= 16;
+    else {
+      if (!ok) { set_error("tensor-core path needs K>=32, 16-byte aligned tables with ld%%4==0"); return B200KGE_ERR_UNSUPPORTED; }
+      use_tc = true;
+    }
+  } else if (precision == B200KGE_PREC_3XTF32 || precision == B200KGE_PREC_TF32) {
+    if (f0.pair_op != PAIR_DOT) { set_error("tensor-core precision modes apply to dot-product scorers only"); return B200KGE_ERR_UNSUPPORTED; }
+  }
+
+  if (cols_differ) {
+    // run the two halves as separate blocks (CP reads different candidate columns per direction)
+    Block h0 = B; h0.q1 = nullptr;
+    Block h1 = B; h1.q0 = B.q1; h1.q1 = nullptr; h1.combine = 1 - B.combine;
+    EpiParams P0 = P, P1 = P;
+    P0.n_rows_out = 0; P1.n_rows_out = 0;
+    if (epi_kind == EPI_STORE) { P1.out = P.out + P.col_block; }
+    else { set_error("stacked fused epilogues are not available for CP"); return B200KGE_ERR_UNSUPPORTED; }
+    int rc = run_block(h0, l_norm, precision, epi_kind, P0, ws, st, nchunks_out);
+    if (rc) return rc;
+    return run_block(h1, l_norm, precision, epi_kind, P1, ws, st, nchunks_out);
+  }
+
+  if (use_tc) {
+    const int passes = (precision == B200KGE_PREC_TF32) ? 1 : 3;
+    float* Qhi = (float*)ws.take((size_t)nq * ldq * 4);
+    float* Qlo = (float*)ws.take((size_t)nq * ldq * 4);
+    if (!Qhi || !Qlo) { set_error("workspace too small for folded queries"); return B200KGE_ERR_WORKSPACE; }
+    int rc = launch_fold_queries(B.model, B.combine, *B.q0, *B.p, n, 0, nullptr, ldq, Qhi, Qlo, st);
+    if (rc) return rc;
+    if (B.q1) { rc = launch_fold_queries(B.model, 1 - B.combine, *B.q1, *B.p, n, n, nullptr, ldq, Qhi, Qlo, st); if (rc) return rc; }
+    const float* T = B.cand->base + f0.col_off;
+    int64_t ldt = B.cand->ld;
+    if (B.cand->idx) {
+      float* G = (float*)ws.take((size_t)m * ldq * 4);
+      if (!G) { set_error("workspace too small to gather the candidate subset"); return B200KGE_ERR_WORKSPACE; }
+      rc = launch_gather_rows(*B.cand, f0.col_off, K, G, ldq, st);
+      if (rc) return rc;
+      T = G; ldt = ldq;
+    }
+    const int nch = tc_nchunks(nq, m);
+    if (epi_kind == EPI_BCE || epi_kind == EPI_KL) {
+      const int F = (epi_kind == EPI_BCE) ? 2 : 5;
+      P.part = (float*)ws.take((size_t)nq * nch * F * 4);
+      if (!P.part) { set_error("workspace too small for loss partials"); return B200KGE_ERR_WORKSPACE; }
+    }
+    P.nchunks = nch;
+    if (nchunks_out) *nchunks_out = nch;
+    return launch_pairwise_tc(epi_kind, passes, Qhi, Qlo, ldq, nq, T, ldt, m, K, P, st);
+  }
+
+  float* Q = (float*)ws.take((size_t)nq * ldq * 4);
+  if (!Q) { set_error("workspace too small for folded queries"); return B200KGE_ERR_WORKSPACE; }
+  int rc = launch_fold_queries(B.model, B.combine, *B.q0, *B.p, n, 0, Q, ldq, nullptr, nullptr, st);
+  if (rc) return rc;
+  if (B.q1) { rc = launch_fold_queries(B.model, 1 - B.combine, *B.q1, *B.p, n, n, Q, ldq, nullptr, nullptr, st); if (rc) return rc; }
+  const int nch = pairwise_simt_nchunks(nq, m);
+  if (epi_kind == EPI_BCE || epi_kind == EPI_KL) {
+    const int F = (epi_kind == EPI_BCE) ? 2 : 5;
+    P.part = (float*)ws.take((size_t)nq * nch * F * 4);
+    if (!P.part) { set_error("workspace too small for loss partials"); return B200KGE_ERR_WORKSPACE; }
+  }
+  P.nchunks = nch;
+  if (nchunks_out) *nchunks_out = nch;
+  return launch_pairwise_simt(epi_kind, f0.pair_op, l_norm, Q, ldq, nq, *B.cand, f0.col_off, K, P, st);
+}
+
+EpiParams empty_epi() {
+  EpiParams P;
+  memset(&P, 0, sizeof(P));
+  return P;
+}
+
+int check_1vsN_args(int model, int combine, const b200kge_rows_t* q, const b200kge_rows_t* p,
+                    const b200kge_rows_t* cand, int64_t n) {
+  if (!q || !p || !cand) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  if (combine != B200KGE_SP_ && combine != B200KGE__PO) {
+    set_error("cannot handle combine=%d", combine);   // ValueError in kge_model.py:211
+    return B200KGE_ERR_INVALID;
+  }
+  if (n < 0 || q->rows < n || p->rows < n) { set_error("operand has fewer than n=%lld rows", (long long)n); return B200KGE_ERR_INVALID; }
+  if (cand->dim != q->dim) { set_error("candidate dim %d != query entity dim %d", cand->dim, q->dim); return B200KGE_ERR_INVALID; }
+  return validate_model(model, to_rows(q), to_rows(p));
+}
+
+__global__ void unpack_triples_kernel(const int64_t* __restrict__ tri, int64_t n, int64_t* s, int64_t* p,
+                                      int64_t* o, int64_t* labels2n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int64_t a = tri[3 * i], b = tri[3 * i + 1], c = tri[3 * i + 2];
+    s[i] = a; p[i] = b; o[i] = c;
+    labels2n[i] = c;       // sp_ rows are labelled with the object      train_1vsAll.py:64-65
+    labels2n[n + i] = a;   // _po rows are labelled with the subject     train_1vsAll.py:75-76
+  }
+}
+
+}  // namespace
+}  // namespace b200kge
+
+using namespace b200kge;
+
+extern "C" {
+
+int b200kge_version(void) { return B200KGE_VERSION; }
+const char* b200kge_last_error(void) { return g_err; }
+int64_t b200kge_launch_count(int reset) {
+  int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int b200kge_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("no CUDA device available: libb200kge has no CPU fallback");
+    return B200KGE_ERR_NO_DEVICE;
+  }
+  if (major != 10) { set_error("device compute capability %d.x is not sm_100 (B200)", major); return B200KGE_ERR_NO_DEVICE; }
+  return 0;
+}
+
+size_t b200kge_workspace_bytes(int model, int64_t n, int64_t m, int32_t D, int cand_has_idx) {
+  (void)model;
+  const int64_t ldq = round_up(D, 32);
+  const int64_t nq = 2 * n;
+  size_t b = 0;
+  b += 2 * ((size_t)nq * ldq * 4 + 256);                 // Qhi/Qlo (or Q)
+  if (cand_has_idx) b += (size_t)m * ldq * 4 + 256;      // gathered candidate subset
+  int64_t nch = pairwise_simt_nchunks(nq, m);
+  if (nch < 160) nch = 160;
+  b += (size_t)nq * nch * 5 * 4 + 256;                   // loss partials
+  b += (size_t)n * 3 * 8 + (size_t)n * 5 * 8 + 2048;     // host entry: triples, s/p/o, labels, scalar
+  return b + 4096;
+}
+
+int b200kge_score_spo(int model, float l_norm, const b200kge_rows_t* s, const b200kge_rows_t* p,
+                      const b200kge_rows_t* o, int64_t n, float* out, b200kge_stream_t stream) {
+  if (!s || !p || !o || (!out && n > 0)) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  int rc = validate_model(model, to_rows(s), to_rows(p)); if (rc) return rc;
+  if ((rc = validate_norm(model, l_norm))) return rc;
+  if (s->rows < n || p->rows < n || o->rows < n) { set_error("operand has fewer than n rows"); return B200KGE_ERR_INVALID; }
+  return launch_spo(model, l_norm, to_rows(s), to_rows(p), to_rows(o), n, out, 1, (cudaStream_t)stream);
+}
+
+int b200kge_score_1vsN(int model, int combine, float l_norm, int precision,
+                       const b200kge_rows_t* q, const b200kge_rows_t* p,
+                       const b200kge_rows_t* cand, int64_t n, float* out, int64_t ldo,
+                       void* workspace, size_t workspace_bytes, b200kge_stream_t stream) {
+  int rc = check_1vsN_args(model, combine, q, p, cand, n); if (rc) return rc;
+  if ((rc = validate_norm(model, l_norm))) return rc;
+  Rows Q = to_rows(q), Pr = to_rows(p), C = to_rows(cand);
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  EpiParams P = empty_epi();
+  P.out = out; P.ldo = ldo;
+  Block B{model, combine, &Q, nullptr, &Pr, &C, n};
+  return run_block(B, l_norm, precision, EPI_STORE, P, ws, (cudaStream_t)stream, nullptr);
+}
+
+int b200kge_score_sp_po(int model, float l_norm, int precision, const b200kge_rows_t* s,
+                        const b200kge_rows_t* p, const b200kge_rows_t* o,
+                        const b200kge_rows_t* cand, int64_t n, float* out, int64_t ldo,
+                        void* workspace, size_t workspace_bytes, b200kge_stream_t stream) {
+  int rc = check_1vsN_args(model, B200KGE_SP_, s, p, cand, n); if (rc) return rc;
+  if ((rc = check_1vsN_args(model, B200KGE__PO, o, p, cand, n))) return rc;
+  if ((rc = validate_norm(model, l_norm))) return rc;
+  Rows Sr = to_rows(s), Pr = to_rows(p), Or = to_rows(o), C = to_rows(cand);
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  EpiParams P = empty_epi();
+  P.out = out; P.ldo = ldo; P.n_rows_out = n; P.col_block = cand->rows;
+  Block B{model, B200KGE_SP_, &Sr, &Or, &Pr, &C, n};
+  return run_block(B, l_norm, precision, EPI_STORE, P, ws, (cudaStream_t)stream, nullptr);
+}
+
+int b200kge_score_1vsN_loss(int model, int combine, float l_norm, int precision,
+                            const b200kge_rows_t* q, const b200kge_rows_t* p,
+                            const b200kge_rows_t* cand, int64_t n, const b200kge_labels_t* labels,
+                            int loss_kind, float offset, float* loss_out, float* row_loss_out,
+                            void* workspace, size_t workspace_bytes, b200kge_stream_t stream) {
+  int rc = check_1vsN_args(model, combine, q, p, cand, n); if (rc) return rc;
+  if ((rc = validate_norm(model, l_norm))) return rc;
+  if (!labels || (!labels->idx) == (!labels->dense)) { set_error("exactly one of labels.idx / labels.dense must be given"); return B200KGE_ERR_INVALID; }
+  if (loss_kind != B200KGE_LOSS_BCE && loss_kind != B200KGE_LOSS_KL) { set_error("unknown loss kind %d", loss_kind); return B200KGE_ERR_INVALID; }
+  if (!loss_out) { set_error("loss_out is null"); return B200KGE_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Rows Q = to_rows(q), Pr = to_rows(p), C = to_rows(cand);
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  EpiParams P = empty_epi();
+  P.label_idx = labels->idx; P.label_dense = labels->dense; P.ldl = labels->ldl;
+  P.offset = (loss_kind == B200KGE_LOSS_BCE) ? offset : 0.f;
+  Block B{model, combine, &Q, nullptr, &Pr, &C, n};
+  int nch = 0;
+  const int epi = (loss_kind == B200KGE_LOSS_BCE) ? EPI_BCE : EPI_KL;
+  rc = run_block(B, l_norm, precision, epi, P, ws, st, &nch);
+  if (rc) return rc;
+  if (n == 0 || C.rows == 0) { B2K_CUDA(cudaMemsetAsync(loss_out, 0, 4, st)); return 0; }
+  const int F = (epi == EPI_BCE) ? 2 : 5;
+  // the partial buffer is the LAST thing run_block took from the arena
+  const size_t part_bytes = (size_t)n * nch * F * 4;
+  float* part = (float*)(ws.base + (ws.off - part_bytes));
+  return launch_loss_finalize(loss_kind, part, nch, n, labels->idx, loss_out, row_loss_out, 1.0f, 0, st);
+}
+
+int b200kge_score_1vsN_rank(int model, int combine, float l_norm, int precision,
+                            const b200kge_rows_t* q, const b200kge_rows_t* p,
+                            const b200kge_rows_t* cand, int64_t n, const float* true_score,
+                            const float* filter, int64_t ldf, float rtol, float atol,
+                            int64_t* rank, int64_t* ties, void* workspace, size_t workspace_bytes,
+                            b200kge_stream_t stream) {
+  int rc = check_1vsN_args(model, combine, q, p, cand, n); if (rc) return rc;
+  if ((rc = validate_norm(model, l_norm))) return rc;
+  if (!true_score || !rank || !ties) { set_error("null rank operand"); return B200KGE_ERR_INVALID; }
+  Rows Q = to_rows(q), Pr = to_rows(p), C = to_rows(cand);
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  EpiParams P = empty_epi();
+  P.true_score = true_score; P.filter = filter; P.ldf = ldf; P.rtol = rtol; P.atol = atol;
+  P.rank = reinterpret_cast<unsigned long long*>(rank);
+  P.ties = reinterpret_cast<unsigned long long*>(ties);
+  Block B{model, combine, &Q, nullptr, &Pr, &C, n};
+  return run_block(B, l_norm, precision, EPI_RANK, P, ws, (cudaStream_t)stream, nullptr);
+}
+
+int b200kge_loss_dense(const float* scores, int64_t lds, int64_t n, int64_t m,
+                       const b200kge_labels_t* labels, int loss_kind, float offset,
+                       float* loss_out, float* row_loss_out, void* workspace,
+                       size_t workspace_bytes, b200kge_stream_t stream) {
+  if (!scores || !labels || !loss_out) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  if ((!labels->idx) == (!labels->dense)) { set_error("exactly one of labels.idx / labels.dense must be given"); return B200KGE_ERR_INVALID; }
+  if (loss_kind != B200KGE_LOSS_BCE && loss_kind != B200KGE_LOSS_KL) { set_error("unknown loss kind %d", loss_kind); return B200KGE_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0 || m == 0) { B2K_CUDA(cudaMemsetAsync(loss_out, 0, 4, st)); return 0; }
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  const int nch = loss_dense_nchunks(m);
+  const int F = (loss_kind == B200KGE_LOSS_BCE) ? 2 : 5;
+  EpiParams P = empty_epi();
+  P.label_idx = labels->idx; P.label_dense = labels->dense; P.ldl = labels->ldl;
+  P.offset = (loss_kind == B200KGE_LOSS_BCE) ? offset : 0.f;
+  P.nchunks = nch;
+  P.part = (float*)ws.take((size_t)n * nch * F * 4);
+  if (!P.part) { set_error("workspace too small for loss partials (need %zu bytes)", (size_t)n * nch * F * 4); return B200KGE_ERR_WORKSPACE; }
+  int rc = launch_loss_dense(loss_kind, scores, lds, n, m, P, st);
+  if (rc) return rc;
+  return launch_loss_finalize(loss_kind, P.part, nch, n, labels->idx, loss_out, row_loss_out, 1.0f, 0, st);
+}
+
+int b200kge_rank_dense(const float* scores, int64_t lds, int64_t n, int64_t m,
+                       const float* true_score, const float* filter, int64_t ldf, float rtol,
+                       float atol, int64_t* rank, int64_t* ties, b200kge_stream_t stream) {
+  if (!scores || !true_score || !rank || !ties) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  EpiParams P = empty_epi();
+  P.true_score = true_score; P.filter = filter; P.ldf = ldf; P.rtol = rtol; P.atol = atol;
+  P.rank = reinterpret_cast<unsigned long long*>(rank);
+  P.ties = reinterpret_cast<unsigned long long*>(ties);
+  return launch_rank_dense(scores, lds, n, m, P, (cudaStream_t)stream);
+}
+
+int b200kge_ns_score(int model, float l_norm, const b200kge_rows_t* s, const b200kge_rows_t* p,
+                     const b200kge_rows_t* o, const b200kge_rows_t* slot_table, int slot,
+                     const int64_t* neg, int64_t n, int64_t K, int with_positive, float* out,
+                     int64_t ldo, b200kge_stream_t stream) {
+  if (!s || !p || !o || !slot_table || (!neg && n * K > 0) || !out) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  if (slot < 0 || slot > 2) { set_error("slot must be 0 (S), 1 (P) or 2 (O)"); return B200KGE_ERR_INVALID; }
+  int rc = validate_model(model, to_rows(s), to_rows(p)); if (rc) return rc;
+  if ((rc = validate_norm(model, l_norm))) return rc;
+  if (slot_table->idx) { set_error("slot_table must be a plain table (idx == NULL)"); return B200KGE_ERR_INVALID; }
+  if (slot_table->dim != (slot == 1 ? p->dim : s->dim)) { set_error("slot_table width does not match the slot"); return B200KGE_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int col0 = with_positive ? 1 : 0;
+  if (with_positive) {
+    rc = launch_spo(model, l_norm, to_rows(s), to_rows(p), to_rows(o), n, out, ldo, st);
+    if (rc) return rc;
+  }
+  return launch_ns(model, l_norm, to_rows(s), to_rows(p), to_rows(o), to_rows(slot_table), slot, neg, n, K,
+                   out, ldo, col0, st);
+}
+
+int b200kge_train_1vsall_forward_host(int model, float l_norm, int precision,
+                                      const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+                                      const int64_t* triples_host, int64_t n, int loss_kind,
+                                      float offset, float* loss_host, void* workspace,
+                                      size_t workspace_bytes, b200kge_stream_t stream) {
+  if (!ent || !rel || !triples_host || !loss_host) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  if (ent->idx || rel->idx) { set_error("ent/rel must be plain tables"); return B200KGE_ERR_INVALID; }
+  int rc = validate_model(model, to_rows(ent), to_rows(rel)); if (rc) return rc;
+  if ((rc = validate_norm(model, l_norm))) return rc;
+  if (loss_kind != B200KGE_LOSS_BCE && loss_kind != B200KGE_LOSS_KL) { set_error("unknown loss kind %d", loss_kind); return B200KGE_ERR_INVALID; }
+  if (n <= 0) { *loss_host = 0.f; return 0; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  int64_t* tri = (int64_t*)ws.take((size_t)n * 3 * 8);
+  int64_t* sidx = (int64_t*)ws.take((size_t)n * 8);
+  int64_t* pidx = (int64_t*)ws.take((size_t)n * 8);
+  int64_t* oidx = (int64_t*)ws.take((size_t)n * 8);
+  int64_t* lab = (int64_t*)ws.take((size_t)n * 2 * 8);
+  float* loss_dev = (float*)ws.take(256);
+  if (!tri || !sidx || !pidx || !oidx || !lab || !loss_dev) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+  // triples.to(device)   train_1vsAll.py:59
+  B2K_CUDA(cudaMemcpyAsync(tri, triples_host, (size_t)n * 3 * 8, cudaMemcpyHostToDevice, st));
+  unpack_triples_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tri, n, sidx, pidx, oidx, lab);
+  B2K_LAUNCH_CHECK("unpack_triples_kernel");
+
+  Rows E = to_rows(ent), R = to_rows(rel);
+  Rows S = E; S.idx = sidx; S.rows = n;
+  Rows O = E; O.idx = oidx; O.rows = n;
+  Rows Pr = R; Pr.idx = pidx; Pr.rows = n;
+  const int epi = (loss_kind == B200KGE_LOSS_BCE) ? EPI_BCE : EPI_KL;
+  const int F = (epi == EPI_BCE) ? 2 : 5;
+  EpiParams P = empty_epi();
+  P.label_idx = lab;
+  P.offset = (loss_kind == B200KGE_LOSS_BCE) ? offset : 0.f;
+  const float scale = 1.0f / (float)n;       // "/ batch_size"   train_1vsAll.py:65,76
+  Folded f0 = folded_problem(model, B200KGE_SP_, E.dim, l_norm), f1 = folded_problem(model, B200KGE__PO, E.dim, l_norm);
+  if (f0.col_off == f1.col_off) {
+    // sp_ and _po rows stacked into one launch of 2n query rows against the same table
+    Block B{model, B200KGE_SP_, &S, &O, &Pr, &E, n};
+    int nch = 0;
+    rc = run_block(B, l_norm, precision, epi, P, ws, st, &nch);
+    if (rc) return rc;
+    const size_t part_bytes = (size_t)(2 * n) * nch * F * 4;
+    float* part = (float*)(ws.base + (ws.off - part_bytes));
+    rc = launch_loss_finalize(loss_kind, part, nch, 2 * n, lab, loss_dev, nullptr, scale, 0, st);
+    if (rc) return rc;
+  } else {
+    for (int dir = 0; dir < 2; ++dir) {
+      Arena w2 = ws;
+      EpiParams Pd = P;
+      Pd.label_idx = lab + dir * n;
+      Block B{model, dir, dir == 0 ? &S : &O, nullptr, &Pr, &E, n};
+      int nch = 0;
+      rc = run_block(B, l_norm, precision, epi, Pd, w2, st, &nch);
+      if (rc) return rc;
+      const size_t part_bytes = (size_t)n * nch * F * 4;
+      float* part = (float*)(w2.base + (w2.off - part_bytes));
+      rc = launch_loss_finalize(loss_kind, part, nch, n, nullptr, loss_dev, nullptr, scale, dir, st);
+      if (rc) return rc;
+    }
+  }
+  // .item()   train_1vsAll.py:66,77
+  B2K_CUDA(cudaMemcpyAsync(loss_host, loss_dev, 4, cudaMemcpyDeviceToHost, st));
+  B2K_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+// rowwise.cu — row-wise triple scoring (combine="spo") and fused negative-sample scoring.
+//
+//  * spo_kernel: one warp per triple; gathers the three rows by index and reduces the model's
+//    trilinear form / distance in registers.  Replaces KgeModel.score_spo (kge_model.py:663-680) +
+//    score_emb(combine="spo") of complex.py:34-35, distmult.py:16-17, simple.py:21-23,
+//    cp.py:21-22, rescal.py:27-35, transe.py:17-18, rotate.py:30-41.
+//  * ns_kernel: BatchNegativeSample.score (sampler.py:263-344) for the S and O slots: the CTA folds
+//    (other entity, relation) of its positive triple into q once, then each warp gathers sampled
+//    rows and reduces pair(q, row) — the gather of the sampled indexes is fused with the
+//    per-negative dot/distance; nothing of size [n*K, D] is materialised (the reference's `triple`
+//    implementation gathers 3 x [n*K, D]).  The P slot goes through spo_kernel with row divisors.
+#include "fold.cuh"
+
+namespace b200kge {
+
+namespace {
+
+struct RowsDiv {
+  Rows r;
+  int64_t div;  // logical row t reads operand row t / div
+  __device__ __forceinline__ const float* row(int64_t t) const { return r.row(div > 1 ? t / div : t); }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(256)
+spo_kernel(RowsDiv S, RowsDiv Pr, RowsDiv O, int64_t n, float l_norm, float* __restrict__ out,
+           int64_t out_ld, int64_t out_div, int64_t col0) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= n) return;
+  const float* __restrict__ s = S.row(t);
+  const float* __restrict__ p = Pr.row(t);
+  const float* __restrict__ o = O.row(t);
+  const int D = S.r.dim, h = D >> 1;
+  float acc = 0.f;
+  if constexpr (MODEL == B200KGE_COMPLEX) {
+    for (int k = lane; k < h; k += 32) {
+      const float s_re = s[k], s_im = s[k + h], p_re = p[k], p_im = p[k + h], o_re = o[k], o_im = o[k + h];
+      acc += s_re * p_re * o_re + s_im * p_re * o_im + s_re * p_im * o_im - s_im * p_im * o_re;
+    }
+  } else if constexpr (MODEL == B200KGE_DISTMULT) {
+    for (int k = lane; k < D; k += 32) acc = fmaf(s[k] * p[k], o[k], acc);
+  } else if constexpr (MODEL == B200KGE_SIMPLE) {
+    for (int k = lane; k < h; k += 32)
+      acc += 0.5f * (s[k] * p[k] * o[k + h] + s[k + h] * p[k + h] * o[k]);
+  } else if constexpr (MODEL == B200KGE_CP) {
+    for (int k = lane; k < h; k += 32) acc = fmaf(s[k] * p[k], o[k + h], acc);
+  } else if constexpr (MODEL == B200KGE_RESCAL) {
+    const int64_t dd = (int64_t)D * D;
+    for (int64_t e = lane; e < dd; e += 32) {
+      const int r = (int)(e / D), c = (int)(e - (int64_t)r * D);
+      acc = fmaf(s[r] * p[e], o[c], acc);
+    }
+  } else if constexpr (MODEL == B200KGE_TRANSE) {
+    for (int k = lane; k < D; k += 32) {
+      const float d = fabsf(((s[k] + p[k]) - o[k]) + 1e-6f);  // F.pairwise_distance eps, transe.py:18
+      if (l_norm == 1.0f) acc += d;
+      else if (l_norm == 2.0f) acc = fmaf(d, d, acc);
+      else acc += __powf(d, l_norm);
+    }
+  } else {  // ROTATE
+    for (int k = lane; k < h; k += 32) {
+      float sn, c;
+      sincosf(p[k], &sn, &c);
+      const float q_re = s[k] * c - s[k + h] * sn, q_im = s[k] * sn + s[k + h] * c;
+      const float d_re = q_re - o[k], d_im = q_im - o[k + h];
+      const float m2 = fmaf(d_im, d_im, d_re * d_re);
+      if (l_norm == 1.0f) acc += sqrtf(m2);
+      else acc += __powf(m2, 0.5f * l_norm);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if constexpr (MODEL == B200KGE_TRANSE || MODEL == B200KGE_ROTATE) {
+      if (l_norm == 1.0f) acc = -acc;
+      else if (l_norm == 2.0f) acc = -sqrtf(acc);
+      else acc = -powf(acc, 1.0f / l_norm);
+    }
+    // logical triple t lands at out[(t / out_div) * out_ld + col0 + t % out_div]
+    int64_t r = t, c = 0;
+    if (out_div > 1) { r = t / out_div; c = t - r * out_div; }
+    out[r * out_ld + col0 + c] = acc;
+  }
+}
+
+int launch_spo_div(int model, float l_norm, const RowsDiv& s, const RowsDiv& p, const RowsDiv& o,
+                   int64_t n, float* out, int64_t out_ld, int64_t out_div, int64_t col0,
+                   cudaStream_t st) {
+  if (n == 0) return 0;
+  const int wpb = 8;
+  const int64_t blocks = (n + wpb - 1) / wpb;
+  if (blocks > 2147483647LL) { set_error("too many triples"); return B200KGE_ERR_UNSUPPORTED; }
+  dim3 grid((unsigned)blocks), block(wpb * 32);
+#define B2K_SPO(M) case M: spo_kernel<M><<<grid, block, 0, st>>>(s, p, o, n, l_norm, out, out_ld, out_div, col0); break;
+  switch (model) {
+    B2K_SPO(B200KGE_COMPLEX) B2K_SPO(B200KGE_DISTMULT) B2K_SPO(B200KGE_SIMPLE) B2K_SPO(B200KGE_CP)
+    B2K_SPO(B200KGE_RESCAL) B2K_SPO(B200KGE_TRANSE) B2K_SPO(B200KGE_ROTATE)
+    default: set_error("unknown model %d", model); return B200KGE_ERR_INVALID;
+  }
+#undef B2K_SPO
+  B2K_LAUNCH_CHECK("spo_kernel");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int NS_WARPS = 4, NS_PER_BLOCK = 64;
+
+template <int MODEL>
+__global__ void __launch_bounds__(NS_WARPS * 32)
+ns_kernel(Rows A, Rows Pr, Rows table, int sp, const int64_t* __restrict__ neg, int64_t Kneg,
+          Folded f, float l_norm, float* __restrict__ out, int64_t ldo, int col0) {
+  extern __shared__ __align__(16) float sh[];  // q[K] (+ entity row for RESCAL)
+  const int64_t i = blockIdx.x;
+  const int D = A.dim, h = D >> 1, K = f.K;
+  const float* __restrict__ a = A.row(i);
+  const float* __restrict__ p = Pr.row(i);
+  float* q = sh;
+  if constexpr (MODEL == B200KGE_RESCAL) {
+    float* sa = sh + K;
+    for (int k = threadIdx.x; k < D; k += blockDim.x) sa[k] = a[k];
+    __syncthreads();
+    fold_rescal_block(sp != 0, sa, p, D, [&](int k, float v) { q[k] = v; });
+  } else {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) q[k] = fold_element<MODEL>(sp != 0, a, p, k, h);
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t k0 = (int64_t)blockIdx.y * NS_PER_BLOCK;
+  const int hk = K >> 1;
+  for (int64_t kk = k0 + warp; kk < k0 + NS_PER_BLOCK && kk < Kneg; kk += NS_WARPS) {
+    const int64_t e = neg[i * Kneg + kk];
+    const float* __restrict__ t = table.base + e * table.ld + f.col_off;
+    float acc = 0.f;
+    if (f.pair_op == PAIR_DOT) {
+      for (int k = lane; k < K; k += 32) acc = fmaf(q[k], t[k], acc);
+    } else if (f.pair_op == PAIR_L1) {
+      for (int k = lane; k < K; k += 32) acc += fabsf(q[k] - t[k]);
+    } else if (f.pair_op == PAIR_L2) {
+      for (int k = lane; k < K; k += 32) { const float d = q[k] - t[k]; acc = fmaf(d, d, acc); }
+    } else if (f.pair_op == PAIR_LP) {
+      for (int k = lane; k < K; k += 32) acc += __powf(fabsf(q[k] - t[k]), l_norm);
+    } else {
+      for (int k = lane; k < hk; k += 32) {
+        const float d_re = q[k] - t[k], d_im = q[k + hk] - t[k + hk];
+        const float m2 = fmaf(d_im, d_im, d_re * d_re);
+        acc += (f.pair_op == PAIR_CMOD_L1) ? sqrtf(m2) : __powf(m2, 0.5f * l_norm);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (f.pair_op == PAIR_L1 || f.pair_op == PAIR_CMOD_L1) acc = -acc;
+      else if (f.pair_op == PAIR_L2) acc = -sqrtf(acc);
+      else if (f.pair_op != PAIR_DOT) acc = -powf(acc, 1.0f / l_norm);
+      out[i * ldo + col0 + kk] = acc;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_spo(int model, float l_norm, const Rows& s, const Rows& p, const Rows& o, int64_t n,
+               float* out, int64_t out_stride, cudaStream_t st) {
+  RowsDiv S{s, 1}, P{p, 1}, O{o, 1};
+  return launch_spo_div(model, l_norm, S, P, O, n, out, out_stride, 1, 0, st);
+}
+
+int launch_ns(int model, float l_norm, const Rows& s, const Rows& p, const Rows& o,
+              const Rows& table, int slot, const int64_t* neg, int64_t n, int64_t K, float* out,
+              int64_t ldo, int col0, cudaStream_t st) {
+  if (n == 0 || K == 0) return 0;
+  if (slot == 1) {
+    // P slot: score(s_i, neg[i,k], o_i) for every (i,k) through the row-wise kernel: logical triple
+    // t = i*K + k reads s/o row t/K and relation row neg[t]  (num_samples.p defaults to 0, so this
+    // path is rare; config-default.yaml:346-349).
+    Rows pneg = table; pneg.idx = neg; pneg.rows = n * K;
+    RowsDiv S{s, K}, P{pneg, 1}, O{o, K};
+    return launch_spo_div(model, l_norm, S, P, O, n * K, out, ldo, K, col0, st);
+  }
+  const int sp = (slot == 2) ? 1 : 0;  // O slot: fold (s,p) and score against sampled objects
+  const Rows& a = sp ? s : o;
+  Folded f = folded_problem(model, sp ? B200KGE_SP_ : B200KGE__PO, a.dim, l_norm);
+  size_t smem = (size_t)f.K * sizeof(float) + (model == B200KGE_RESCAL ? (size_t)a.dim * sizeof(float) : 0);
+  const int64_t by = (K + NS_PER_BLOCK - 1) / NS_PER_BLOCK;
+  if (by > 65535) { set_error("too many negatives per row (%lld)", (long long)K); return B200KGE_ERR_UNSUPPORTED; }
+  dim3 grid((unsigned)n, (unsigned)by), block(NS_WARPS * 32);
+#define B2K_NS(M) case M: ns_kernel<M><<<grid, block, smem, st>>>(a, p, table, sp, neg, K, f, l_norm, out, ldo, col0); break;
+  switch (model) {
+    B2K_NS(B200KGE_COMPLEX) B2K_NS(B200KGE_DISTMULT) B2K_NS(B200KGE_SIMPLE) B2K_NS(B200KGE_CP)
+    B2K_NS(B200KGE_RESCAL) B2K_NS(B200KGE_TRANSE) B2K_NS(B200KGE_ROTATE)
+    default: set_error("unknown model %d", model); return B200KGE_ERR_INVALID;
+  }
+#undef B2K_NS
+  B2K_LAUNCH_CHECK("ns_kernel");
+  return 0;
+}
+
+}  // namespace b200kge

@@ -1,0 +1,289 @@
+"""Tensor-level façade over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+torch is used for device memory (caching allocator), streams and nothing else: every number is
+produced by libb200kge's hand-written sm_100a kernels.  All functions raise on CPU tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import LOSS, MODELS, PREC, Labels, Rows, SP_, _PO
+
+S, P, O = 0, 1, 2
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "kge_b200 runs on CUDA (sm_100) tensors only; there is no CPU path "
+                f"(got a tensor on {t.device})"
+            )
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32 embeddings, got {t.dtype}")
+    if t.dim() != 2:
+        raise ValueError(f"expected a 2-D embedding matrix, got shape {tuple(t.shape)}")
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def _i64(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dim() != 1:
+        t = t.reshape(-1)
+    if t.dtype != torch.int64 or not t.is_contiguous():
+        t = t.long().contiguous()  # lookup_embedder.py:97 does indexes.long()
+    return t
+
+
+class _Keep:
+    """Keeps tensors alive for the duration of a call (the C side borrows raw pointers)."""
+
+    def __init__(self):
+        self.refs = []
+
+    def rows(self, base: torch.Tensor, idx: Optional[torch.Tensor] = None) -> Rows:
+        base = _f32(base)
+        idx = _i64(idx)
+        self.refs += [base, idx]
+        r = Rows()
+        r.base = base.data_ptr()
+        r.idx = idx.data_ptr() if idx is not None else None
+        r.rows = idx.numel() if idx is not None else base.shape[0]
+        r.ld = base.stride(0) if base.shape[0] > 1 else max(base.shape[1], base.stride(0))
+        r.dim = base.shape[1]
+        return r
+
+
+def _stream(dev) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _workspace(model_id: int, n: int, m: int, D: int, has_idx: bool, dev) -> torch.Tensor:
+    nbytes = _lib.load().b200kge_workspace_bytes(model_id, n, m, D, 1 if has_idx else 0)
+    # torch's caching allocator raises torch.cuda.OutOfMemoryError ("CUDA out of memory") on failure
+    return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+
+def device_ok() -> bool:
+    return _lib.load().b200kge_device_ok() == 0
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(_lib.load().b200kge_launch_count(1 if reset else 0))
+
+
+# ------------------------------------------------------------------------------------------------
+def score_spo(model: str, ent_s, rel, ent_o, s=None, p=None, o=None, l_norm: float = 1.0):
+    """Row-wise scores.  With indexes: tables + gather fused (KgeModel.score_spo); without:
+    already-gathered embeddings (RelationalScorer.score_emb(..., "spo"))."""
+    _require_cuda(ent_s, rel, ent_o)
+    lib, k = _lib.load(), _Keep()
+    rs, rp, ro = k.rows(ent_s, s), k.rows(rel, p), k.rows(ent_o, o)
+    n = int(rs.rows)
+    if rp.rows != n or ro.rows != n:
+        raise ValueError("spo scoring needs the same number of s, p and o rows")
+    out = torch.empty(n, dtype=torch.float32, device=ent_s.device)
+    _lib.check(lib.b200kge_score_spo(MODELS[model], l_norm, C.byref(rs), C.byref(rp), C.byref(ro), n,
+                                     out.data_ptr(), _stream(ent_s.device)))
+    return out
+
+
+def score_1vsN(model: str, combine: str, q_tab, rel, cand_tab, q=None, p=None, cand=None,
+               l_norm: float = 1.0, precision: str = "auto", out: Optional[torch.Tensor] = None):
+    """[n, m] scores of n (entity, relation) rows against m candidate entities.
+
+    combine "sp_": q rows are subjects, candidates are objects; "_po": q rows are objects,
+    candidates are subjects (kge_model.py:164-181)."""
+    if combine not in ("sp_", "_po"):
+        raise ValueError('cannot handle combine="{}"'.format(combine))
+    _require_cuda(q_tab, rel, cand_tab)
+    lib, k = _lib.load(), _Keep()
+    rq, rp, rc = k.rows(q_tab, q), k.rows(rel, p), k.rows(cand_tab, cand)
+    n, m = int(rq.rows), int(rc.rows)
+    if rp.rows != n:
+        raise ValueError("need as many relation rows as entity rows")
+    dev = q_tab.device
+    if out is None:
+        out = torch.empty((n, m), dtype=torch.float32, device=dev)
+    ws = _workspace(MODELS[model], n, m, rq.dim, cand is not None, dev)
+    _lib.check(lib.b200kge_score_1vsN(MODELS[model], SP_ if combine == "sp_" else _PO, l_norm,
+                                      PREC[precision], C.byref(rq), C.byref(rp), C.byref(rc), n,
+                                      out.data_ptr(), out.stride(0), ws.data_ptr(), ws.numel(),
+                                      _stream(dev)))
+    return out
+
+
+def score_sp_po(model: str, ent, rel, s, p, o, entity_subset=None, l_norm: float = 1.0,
+                precision: str = "auto"):
+    """[n, 2m] = [score_sp | score_po] in one launch sequence (kge_model.py:749-789)."""
+    _require_cuda(ent, rel)
+    lib, k = _lib.load(), _Keep()
+    rs, rp, ro = k.rows(ent, s), k.rows(rel, p), k.rows(ent, o)
+    rc = k.rows(ent, entity_subset)
+    n, m = int(rs.rows), int(rc.rows)
+    dev = ent.device
+    out = torch.empty((n, 2 * m), dtype=torch.float32, device=dev)
+    ws = _workspace(MODELS[model], n, m, rs.dim, entity_subset is not None, dev)
+    _lib.check(lib.b200kge_score_sp_po(MODELS[model], l_norm, PREC[precision], C.byref(rs), C.byref(rp),
+                                       C.byref(ro), C.byref(rc), n, out.data_ptr(), out.stride(0),
+                                       ws.data_ptr(), ws.numel(), _stream(dev)))
+    return out
+
+
+def _labels(k: _Keep, labels: torch.Tensor) -> Labels:
+    lab = Labels()
+    if labels.dim() == 1:
+        li = _i64(labels)
+        k.refs.append(li)
+        lab.idx, lab.dense, lab.ldl = li.data_ptr(), None, 0
+    else:
+        ld = labels if (labels.dtype == torch.float32 and labels.stride(1) == 1) else labels.float().contiguous()
+        k.refs.append(ld)
+        lab.idx, lab.dense, lab.ldl = None, ld.data_ptr(), ld.stride(0)
+    return lab
+
+
+def score_1vsN_loss(model: str, combine: str, q_tab, rel, cand_tab, labels, q=None, p=None, cand=None,
+                    loss: str = "bce", offset: float = 0.0, l_norm: float = 1.0, precision: str = "auto",
+                    return_rows: bool = False):
+    """Fused scoring + KgeLoss (sum reduction): returns a 0-d tensor (and per-row terms)."""
+    _require_cuda(q_tab, rel, cand_tab, labels)
+    lib, k = _lib.load(), _Keep()
+    rq, rp, rc = k.rows(q_tab, q), k.rows(rel, p), k.rows(cand_tab, cand)
+    n, m = int(rq.rows), int(rc.rows)
+    dev = q_tab.device
+    lab = _labels(k, labels)
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    rows = torch.empty(n, dtype=torch.float32, device=dev) if return_rows else None
+    ws = _workspace(MODELS[model], n, m, rq.dim, cand is not None, dev)
+    _lib.check(lib.b200kge_score_1vsN_loss(
+        MODELS[model], SP_ if combine == "sp_" else _PO, l_norm, PREC[precision], C.byref(rq), C.byref(rp),
+        C.byref(rc), n, C.byref(lab), LOSS[loss], offset, out.data_ptr(),
+        rows.data_ptr() if rows is not None else None, ws.data_ptr(), ws.numel(), _stream(dev)))
+    return (out, rows) if return_rows else out
+
+
+def score_1vsN_rank(model: str, combine: str, q_tab, rel, cand_tab, true_scores, q=None, p=None, cand=None,
+                    filter_labels=None, rtol: float = 1e-4, atol: float = 1e-5, l_norm: float = 1.0,
+                    precision: str = "auto", rank=None, ties=None):
+    """Fused scoring + rank/tie counting for one chunk of candidates; accumulates into rank/ties."""
+    _require_cuda(q_tab, rel, cand_tab, true_scores, filter_labels)
+    lib, k = _lib.load(), _Keep()
+    rq, rp, rc = k.rows(q_tab, q), k.rows(rel, p), k.rows(cand_tab, cand)
+    n, m = int(rq.rows), int(rc.rows)
+    dev = q_tab.device
+    t = true_scores.reshape(-1).float().contiguous()
+    if rank is None:
+        rank = torch.zeros(n, dtype=torch.int64, device=dev)
+    if ties is None:
+        ties = torch.zeros(n, dtype=torch.int64, device=dev)
+    f = None
+    if filter_labels is not None:
+        f = filter_labels if (filter_labels.dtype == torch.float32 and filter_labels.stride(1) == 1) \
+            else filter_labels.float().contiguous()
+    ws = _workspace(MODELS[model], n, m, rq.dim, cand is not None, dev)
+    _lib.check(lib.b200kge_score_1vsN_rank(
+        MODELS[model], SP_ if combine == "sp_" else _PO, l_norm, PREC[precision], C.byref(rq), C.byref(rp),
+        C.byref(rc), n, t.data_ptr(), f.data_ptr() if f is not None else None,
+        f.stride(0) if f is not None else 0, rtol, atol, rank.data_ptr(), ties.data_ptr(), ws.data_ptr(),
+        ws.numel(), _stream(dev)))
+    return rank, ties
+
+
+def loss_dense(scores, labels, loss: str = "bce", offset: float = 0.0, return_rows: bool = False):
+    """KgeLoss (sum) on a dense score matrix (loss.py:153-159 / :198-213)."""
+    _require_cuda(scores, labels)
+    lib, k = _lib.load(), _Keep()
+    x = scores if (scores.dtype == torch.float32 and scores.stride(1) == 1) else scores.float().contiguous()
+    n, m = x.shape
+    lab = _labels(k, labels)
+    dev = x.device
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    rows = torch.empty(n, dtype=torch.float32, device=dev) if return_rows else None
+    nbytes = n * ((m + 4095) // 4096) * 5 * 4 + 4096
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.b200kge_loss_dense(x.data_ptr(), x.stride(0), n, m, C.byref(lab), LOSS[loss], offset,
+                                      out.data_ptr(), rows.data_ptr() if rows is not None else None,
+                                      ws.data_ptr(), ws.numel(), _stream(dev)))
+    return (out, rows) if return_rows else out
+
+
+def rank_dense(scores, true_scores, filter_labels=None, rtol: float = 1e-4, atol: float = 1e-5,
+               rank=None, ties=None):
+    """_get_ranks_and_num_ties (+ optional filter subtraction) on dense scores; integer, bit-exact."""
+    _require_cuda(scores, true_scores, filter_labels)
+    lib = _lib.load()
+    x = scores if (scores.dtype == torch.float32 and scores.stride(1) == 1) else scores.float().contiguous()
+    n, m = x.shape
+    dev = x.device
+    t = true_scores.reshape(-1).float().contiguous()
+    if rank is None:
+        rank = torch.zeros(n, dtype=torch.int64, device=dev)
+    if ties is None:
+        ties = torch.zeros(n, dtype=torch.int64, device=dev)
+    f = None
+    if filter_labels is not None:
+        f = filter_labels if (filter_labels.dtype == torch.float32 and filter_labels.stride(1) == 1) \
+            else filter_labels.float().contiguous()
+    _lib.check(lib.b200kge_rank_dense(x.data_ptr(), x.stride(0), n, m, t.data_ptr(),
+                                      f.data_ptr() if f is not None else None,
+                                      f.stride(0) if f is not None else 0, rtol, atol, rank.data_ptr(),
+                                      ties.data_ptr(), _stream(dev)))
+    return rank, ties
+
+
+def ns_score(model: str, ent, rel, triples, negatives, slot: int, with_positive: bool = False,
+             l_norm: float = 1.0):
+    """[n, K] (or [n, 1+K] with the positive in column 0) negative-sample scores."""
+    _require_cuda(ent, rel, triples, negatives)
+    lib, k = _lib.load(), _Keep()
+    tri = triples.long()
+    rs, rp, ro = k.rows(ent, tri[:, S].contiguous()), k.rows(rel, tri[:, P].contiguous()), \
+        k.rows(ent, tri[:, O].contiguous())
+    neg = negatives.long().contiguous()
+    n, K = neg.shape
+    table = k.rows(rel if slot == P else ent)
+    dev = ent.device
+    out = torch.empty((n, K + (1 if with_positive else 0)), dtype=torch.float32, device=dev)
+    _lib.check(lib.b200kge_ns_score(MODELS[model], l_norm, C.byref(rs), C.byref(rp), C.byref(ro),
+                                    C.byref(table), slot, neg.data_ptr(), n, K, 1 if with_positive else 0,
+                                    out.data_ptr(), out.stride(0), _stream(dev)))
+    return out
+
+
+class HostStep:
+    """End-to-end 1vsAll forward step with HOST buffers (pinned in, scalar out): the call a
+    training loop makes per batch — triples.to(device) ... loss.item() (train_1vsAll.py:59-77)."""
+
+    def __init__(self, model: str, ent: torch.Tensor, rel: torch.Tensor, max_n: int, loss: str = "bce",
+                 offset: float = 0.0, l_norm: float = 1.0, precision: str = "auto"):
+        _require_cuda(ent, rel)
+        self.model, self.loss, self.offset, self.l_norm, self.precision = model, loss, offset, l_norm, precision
+        self.ent, self.rel = _f32(ent), _f32(rel)
+        self.k = _Keep()
+        self.re, self.rr = self.k.rows(self.ent), self.k.rows(self.rel)
+        self.ws = _workspace(MODELS[model], max_n, ent.shape[0], ent.shape[1], False, ent.device)
+        self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.h2d_bytes = 0
+        self.d2h_bytes = 4
+
+    def __call__(self, triples_host: torch.Tensor) -> float:
+        if triples_host.is_cuda or triples_host.dtype != torch.int64 or not triples_host.is_contiguous():
+            raise ValueError("triples_host must be a contiguous int64 CPU tensor [n,3]")
+        n = triples_host.shape[0]
+        self.h2d_bytes = n * 3 * 8
+        _lib.check(_lib.load().b200kge_train_1vsall_forward_host(
+            MODELS[self.model], self.l_norm, PREC[self.precision], C.byref(self.re), C.byref(self.rr),
+            triples_host.data_ptr(), n, LOSS[self.loss], self.offset, self.loss_host.data_ptr(),
+            self.ws.data_ptr(), self.ws.numel(), _stream(self.ent.device)))
+        return float(self.loss_host[0])
