@@ -104,6 +104,12 @@ int b200kge_device_ok(void);
  * (bench.py reports it as gpu_launches). */
 int64_t b200kge_launch_count(int reset);
 
+/* Profiling aid (bench.py): when enabled, the dominant pairwise kernel of every 1-vs-N call on this
+ * thread is bracketed by CUDA events recorded on the stream it is launched on;
+ * b200kge_profile_last_ms synchronises on the closing event and returns that kernel's duration. */
+int b200kge_profile_enable(int on);
+int b200kge_profile_last_ms(float* ms);
+
 /* Bytes of device workspace sufficient for any call below with n query rows (per direction), m
  * candidate rows and entity width D.  cand_has_idx != 0 reserves room to gather an index subset
  * of candidates for the tensor-core path. */
@@ -184,13 +190,21 @@ int b200kge_ns_score(int model, float l_norm, const b200kge_rows_t* s, const b20
                      const int64_t* neg, int64_t n, int64_t K, int with_positive, float* out,
                      int64_t ldo, b200kge_stream_t stream);
 
-/* Host-buffer entry point (end-to-end measurement and simple embedding use) --------------------
- * One 1vsAll forward step (train_1vsAll.py:48-82) for a batch of triples held in HOST memory:
- * copies triples_host [n,3] int64 to the device, runs fused score_sp+loss and score_po+loss
- * against the whole entity table, copies the scalar
- *     (loss(score_sp, o) + loss(score_po, s)) / n
- * back to *loss_host and synchronises the stream.  `ent`/`rel` are the device-resident tables
- * (idx must be NULL). */
+/* One whole 1vsAll forward step (train_1vsAll.py:48-82) for a batch of triples [n,3] (int64,
+ * row-major s,p,o): fused score_sp+loss and score_po+loss against the whole entity table, both
+ * directions stacked into one launch of 2n query rows where the model allows it.  loss_out[0]
+ * (device) receives  (loss(score_sp, o) + loss(score_po, s)) / n.  `ent`/`rel` are the
+ * device-resident tables (idx must be NULL). */
+int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
+                                 const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+                                 const int64_t* triples, int64_t n, int loss_kind, float offset,
+                                 float* loss_out, void* workspace, size_t workspace_bytes,
+                                 b200kge_stream_t stream);
+
+/* Host-buffer form of the same step (end-to-end measurement, embedding in a host-side loop):
+ * copies triples_host [n,3] to the device (triples.to(device), train_1vsAll.py:59), runs
+ * b200kge_train_1vsall_forward, copies the scalar back to *loss_host (.item(), :66,77) and
+ * synchronises the stream. */
 int b200kge_train_1vsall_forward_host(int model, float l_norm, int precision,
                                       const b200kge_rows_t* ent, const b200kge_rows_t* rel,
                                       const int64_t* triples_host, int64_t n, int loss_kind,

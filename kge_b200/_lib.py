@@ -35,6 +35,8 @@ SIGNATURES = {
     "b200kge_last_error": (C.c_char_p, []),
     "b200kge_device_ok": (C.c_int, []),
     "b200kge_launch_count": (C.c_int64, [C.c_int]),
+    "b200kge_profile_enable": (C.c_int, [C.c_int]),
+    "b200kge_profile_last_ms": (C.c_int, [C.POINTER(C.c_float)]),
     "b200kge_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int64, C.c_int32, C.c_int]),
     "b200kge_score_spo": (C.c_int, [C.c_int, C.c_float, _RP, _RP, _RP, C.c_int64, C.c_void_p, C.c_void_p]),
     "b200kge_score_1vsN": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_int, _RP, _RP, _RP, C.c_int64,
@@ -53,6 +55,9 @@ SIGNATURES = {
                                      C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200kge_ns_score": (C.c_int, [C.c_int, C.c_float, _RP, _RP, _RP, _RP, C.c_int, C.c_void_p, C.c_int64,
                                    C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "b200kge_train_1vsall_forward": (C.c_int, [C.c_int, C.c_float, C.c_int, _RP, _RP, C.c_void_p,
+                                               C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                               C.c_size_t, C.c_void_p]),
     "b200kge_train_1vsall_forward_host": (C.c_int, [C.c_int, C.c_float, C.c_int, _RP, _RP, C.c_void_p,
                                                     C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                                     C.c_size_t, C.c_void_p]),

@@ -26,6 +26,21 @@ int check_cuda(cudaError_t e, const char* what) {
   return B200KGE_ERR_CUDA;
 }
 
+static thread_local int g_prof_on = 0;
+static thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static thread_local int g_prof_valid = 0;
+
+void profile_begin(cudaStream_t st) {
+  if (!g_prof_on) return;
+  if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+  cudaEventRecord(g_ev0, st);
+}
+void profile_end(cudaStream_t st) {
+  if (!g_prof_on || !g_ev0) return;
+  cudaEventRecord(g_ev1, st);
+  g_prof_valid = 1;
+}
+
 namespace {
 
 // bump allocator over the caller's workspace
@@ -201,6 +216,15 @@ int64_t b200kge_launch_count(int reset) {
   return v;
 }
 
+int b200kge_profile_enable(int on) { g_prof_on = on; g_prof_valid = 0; return 0; }
+int b200kge_profile_last_ms(float* ms) {
+  if (!ms) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  if (!g_prof_valid) { set_error("no profiled kernel yet"); return B200KGE_ERR_INVALID; }
+  B2K_CUDA(cudaEventSynchronize(g_ev1));
+  B2K_CUDA(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+  return 0;
+}
+
 int b200kge_device_ok(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||
@@ -367,29 +391,25 @@ int b200kge_ns_score(int model, float l_norm, const b200kge_rows_t* s, const b20
                    out, ldo, col0, st);
 }
 
-int b200kge_train_1vsall_forward_host(int model, float l_norm, int precision,
-                                      const b200kge_rows_t* ent, const b200kge_rows_t* rel,
-                                      const int64_t* triples_host, int64_t n, int loss_kind,
-                                      float offset, float* loss_host, void* workspace,
-                                      size_t workspace_bytes, b200kge_stream_t stream) {
-  if (!ent || !rel || !triples_host || !loss_host) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
+                                 const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+                                 const int64_t* triples, int64_t n, int loss_kind, float offset,
+                                 float* loss_out, void* workspace, size_t workspace_bytes,
+                                 b200kge_stream_t stream) {
+  if (!ent || !rel || !triples || !loss_out) { set_error("null operand"); return B200KGE_ERR_INVALID; }
   if (ent->idx || rel->idx) { set_error("ent/rel must be plain tables"); return B200KGE_ERR_INVALID; }
   int rc = validate_model(model, to_rows(ent), to_rows(rel)); if (rc) return rc;
   if ((rc = validate_norm(model, l_norm))) return rc;
   if (loss_kind != B200KGE_LOSS_BCE && loss_kind != B200KGE_LOSS_KL) { set_error("unknown loss kind %d", loss_kind); return B200KGE_ERR_INVALID; }
-  if (n <= 0) { *loss_host = 0.f; return 0; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) { B2K_CUDA(cudaMemsetAsync(loss_out, 0, 4, st)); return 0; }
   Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
-  int64_t* tri = (int64_t*)ws.take((size_t)n * 3 * 8);
   int64_t* sidx = (int64_t*)ws.take((size_t)n * 8);
   int64_t* pidx = (int64_t*)ws.take((size_t)n * 8);
   int64_t* oidx = (int64_t*)ws.take((size_t)n * 8);
   int64_t* lab = (int64_t*)ws.take((size_t)n * 2 * 8);
-  float* loss_dev = (float*)ws.take(256);
-  if (!tri || !sidx || !pidx || !oidx || !lab || !loss_dev) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
-  // triples.to(device)   train_1vsAll.py:59
-  B2K_CUDA(cudaMemcpyAsync(tri, triples_host, (size_t)n * 3 * 8, cudaMemcpyHostToDevice, st));
-  unpack_triples_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tri, n, sidx, pidx, oidx, lab);
+  if (!sidx || !pidx || !oidx || !lab) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+  unpack_triples_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(triples, n, sidx, pidx, oidx, lab);
   B2K_LAUNCH_CHECK("unpack_triples_kernel");
 
   Rows E = to_rows(ent), R = to_rows(rel);
@@ -411,23 +431,42 @@ int b200kge_train_1vsall_forward_host(int model, float l_norm, int precision,
     if (rc) return rc;
     const size_t part_bytes = (size_t)(2 * n) * nch * F * 4;
     float* part = (float*)(ws.base + (ws.off - part_bytes));
-    rc = launch_loss_finalize(loss_kind, part, nch, 2 * n, lab, loss_dev, nullptr, scale, 0, st);
-    if (rc) return rc;
-  } else {
-    for (int dir = 0; dir < 2; ++dir) {
-      Arena w2 = ws;
-      EpiParams Pd = P;
-      Pd.label_idx = lab + dir * n;
-      Block B{model, dir, dir == 0 ? &S : &O, nullptr, &Pr, &E, n};
-      int nch = 0;
-      rc = run_block(B, l_norm, precision, epi, Pd, w2, st, &nch);
-      if (rc) return rc;
-      const size_t part_bytes = (size_t)n * nch * F * 4;
-      float* part = (float*)(w2.base + (w2.off - part_bytes));
-      rc = launch_loss_finalize(loss_kind, part, nch, n, nullptr, loss_dev, nullptr, scale, dir, st);
-      if (rc) return rc;
-    }
+    return launch_loss_finalize(loss_kind, part, nch, 2 * n, lab, loss_out, nullptr, scale, 0, st);
   }
+  for (int dir = 0; dir < 2; ++dir) {   // CP: the two directions read different table columns
+    Arena w2 = ws;
+    EpiParams Pd = P;
+    Pd.label_idx = lab + dir * n;
+    Block B{model, dir, dir == 0 ? &S : &O, nullptr, &Pr, &E, n};
+    int nch = 0;
+    rc = run_block(B, l_norm, precision, epi, Pd, w2, st, &nch);
+    if (rc) return rc;
+    const size_t part_bytes = (size_t)n * nch * F * 4;
+    float* part = (float*)(w2.base + (w2.off - part_bytes));
+    rc = launch_loss_finalize(loss_kind, part, nch, n, nullptr, loss_out, nullptr, scale, dir, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int b200kge_train_1vsall_forward_host(int model, float l_norm, int precision,
+                                      const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+                                      const int64_t* triples_host, int64_t n, int loss_kind,
+                                      float offset, float* loss_host, void* workspace,
+                                      size_t workspace_bytes, b200kge_stream_t stream) {
+  if (!triples_host || !loss_host) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  if (n <= 0) { *loss_host = 0.f; return 0; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  int64_t* tri = (int64_t*)ws.take((size_t)n * 3 * 8);
+  float* loss_dev = (float*)ws.take(256);
+  if (!tri || !loss_dev) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+  // triples.to(device)   train_1vsAll.py:59
+  B2K_CUDA(cudaMemcpyAsync(tri, triples_host, (size_t)n * 3 * 8, cudaMemcpyHostToDevice, st));
+  size_t used = (ws.off + 255) & ~size_t(255);
+  int rc = b200kge_train_1vsall_forward(model, l_norm, precision, ent, rel, tri, n, loss_kind, offset, loss_dev,
+                                        ws.base + used, workspace_bytes - used, stream);
+  if (rc) return rc;
   // .item()   train_1vsAll.py:66,77
   B2K_CUDA(cudaMemcpyAsync(loss_host, loss_dev, 4, cudaMemcpyDeviceToHost, st));
   B2K_CUDA(cudaStreamSynchronize(st));

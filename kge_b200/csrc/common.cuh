@@ -12,6 +12,9 @@ namespace b200kge {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_cuda(cudaError_t e, const char* what);
+// profiling brackets around the dominant kernel (no-ops unless b200kge_profile_enable(1))
+void profile_begin(cudaStream_t st);
+void profile_end(cudaStream_t st);
 
 #define B2K_CUDA(expr)                                             \
   do {                                                             \

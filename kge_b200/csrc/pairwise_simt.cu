@@ -193,8 +193,10 @@ template <int PAIR, int EPI>
 int launch_pe(bool vec, dim3 grid, cudaStream_t st, const float* Q, int64_t ldq, int64_t nq,
               const Rows& cand, int col_off, int K, float p, const EpiParams& P) {
   const int col_tiles = (int)((cand.rows + BN - 1) / BN);
+  profile_begin(st);
   if (vec) pairwise_simt_kernel<PAIR, EPI, true><<<grid, NT, 0, st>>>(Q, ldq, nq, cand, col_off, K, p, col_tiles, P);
   else     pairwise_simt_kernel<PAIR, EPI, false><<<grid, NT, 0, st>>>(Q, ldq, nq, cand, col_off, K, p, col_tiles, P);
+  profile_end(st);
   B2K_LAUNCH_CHECK("pairwise_simt_kernel");
   return 0;
 }

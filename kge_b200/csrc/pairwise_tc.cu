@@ -326,6 +326,7 @@ template <int EPI>
 int launch_e(int passes, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const TcParams& prm,
              int grid, cudaStream_t st) {
   cudaError_t e;
+  profile_begin(st);
   if (passes == 3) {
     e = cudaFuncSetAttribute(pairwise_tc_kernel<EPI, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pairwise_tc_kernel)");
@@ -335,6 +336,7 @@ int launch_e(int passes, const CUtensorMap& a, const CUtensorMap& b, const CUten
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pairwise_tc_kernel)");
     pairwise_tc_kernel<EPI, 1><<<grid, NTHREADS, SMEM_BYTES, st>>>(a, b, c, prm);
   }
+  profile_end(st);
   B2K_LAUNCH_CHECK("pairwise_tc_kernel");
   return 0;
 }

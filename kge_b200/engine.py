@@ -82,6 +82,16 @@ def launch_count(reset: bool = False) -> int:
     return int(_lib.load().b200kge_launch_count(1 if reset else 0))
 
 
+def profile_enable(on: bool = True) -> None:
+    _lib.load().b200kge_profile_enable(1 if on else 0)
+
+
+def profile_last_ms() -> float:
+    ms = C.c_float(0.0)
+    _lib.check(_lib.load().b200kge_profile_last_ms(C.byref(ms)))
+    return float(ms.value)
+
+
 # ------------------------------------------------------------------------------------------------
 def score_spo(model: str, ent_s, rel, ent_o, s=None, p=None, o=None, l_norm: float = 1.0):
     """Row-wise scores.  With indexes: tables + gather fused (KgeModel.score_spo); without:
@@ -258,6 +268,25 @@ def ns_score(model: str, ent, rel, triples, negatives, slot: int, with_positive:
     _lib.check(lib.b200kge_ns_score(MODELS[model], l_norm, C.byref(rs), C.byref(rp), C.byref(ro),
                                     C.byref(table), slot, neg.data_ptr(), n, K, 1 if with_positive else 0,
                                     out.data_ptr(), out.stride(0), _stream(dev)))
+    return out
+
+
+def train_1vsall_forward(model: str, ent, rel, triples, loss: str = "bce", offset: float = 0.0,
+                         l_norm: float = 1.0, precision: str = "auto", out=None, workspace=None):
+    """One fused 1vsAll forward step for device-resident triples [n,3]; returns the 0-d loss
+    (loss(score_sp,o) + loss(score_po,s)) / n  (train_1vsAll.py:48-82)."""
+    _require_cuda(ent, rel, triples)
+    lib, k = _lib.load(), _Keep()
+    re_, rr = k.rows(ent), k.rows(rel)
+    tri = triples if (triples.dtype == torch.int64 and triples.is_contiguous()) else triples.long().contiguous()
+    n = tri.shape[0]
+    dev = ent.device
+    if out is None:
+        out = torch.empty((), dtype=torch.float32, device=dev)
+    ws = workspace if workspace is not None else _workspace(MODELS[model], n, ent.shape[0], ent.shape[1], False, dev)
+    _lib.check(lib.b200kge_train_1vsall_forward(
+        MODELS[model], l_norm, PREC[precision], C.byref(re_), C.byref(rr), tri.data_ptr(), n, LOSS[loss],
+        offset, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
     return out
 
 
