@@ -19,10 +19,14 @@ namespace b200kge {
 __device__ __forceinline__ void store_q(float* Q, float* Qhi, float* Qlo, int64_t off, float v) {
   if (Q) Q[off] = v;
   if (Qhi) {
-    // tf32-exact hi/lo split: hi keeps the top 11 significand bits (truncation), lo is the exact
-    // remainder, itself truncated to tf32 so that the tensor core sees exactly these values.
+    // tf32 hi/lo split: hi = truncation to tf32 (what the tensor core does to a raw fp32 operand:
+    // it ignores the low 13 mantissa bits — verified on B200, profiles/r1_notes.md), lo = the exact
+    // remainder rounded-to-nearest to tf32 (halves the dominant error term vs letting the
+    // hardware truncate it).
     float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-    float lo = __uint_as_float(__float_as_uint(v - hi) & 0xFFFFE000u);
+    uint32_t lo_bits;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo_bits) : "f"(v - hi));
+    float lo = __uint_as_float(lo_bits);
     Qhi[off] = hi;
     Qlo[off] = lo;
   }

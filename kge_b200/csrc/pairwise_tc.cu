@@ -12,9 +12,10 @@
 // (hard part 1).  We split x = hi + lo with hi = x & 0xFFFFE000 (tf32-exact) and issue
 //   D += Q_lo*T_hi + Q_hi*T_lo + Q_hi*T_hi          (kind::tf32, fp32 accumulate in TMEM)
 // which is fp32-equivalent (dropped term lo*lo ~ 2^-22).  Q is split once by the prologue; the
-// table is split ON THE FLY: TMA lands the raw fp32 tile in shared memory, four "splitter" warps
-// rewrite it in place as hi and write lo next to it (same swizzled layout, element-wise), fence
-// to the async proxy, and only then may the MMA warp consume the stage.
+// table is split ON THE FLY: TMA lands the raw fp32 tile in shared memory; the raw tile IS the hi
+// operand (kind::tf32 ignores the low 13 mantissa bits — truncation, measured on B200), and four
+// "splitter" warps write lo = rn_tf32(x - trunc_tf32(x)) next to it (same swizzled layout,
+// element-wise), fence to the async proxy, and only then may the MMA warp consume the stage.
 //
 // CTA = 12 warps, one CTA per SM, persistent over (query tile, range of entity tiles):
 //   warp 0      TMA producer   (one elected lane)     full[s]   <- expect_tx
@@ -26,6 +27,7 @@
 // so the epilogue of tile i overlaps the MMAs of tile i+1.  TMEM lane = query row, so every
 // per-row reduction (loss terms, logsumexp, rank counters) is thread-local.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -46,6 +48,12 @@ constexpr int STG_LD = 33;
 constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
 constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + STG_BYTES + 256 /*barriers*/;
 constexpr int TMEM_COLS = 512;
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 
 struct TcParams {
   int64_t nq, m;
@@ -182,13 +190,14 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_const
             float4* bl = reinterpret_cast<float4*>(stage_ptr(s) + 2 * A_BYTES + B_BYTES);
 #pragma unroll 4
             for (int i = t; i < B_BYTES / 16; i += SPLIT_WARPS * 32) {
-              float4 v = bh[i], h, l;
-              h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-              h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-              h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-              h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-              l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-              bh[i] = h;
+              // hi needs no write: the tensor core ignores the low 13 mantissa bits of the raw
+              // fp32 tile (truncation, verified on B200); lo = rn_tf32(x - trunc_tf32(x)).
+              const float4 v = bh[i];
+              float4 l;
+              l.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+              l.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+              l.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+              l.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
               bl[i] = l;
             }
             ptx::fence_proxy_async_smem();

@@ -1,0 +1,71 @@
+"""The LibKGE plugin loads through the reference's own plugin mechanism (config `modules:` +
+`<model>.yaml` class_name, kge/misc.py:13-42, kge_model.py:473-503).  Needs the live reference
+(/root/reference), which exists only in the build container; skipped elsewhere."""
+import pytest
+import torch
+
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+
+MODELS = ["complex", "distmult", "simple", "cp", "rescal", "transe", "rotate"]
+
+
+def _create(model, extra=None):
+    ref_shim.import_reference()
+    from kge import Config, Dataset
+    from kge.model import KgeModel
+
+    config = Config()
+    config.folder = None
+    config.set("console.quiet", True)
+    config.set("modules", ["kge.job", "kge.model", "kge.model.embedder", "kge_b200.plugin"])
+    config.set("model", model)
+    config._import(model)
+    config.set("dataset.name", "synthetic")
+    config.set("dataset.num_entities", 30)
+    config.set("dataset.num_relations", 4)
+    config.set("dataset.pickle", False)
+    config.set("job.device", "cpu")
+    config.set_all({"lookup_embedder.dim": 8})
+    if extra:
+        config.set_all(extra)
+    ds = Dataset(config, None)
+    ds._meta["relation_ids"] = [f"r{i}" for i in range(4)]    # in-memory dataset: no files to read
+    ds._meta["entity_ids"] = [f"e{i}" for i in range(30)]
+    return KgeModel.create(config, ds), config
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_plugin_model_loads_with_reference_parameter_names(name):
+    m, _ = _create("b200_" + name)
+    import kge_b200.plugin as plug
+
+    assert type(m).__name__.startswith("B200")
+    assert isinstance(m, getattr(plug, type(m).__name__))
+    keys = set(m.state_dict().keys())
+    assert "_entity_embedder._embeddings.weight" in keys       # lookup_embedder.py:44
+    assert "_relation_embedder._embeddings.weight" in keys
+    assert type(m.get_scorer()).__name__.startswith("B200")
+    # same relation-embedder sizing rules as the reference models
+    D = 8
+    want = {"cp": D // 2, "rotate": D // 2, "rescal": D * D}.get(name, D)
+    assert m.get_p_embedder()._embeddings.weight.shape == (4, want)
+
+
+def test_plugin_refuses_cpu_tensors():
+    m, _ = _create("b200_complex")
+    idx = torch.tensor([0, 1, 2])
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            m.score_sp(idx, idx % 4)
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            m.score_spo(idx, idx % 4, idx)
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            m.get_scorer().score_emb(torch.zeros(3, 8), torch.zeros(3, 8), torch.zeros(5, 8), "sp_")
+
+
+def test_reciprocal_relations_model_uses_plugin_scorer():
+    m, _ = _create("reciprocal_relations_model",
+                   {"reciprocal_relations_model.base_model.type": "b200_distmult"})
+    assert type(m._base_model.get_scorer()).__name__ == "B200DistMultScorer"
