@@ -2,7 +2,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "fold.cuh"
+#include "tc_common.cuh"
 
 namespace b200kge {
 
@@ -88,10 +90,11 @@ struct Block {
   const Rows* p;
   const Rows* cand;
   int64_t n;
+  const float* Qpre = nullptr;   // already-folded queries [nq, round_up(K,32)] (skips the fold launches)
 };
 
 int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiParams P, Arena& ws,
-              cudaStream_t st, int* nchunks_out) {
+              cudaStream_t st, int* nchunks_out, int* used_tc_out = nullptr) {
   const int64_t n = B.n, nq = B.q1 ? 2 * n : n, m = B.cand->rows;
   const int D = B.q0->dim;
   Folded f0 = folded_problem(B.model, B.combine, D, l_norm);
@@ -128,14 +131,19 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
     return run_block(h1, l_norm, precision, epi_kind, P1, ws, st, nchunks_out);
   }
 
+  if (used_tc_out) *used_tc_out = use_tc ? 1 : 0;
   if (use_tc) {
     const int passes = (precision == B200KGE_PREC_TF32) ? 1 : 3;
-    float* Qhi = (float*)ws.take((size_t)nq * ldq * 4);
-    float* Qlo = (float*)ws.take((size_t)nq * ldq * 4);
-    if (!Qhi || !Qlo) { set_error("workspace too small for folded queries"); return B200KGE_ERR_WORKSPACE; }
-    int rc = launch_fold_queries(B.model, B.combine, *B.q0, *B.p, n, 0, nullptr, ldq, Qhi, Qlo, st);
-    if (rc) return rc;
-    if (B.q1) { rc = launch_fold_queries(B.model, 1 - B.combine, *B.q1, *B.p, n, n, nullptr, ldq, Qhi, Qlo, st); if (rc) return rc; }
+    int rc = 0;
+    const float* Q = B.Qpre;
+    if (!Q) {
+      float* Qw = (float*)ws.take((size_t)nq * ldq * 4);
+      if (!Qw) { set_error("workspace too small for folded queries"); return B200KGE_ERR_WORKSPACE; }
+      rc = launch_fold_queries(B.model, B.combine, *B.q0, *B.p, n, 0, Qw, ldq, st);
+      if (rc) return rc;
+      if (B.q1) { rc = launch_fold_queries(B.model, 1 - B.combine, *B.q1, *B.p, n, n, Qw, ldq, st); if (rc) return rc; }
+      Q = Qw;
+    }
     const float* T = B.cand->base + f0.col_off;
     int64_t ldt = B.cand->ld;
     if (B.cand->idx) {
@@ -145,7 +153,12 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
       if (rc) return rc;
       T = G; ldt = ldq;
     }
-    const int nch = tc_nchunks(nq, m);
+    // The 1-CTA kernel is the default: on B200 it measured faster than the CTA-pair (cta_group::2)
+    // kernel at every batch size once the epilogue stopped being the bottleneck
+    // (profiles/r1_notes.md).  B200KGE_TC_VERSION=2 selects the pair kernel (kept for experiments).
+    const char* env_v = getenv("B200KGE_TC_VERSION");
+    const bool pair = env_v && atoi(env_v) == 2;
+    const int nch = pair ? tc2_nchunks(nq, m) : tc_nchunks(nq, m);
     if (epi_kind == EPI_BCE || epi_kind == EPI_KL) {
       const int F = (epi_kind == EPI_BCE) ? 2 : 5;
       P.part = (float*)ws.take((size_t)nq * nch * F * 4);
@@ -153,14 +166,20 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
     }
     P.nchunks = nch;
     if (nchunks_out) *nchunks_out = nch;
-    return launch_pairwise_tc(epi_kind, passes, Qhi, Qlo, ldq, nq, T, ldt, m, K, P, st);
+    if (pair) return launch_pairwise_tc2(epi_kind, passes, Q, ldq, nq, T, ldt, m, K, P, st);
+    return launch_pairwise_tc(epi_kind, passes, Q, ldq, nq, T, ldt, m, K, P, st);
   }
 
-  float* Q = (float*)ws.take((size_t)nq * ldq * 4);
-  if (!Q) { set_error("workspace too small for folded queries"); return B200KGE_ERR_WORKSPACE; }
-  int rc = launch_fold_queries(B.model, B.combine, *B.q0, *B.p, n, 0, Q, ldq, nullptr, nullptr, st);
-  if (rc) return rc;
-  if (B.q1) { rc = launch_fold_queries(B.model, 1 - B.combine, *B.q1, *B.p, n, n, Q, ldq, nullptr, nullptr, st); if (rc) return rc; }
+  int rc = 0;
+  const float* Q = B.Qpre;
+  if (!Q) {
+    float* Qw = (float*)ws.take((size_t)nq * ldq * 4);
+    if (!Qw) { set_error("workspace too small for folded queries"); return B200KGE_ERR_WORKSPACE; }
+    rc = launch_fold_queries(B.model, B.combine, *B.q0, *B.p, n, 0, Qw, ldq, st);
+    if (rc) return rc;
+    if (B.q1) { rc = launch_fold_queries(B.model, 1 - B.combine, *B.q1, *B.p, n, n, Qw, ldq, st); if (rc) return rc; }
+    Q = Qw;
+  }
   const int nch = pairwise_simt_nchunks(nq, m);
   if (epi_kind == EPI_BCE || epi_kind == EPI_KL) {
     const int F = (epi_kind == EPI_BCE) ? 2 : 5;
@@ -315,7 +334,9 @@ int b200kge_score_1vsN_loss(int model, int combine, float l_norm, int precision,
   // the partial buffer is the LAST thing run_block took from the arena
   const size_t part_bytes = (size_t)n * nch * F * 4;
   float* part = (float*)(ws.base + (ws.off - part_bytes));
-  return launch_loss_finalize(loss_kind, part, nch, n, labels->idx, loss_out, row_loss_out, 1.0f, 0, st);
+  void* scratch = ws.take(512);
+  if (!scratch) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+  return launch_loss_finalize(loss_kind, part, nch, n, loss_out, row_loss_out, 1.0f, 0, scratch, 0, st);
 }
 
 int b200kge_score_1vsN_rank(int model, int combine, float l_norm, int precision,
@@ -355,9 +376,11 @@ int b200kge_loss_dense(const float* scores, int64_t lds, int64_t n, int64_t m,
   P.nchunks = nch;
   P.part = (float*)ws.take((size_t)n * nch * F * 4);
   if (!P.part) { set_error("workspace too small for loss partials (need %zu bytes)", (size_t)n * nch * F * 4); return B200KGE_ERR_WORKSPACE; }
+  void* scratch = ws.take(512);
+  if (!scratch) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
   int rc = launch_loss_dense(loss_kind, scores, lds, n, m, P, st);
   if (rc) return rc;
-  return launch_loss_finalize(loss_kind, P.part, nch, n, labels->idx, loss_out, row_loss_out, 1.0f, 0, st);
+  return launch_loss_finalize(loss_kind, P.part, nch, n, loss_out, row_loss_out, 1.0f, 0, scratch, 0, st);
 }
 
 int b200kge_rank_dense(const float* scores, int64_t lds, int64_t n, int64_t m,
@@ -404,6 +427,35 @@ int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
   cudaStream_t st = (cudaStream_t)stream;
   if (n <= 0) { B2K_CUDA(cudaMemsetAsync(loss_out, 0, 4, st)); return 0; }
   Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  Rows E = to_rows(ent), R = to_rows(rel);
+  const int epi = (loss_kind == B200KGE_LOSS_BCE) ? EPI_BCE : EPI_KL;
+  const int F = (epi == EPI_BCE) ? 2 : 5;
+  const float scale = 1.0f / (float)n;       // "/ batch_size"   train_1vsAll.py:65,76
+  Folded f0 = folded_problem(model, B200KGE_SP_, E.dim, l_norm), f1 = folded_problem(model, B200KGE__PO, E.dim, l_norm);
+  if (f0.col_off == f1.col_off) {
+    // sp_ and _po rows stacked into ONE problem of 2n query rows against the same table:
+    // prologue (unpack + both folds + labels) = 1 launch, scoring + loss + finalisation = 1 launch
+    const int64_t ldq = round_up(f0.K, 32);
+    float* Q = (float*)ws.take((size_t)(2 * n) * ldq * 4);
+    int64_t* lab = (int64_t*)ws.take((size_t)n * 2 * 8);
+    uint8_t* scratch = (uint8_t*)ws.take(512);       // finaliser scratch: block sums + ticket (+256)
+    if (!Q || !lab || !scratch) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+    rc = launch_prep_1vsall(model, E, R, triples, n, Q, ldq, lab, reinterpret_cast<unsigned int*>(scratch + 256), st);
+    if (rc) return rc;
+    Rows S = E; S.idx = lab; S.rows = n;           // placeholders: operands are pre-folded
+    Rows Pr = R; Pr.idx = lab; Pr.rows = n;
+    EpiParams P = empty_epi();
+    P.label_idx = lab;
+    P.offset = (loss_kind == B200KGE_LOSS_BCE) ? offset : 0.f;
+    Block B{model, B200KGE_SP_, &S, &S, &Pr, &E, n};
+    B.Qpre = Q;
+    int nch = 0;
+    rc = run_block(B, l_norm, precision, epi, P, ws, st, &nch);
+    if (rc) return rc;
+    const size_t part_bytes = (size_t)(2 * n) * nch * F * 4;
+    float* part = (float*)(ws.base + (ws.off - part_bytes));
+    return launch_loss_finalize(loss_kind, part, nch, 2 * n, loss_out, nullptr, scale, 0, scratch, 1, st);
+  }
   int64_t* sidx = (int64_t*)ws.take((size_t)n * 8);
   int64_t* pidx = (int64_t*)ws.take((size_t)n * 8);
   int64_t* oidx = (int64_t*)ws.take((size_t)n * 8);
@@ -411,28 +463,12 @@ int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
   if (!sidx || !pidx || !oidx || !lab) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
   unpack_triples_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(triples, n, sidx, pidx, oidx, lab);
   B2K_LAUNCH_CHECK("unpack_triples_kernel");
-
-  Rows E = to_rows(ent), R = to_rows(rel);
   Rows S = E; S.idx = sidx; S.rows = n;
   Rows O = E; O.idx = oidx; O.rows = n;
   Rows Pr = R; Pr.idx = pidx; Pr.rows = n;
-  const int epi = (loss_kind == B200KGE_LOSS_BCE) ? EPI_BCE : EPI_KL;
-  const int F = (epi == EPI_BCE) ? 2 : 5;
   EpiParams P = empty_epi();
   P.label_idx = lab;
   P.offset = (loss_kind == B200KGE_LOSS_BCE) ? offset : 0.f;
-  const float scale = 1.0f / (float)n;       // "/ batch_size"   train_1vsAll.py:65,76
-  Folded f0 = folded_problem(model, B200KGE_SP_, E.dim, l_norm), f1 = folded_problem(model, B200KGE__PO, E.dim, l_norm);
-  if (f0.col_off == f1.col_off) {
-    // sp_ and _po rows stacked into one launch of 2n query rows against the same table
-    Block B{model, B200KGE_SP_, &S, &O, &Pr, &E, n};
-    int nch = 0;
-    rc = run_block(B, l_norm, precision, epi, P, ws, st, &nch);
-    if (rc) return rc;
-    const size_t part_bytes = (size_t)(2 * n) * nch * F * 4;
-    float* part = (float*)(ws.base + (ws.off - part_bytes));
-    return launch_loss_finalize(loss_kind, part, nch, 2 * n, lab, loss_out, nullptr, scale, 0, st);
-  }
   for (int dir = 0; dir < 2; ++dir) {   // CP: the two directions read different table columns
     Arena w2 = ws;
     EpiParams Pd = P;
@@ -443,7 +479,9 @@ int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
     if (rc) return rc;
     const size_t part_bytes = (size_t)n * nch * F * 4;
     float* part = (float*)(w2.base + (w2.off - part_bytes));
-    rc = launch_loss_finalize(loss_kind, part, nch, n, nullptr, loss_out, nullptr, scale, dir, st);
+    void* scratch = w2.take(512);
+    if (!scratch) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+    rc = launch_loss_finalize(loss_kind, part, nch, n, loss_out, nullptr, scale, dir, scratch, 0, st);
     if (rc) return rc;
   }
   return 0;

@@ -76,6 +76,7 @@ __host__ __device__ inline int relation_dim(int model, int D) {
 // one of these functors; per-row state lives in registers and is flushed once per (row, chunk).
 enum EpiKind : int { EPI_STORE = 0, EPI_BCE = 1, EPI_KL = 2, EPI_RANK = 3 };
 
+struct FinalizeArgs;
 struct EpiParams {
   // EPI_STORE
   float* out;
@@ -104,8 +105,12 @@ struct EpiParams {
 
 __device__ __forceinline__ float softplus_f(float z) {
   // max(z,0) + log1p(exp(-|z|)), matching torch's BCEWithLogits formulation (loss.py:150)
-  float e = __expf(-fabsf(z));
-  float l = (e < 1e-4f) ? (e - 0.5f * e * e) : __logf(1.0f + e);
+  // branch-free (a data-dependent branch here diverges per element and cost +40 % kernel time):
+  // log1p(e) ~= e for tiny e (where 1+e would round to 1), else log(1+e); both arms are already
+  // computed, so the compiler emits a select.
+  const float e = __expf(-fabsf(z));
+  const float lg = __logf(1.0f + e);
+  const float l = (e < 1e-5f) ? e : lg;
   return fmaxf(z, 0.0f) + l;
 }
 
@@ -240,11 +245,59 @@ __device__ __forceinline__ void epi_lane_reduce(RowState<KIND>& st, int width) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic finaliser of the fused losses: partial[n][nchunks][F] -> row loss -> scalar.
+// Fixed reduction order at every level (lanes over chunks -> shuffle tree, rows per warp in
+// order, warps per block in order, blocks in index order by the last block): the result does not
+// depend on scheduling.
+struct FinalizeArgs {
+  const float* part;
+  int nchunks;
+  int64_t n;
+  float* loss_out;
+  float* row_loss_out;
+  float scale;
+  int accumulate;
+  unsigned int* ticket;   // zero-initialised counter for the last-block-done protocol
+  float* block_sums;      // [gridDim.x] scratch
+};
+
+template <int LOSS>
+__device__ __forceinline__ float finalize_row(const float* __restrict__ part, int nchunks, int64_t r) {
+  if constexpr (LOSS == B200KGE_LOSS_BCE) {
+    float a = 0.f, b = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const float* p = part + (r * nchunks + c) * 2;
+      a += p[0]; b += p[1];
+    }
+    return a - b;                       // sum softplus(z) - sum y*z
+  } else {
+    RowState<EPI_KL> st;
+    st.init();
+    for (int c = 0; c < nchunks; ++c) {
+      const float* p = part + (r * nchunks + c) * 5;
+      RowState<EPI_KL> o;
+      o.m = p[0]; o.s = p[1]; o.y_sum = p[2]; o.yx = p[3]; o.ylogy = p[4];
+      st.combine(o);
+    }
+    const float lse = st.m + logf(st.s);
+    // KLDiv(log_softmax(x), y / max(||y||_1, 1e-12)), reduction sum   loss.py:209-213
+    const float yc = fmaxf(st.y_sum, 1e-12f);
+    const float w = st.y_sum / yc;
+    return (st.y_sum > 0.f) ? (st.ylogy / yc - w * logf(yc) - st.yx / yc + lse * w) : 0.f;
+  }
+}
+
+
 // ---------------------------------------------------------------------------------------------
 // Internal kernels' host launchers (one per .cu file).
 int launch_fold_queries(int model, int combine, const Rows& q, const Rows& p, int64_t n,
-                        int64_t row0, float* Q, int64_t ldq, float* Qhi, float* Qlo,
-                        cudaStream_t st);
+                        int64_t row0, float* Q, int64_t ldq, cudaStream_t st);
+// one launch: unpack triples [n,3], fold sp_ rows (0..n) and _po rows (n..2n) into Q, write the
+// stacked labels [o ; s] and zero the finalisation ticket
+int launch_prep_1vsall(int model, const Rows& ent, const Rows& rel, const int64_t* triples, int64_t n,
+                       float* Q, int64_t ldq, int64_t* labels2n, unsigned int* ticket, cudaStream_t st);
 int launch_gather_rows(const Rows& src, int col_off, int K, float* dst, int64_t ldd,
                        cudaStream_t st);
 int launch_pairwise_simt(int epi_kind, int pair_op, float l_norm, const float* Q, int64_t ldq,
@@ -254,12 +307,14 @@ int pairwise_simt_nchunks(int64_t nq, int64_t m);
 // tcgen05 path: returns B200KGE_ERR_UNSUPPORTED if the shape cannot be served.
 bool tc_supported(int pair_op, int K, const Rows& cand, int col_off);
 int tc_nchunks(int64_t nq, int64_t m);
-int launch_pairwise_tc(int epi_kind, int passes, const float* Qhi, const float* Qlo, int64_t ldq,
+int launch_pairwise_tc(int epi_kind, int passes, const float* Q, int64_t ldq,
                        int64_t nq, const float* T, int64_t ldt, int64_t m, int K,
                        const EpiParams& P, cudaStream_t st);
-int launch_loss_finalize(int loss_kind, const float* part, int nchunks, int64_t n,
-                         const int64_t* label_idx, float* loss_out, float* row_loss_out,
-                         float scale, int accumulate, cudaStream_t st);
+// scratch: >= 512 bytes of device memory (block sums + ticket); ticket_zeroed: the caller already
+// zeroed the ticket word at scratch+256 on this stream (else a 4-byte memset is enqueued)
+int launch_loss_finalize(int loss_kind, const float* part, int nchunks, int64_t n, float* loss_out,
+                         float* row_loss_out, float scale, int accumulate, void* scratch,
+                         int ticket_zeroed, cudaStream_t st);
 int launch_spo(int model, float l_norm, const Rows& s, const Rows& p, const Rows& o, int64_t n,
                float* out, int64_t out_stride, cudaStream_t st);
 int launch_ns(int model, float l_norm, const Rows& s, const Rows& p, const Rows& o,

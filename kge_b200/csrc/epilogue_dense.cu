@@ -56,48 +56,68 @@ dense_epilogue_kernel(const float* __restrict__ scores, int64_t lds, int64_t m, 
   block_reduce_flush<KIND>(P, st, row, chunk);
 }
 
-// One thread walks the chunks of a row in order (deterministic), then a fixed smem tree sums rows.
+// One warp per row: lanes hold the row's chunk partials (coalesced), a fixed shuffle tree combines
+// them; lane 0 accumulates the warp's rows in order.  Blocks publish their sums; the last block to
+// finish adds them in index order.
+constexpr int FIN_BLOCKS = 64, FIN_THREADS = 256;
+
 template <int LOSS>
-__global__ void __launch_bounds__(1024)
-loss_finalize_kernel(const float* __restrict__ part, int nchunks, int64_t n,
-                     float* __restrict__ loss_out, float* __restrict__ row_loss_out, float scale,
-                     int accumulate) {
-  __shared__ float red[1024];
-  float local = 0.f;
-  for (int64_t r = threadIdx.x; r < n; r += blockDim.x) {
+__global__ void __launch_bounds__(FIN_THREADS)
+loss_finalize_kernel(FinalizeArgs A) {
+  __shared__ float wsum[FIN_THREADS / 32];
+  __shared__ int is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = FIN_THREADS / 32;
+  float acc = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * nw + warp; r < A.n; r += (int64_t)gridDim.x * nw) {
     float rl;
     if constexpr (LOSS == B200KGE_LOSS_BCE) {
+      const float* __restrict__ p = A.part + r * A.nchunks * 2;
       float a = 0.f, b = 0.f;
-      for (int c = 0; c < nchunks; ++c) {
-        const float* p = part + (r * nchunks + c) * 2;
-        a += p[0]; b += p[1];
+      for (int c = lane; c < A.nchunks; c += 32) { a += p[2 * c]; b += p[2 * c + 1]; }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
       }
       rl = a - b;                       // sum softplus(z) - sum y*z
     } else {
       RowState<EPI_KL> st;
       st.init();
-      for (int c = 0; c < nchunks; ++c) {
-        const float* p = part + (r * nchunks + c) * 5;
+      for (int c = lane; c < A.nchunks; c += 32) {
+        const float* __restrict__ p = A.part + (r * A.nchunks + c) * 5;
         RowState<EPI_KL> o;
         o.m = p[0]; o.s = p[1]; o.y_sum = p[2]; o.yx = p[3]; o.ylogy = p[4];
         st.combine(o);
       }
+      epi_lane_reduce<EPI_KL>(st, 32);
       const float lse = st.m + logf(st.s);
       // KLDiv(log_softmax(x), y / max(||y||_1, 1e-12)), reduction sum   loss.py:209-213
       const float yc = fmaxf(st.y_sum, 1e-12f);
       const float w = st.y_sum / yc;
       rl = (st.y_sum > 0.f) ? (st.ylogy / yc - w * logf(yc) - st.yx / yc + lse * w) : 0.f;
     }
-    if (row_loss_out) row_loss_out[r] = rl;
-    local += rl;
+    if (lane == 0) {
+      if (A.row_loss_out) A.row_loss_out[r] = rl;
+      acc += rl;
+    }
   }
-  red[threadIdx.x] = local;
+  if (lane == 0) wsum[warp] = acc;
   __syncthreads();
-  for (int s = 512; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-    __syncthreads();
+  if (threadIdx.x == 0) {
+    float bs = 0.f;
+    for (int w = 0; w < nw; ++w) bs += wsum[w];
+    A.block_sums[blockIdx.x] = bs;
+    __threadfence();
+    is_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
   }
-  if (threadIdx.x == 0) loss_out[0] = (accumulate ? loss_out[0] : 0.f) + scale * red[0];
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    float tot = 0.f;
+    for (unsigned b = 0; b < gridDim.x; ++b) tot += reinterpret_cast<volatile float*>(A.block_sums)[b];
+    A.loss_out[0] = (A.accumulate ? A.loss_out[0] : 0.f) + A.scale * tot;
+    *A.ticket = 0u;
+  }
 }
 
 }  // namespace
@@ -126,13 +146,17 @@ int launch_rank_dense(const float* scores, int64_t lds, int64_t n, int64_t m, co
   return 0;
 }
 
-int launch_loss_finalize(int loss_kind, const float* part, int nchunks, int64_t n,
-                         const int64_t* /*label_idx*/, float* loss_out, float* row_loss_out,
-                         float scale, int accumulate, cudaStream_t st) {
-  if (loss_kind == B200KGE_LOSS_BCE)
-    loss_finalize_kernel<B200KGE_LOSS_BCE><<<1, 1024, 0, st>>>(part, nchunks, n, loss_out, row_loss_out, scale, accumulate);
-  else if (loss_kind == B200KGE_LOSS_KL)
-    loss_finalize_kernel<B200KGE_LOSS_KL><<<1, 1024, 0, st>>>(part, nchunks, n, loss_out, row_loss_out, scale, accumulate);
+int launch_loss_finalize(int loss_kind, const float* part, int nchunks, int64_t n, float* loss_out,
+                         float* row_loss_out, float scale, int accumulate, void* scratch,
+                         int ticket_zeroed, cudaStream_t st) {
+  float* block_sums = reinterpret_cast<float*>(scratch);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(scratch) + 256);
+  if (!ticket_zeroed) B2K_CUDA(cudaMemsetAsync(ticket, 0, 4, st));
+  int64_t want = (n + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32);
+  const int grid = (int)(want < 1 ? 1 : (want > FIN_BLOCKS ? FIN_BLOCKS : want));
+  FinalizeArgs A{part, nchunks, n, loss_out, row_loss_out, scale, accumulate, ticket, block_sums};
+  if (loss_kind == B200KGE_LOSS_BCE) loss_finalize_kernel<B200KGE_LOSS_BCE><<<grid, FIN_THREADS, 0, st>>>(A);
+  else if (loss_kind == B200KGE_LOSS_KL) loss_finalize_kernel<B200KGE_LOSS_KL><<<grid, FIN_THREADS, 0, st>>>(A);
   else { set_error("unknown loss kind %d", loss_kind); return B200KGE_ERR_INVALID; }
   B2K_LAUNCH_CHECK("loss_finalize_kernel");
   return 0;

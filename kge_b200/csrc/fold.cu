@@ -16,26 +16,9 @@
 
 namespace b200kge {
 
-__device__ __forceinline__ void store_q(float* Q, float* Qhi, float* Qlo, int64_t off, float v) {
-  if (Q) Q[off] = v;
-  if (Qhi) {
-    // tf32 hi/lo split: hi = truncation to tf32 (what the tensor core does to a raw fp32 operand:
-    // it ignores the low 13 mantissa bits — verified on B200, profiles/r1_notes.md), lo = the exact
-    // remainder rounded-to-nearest to tf32 (halves the dominant error term vs letting the
-    // hardware truncate it).
-    float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-    uint32_t lo_bits;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo_bits) : "f"(v - hi));
-    float lo = __uint_as_float(lo_bits);
-    Qhi[off] = hi;
-    Qlo[off] = lo;
-  }
-}
-
 template <int MODEL>
 __global__ void __launch_bounds__(128)
-fold_kernel(int combine, Rows qa, Rows pr, int64_t row0, float* __restrict__ Q, int64_t ldq,
-            float* __restrict__ Qhi, float* __restrict__ Qlo, int K) {
+fold_kernel(int combine, Rows qa, Rows pr, int64_t row0, float* __restrict__ Q, int64_t ldq, int K) {
   const int64_t i = blockIdx.x;
   const float* __restrict__ a = qa.row(i);
   const float* __restrict__ p = pr.row(i);
@@ -48,18 +31,64 @@ fold_kernel(int combine, Rows qa, Rows pr, int64_t row0, float* __restrict__ Q, 
     extern __shared__ float sh[];
     for (int k = threadIdx.x; k < D; k += blockDim.x) sh[k] = a[k];
     __syncthreads();
-    fold_rescal_block(sp, sh, p, D, [&](int k, float v) { store_q(Q, Qhi, Qlo, obase + k, v); });
+    fold_rescal_block(sp, sh, p, D, [&](int k, float v) { Q[obase + k] = v; });
   } else {
     for (int k = threadIdx.x; k < K; k += blockDim.x)
-      store_q(Q, Qhi, Qlo, obase + k, fold_element<MODEL>(sp, a, p, k, h));
+      Q[obase + k] = fold_element<MODEL>(sp, a, p, k, h);
   }
   // zero the padding columns [K, ldq) so padded K-chunks contribute nothing
-  for (int64_t k = K + threadIdx.x; k < ldq; k += blockDim.x) store_q(Q, Qhi, Qlo, obase + k, 0.f);
+  for (int64_t k = K + threadIdx.x; k < ldq; k += blockDim.x) Q[obase + k] = 0.f;
+}
+
+// One launch for a whole 1vsAll step's prologue: block b < n folds (s_b, p_b) for the sp_ direction
+// into Q row b and labels it with o_b; block n+b folds (o_b, p_b) for _po into Q row n+b, label s_b
+// (train_1vsAll.py:59-65,75-76).  Replaces unpack + two fold launches.
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+prep_1vsall_kernel(Rows ent, Rows rel, const int64_t* __restrict__ tri, int64_t n, float* __restrict__ Q,
+                   int64_t ldq, int64_t* __restrict__ labels2n, unsigned int* ticket, int K) {
+  const int64_t b = blockIdx.x;
+  const bool sp = b < n;
+  const int64_t i = sp ? b : b - n;
+  const int64_t si = tri[3 * i], pi = tri[3 * i + 1], oi = tri[3 * i + 2];
+  const float* __restrict__ a = ent.base + (sp ? si : oi) * ent.ld;
+  const float* __restrict__ p = rel.base + pi * rel.ld;
+  const int D = ent.dim, h = D >> 1;
+  const int64_t obase = b * ldq;
+  if (threadIdx.x == 0) {
+    labels2n[b] = sp ? oi : si;
+    if (b == 0 && ticket) *ticket = 0u;
+  }
+  if constexpr (MODEL == B200KGE_RESCAL) {
+    extern __shared__ float sh[];
+    for (int k = threadIdx.x; k < D; k += blockDim.x) sh[k] = a[k];
+    __syncthreads();
+    fold_rescal_block(sp, sh, p, D, [&](int k, float v) { Q[obase + k] = v; });
+  } else {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) Q[obase + k] = fold_element<MODEL>(sp, a, p, k, h);
+  }
+  for (int64_t k = K + threadIdx.x; k < ldq; k += blockDim.x) Q[obase + k] = 0.f;
+}
+
+int launch_prep_1vsall(int model, const Rows& ent, const Rows& rel, const int64_t* triples, int64_t n,
+                       float* Q, int64_t ldq, int64_t* labels2n, unsigned int* ticket, cudaStream_t st) {
+  if (n == 0) return 0;
+  const int D = ent.dim;
+  const int K = (model == B200KGE_CP) ? D / 2 : D;
+  dim3 grid((unsigned)(2 * n)), block(128);
+#define B2K_PREP(M, SM) case M: prep_1vsall_kernel<M><<<grid, block, SM, st>>>(ent, rel, triples, n, Q, ldq, labels2n, ticket, K); break;
+  switch (model) {
+    B2K_PREP(B200KGE_COMPLEX, 0) B2K_PREP(B200KGE_DISTMULT, 0) B2K_PREP(B200KGE_SIMPLE, 0)
+    B2K_PREP(B200KGE_RESCAL, D * sizeof(float)) B2K_PREP(B200KGE_TRANSE, 0) B2K_PREP(B200KGE_ROTATE, 0)
+    default: set_error("model %d has no stacked 1vsAll prologue", model); return B200KGE_ERR_INVALID;
+  }
+#undef B2K_PREP
+  B2K_LAUNCH_CHECK("prep_1vsall_kernel");
+  return 0;
 }
 
 int launch_fold_queries(int model, int combine, const Rows& q, const Rows& p, int64_t n,
-                        int64_t row0, float* Q, int64_t ldq, float* Qhi, float* Qlo,
-                        cudaStream_t st) {
+                        int64_t row0, float* Q, int64_t ldq, cudaStream_t st) {
   if (n == 0) return 0;
   const int D = q.dim;
   int K = D;
@@ -67,19 +96,19 @@ int launch_fold_queries(int model, int combine, const Rows& q, const Rows& p, in
   dim3 grid((unsigned)n), block(128);
   switch (model) {
     case B200KGE_COMPLEX:
-      fold_kernel<B200KGE_COMPLEX><<<grid, block, 0, st>>>(combine, q, p, row0, Q, ldq, Qhi, Qlo, K); break;
+      fold_kernel<B200KGE_COMPLEX><<<grid, block, 0, st>>>(combine, q, p, row0, Q, ldq, K); break;
     case B200KGE_DISTMULT:
-      fold_kernel<B200KGE_DISTMULT><<<grid, block, 0, st>>>(combine, q, p, row0, Q, ldq, Qhi, Qlo, K); break;
+      fold_kernel<B200KGE_DISTMULT><<<grid, block, 0, st>>>(combine, q, p, row0, Q, ldq, K); break;
     case B200KGE_SIMPLE:
-      fold_kernel<B200KGE_SIMPLE><<<grid, block, 0, st>>>(combine, q, p, row0, Q, ldq, Qhi, Qlo, K); break;
+      fold_kernel<B200KGE_SIMPLE><<<grid, block, 0, st>>>(combine, q, p, row0, Q, ldq, K); break;
     case B200KGE_CP:
-      fold_kernel<B200KGE_CP><<<grid, block, 0, st>>>(combine, q, p, row0, Q, ldq, Qhi, Qlo, K); break;
+      fold_kernel<B200KGE_CP><<<grid, block, 0, st>>>(combine, q, p, row0, Q, ldq, K); break;
     case B200KGE_RESCAL:
-      fold_kernel<B200KGE_RESCAL><<<grid, block, D * sizeof(float), st>>>(combine, q, p, row0, Q, ldq, Qhi, Qlo, K); break;
+      fold_kernel<B200KGE_RESCAL><<<grid, block, D * sizeof(float), st>>>(combine, q, p, row0, Q, ldq, K); break;
     case B200KGE_TRANSE:
-      fold_kernel<B200KGE_TRANSE><<<grid, block, 0, st>>>(combine, q, p, row0, Q, ldq, Qhi, Qlo, K); break;
+      fold_kernel<B200KGE_TRANSE><<<grid, block, 0, st>>>(combine, q, p, row0, Q, ldq, K); break;
     case B200KGE_ROTATE:
-      fold_kernel<B200KGE_ROTATE><<<grid, block, 0, st>>>(combine, q, p, row0, Q, ldq, Qhi, Qlo, K); break;
+      fold_kernel<B200KGE_ROTATE><<<grid, block, 0, st>>>(combine, q, p, row0, Q, ldq, K); break;
     default:
       set_error("unknown model %d", model);
       return B200KGE_ERR_INVALID;

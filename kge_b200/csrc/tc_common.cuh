@@ -1,0 +1,289 @@
+// tc_common.cuh — pieces shared by the 1-CTA (pairwise_tc.cu) and 2-CTA (pairwise_tc2.cu) tcgen05 kernels.
+#pragma once
+#include <cuda.h>
+#include <cstdlib>
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200kge {
+namespace tc {
+
+constexpr int STG_LD = 33;   // padded row of the per-warp transpose staging buffer
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// lo = rn_tf32(x - trunc_tf32(x)) for 4 packed floats (hi needs no write: kind::tf32 ignores the low
+// 13 mantissa bits of a raw fp32 operand — truncation, measured on B200).
+__device__ __forceinline__ float4 split_lo4(const float4 v) {
+  float4 l;
+  l.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+  l.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+  l.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+  l.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+  return l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// explicit shared-space vector accesses (the compiler otherwise emits generic LD.E/ST.E for pointers
+// carved out of the dynamic smem buffer by integer arithmetic)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// lo tile = split_lo(raw tile) for NBYTES bytes, by `nthreads` threads (thread index t); all loads
+// of a thread are issued before its stores so the smem latency is paid once.
+template <int NBYTES, int NTHR>
+__device__ __forceinline__ void split_tile(uint32_t src, uint32_t dst, int t) {
+  constexpr int PER = NBYTES / 16 / NTHR;   // float4s per thread
+  static_assert(PER * NTHR * 16 == NBYTES, "tile must divide evenly");
+  float4 v[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) v[i] = lds128(src + (uint32_t)(t + i * NTHR) * 16u);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) sts128(dst + (uint32_t)(t + i * NTHR) * 16u, split_lo4(v[i]));
+}
+
+// Epilogue.  TMEM lane = query row, so one thread owns one row and walks 32-column chunks.
+// The first version fed every element through the generic epi_elem functor: ~43 SASS instructions
+// per element (64-bit bounds/label compares, per-element null checks of optional operands) on ONE
+// warp per SM sub-partition — the whole kernel was epilogue-bound (profiles/r1_notes.md).  Here:
+// warp-uniform fast paths for full chunks, optional operands resolved once per chunk, the one-hot
+// label handled outside the element loop, and TWO epilogue warps per sub-partition (each takes
+// half of the accumulator's columns) so dependent-issue latency is hidden.
+
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+constexpr int EPI_WARPS = 8;    // warps 4..11: quadrant = warp % 4 (TMEM lanes), half = (warp-4)/4 (columns)
+constexpr int SPLIT_WARPS = 4;  // warps 12..15
+constexpr int NTHREADS = 16 * 32;
+
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 32 columns [c0, c0+32) of row `row`; v = raw accumulator bits.  FULL: all 32 columns < m.
+template <int EPI, bool FULL>
+__device__ __forceinline__ void epi_chunk32(const EpiParams& P, RowState<EPI>& st, int64_t row, float aux,
+                                            const uint32_t (&v)[32], int64_t c0, int64_t m) {
+  const int nvalid = FULL ? 32 : (int)(m - c0);   // > 0 by construction
+  if constexpr (EPI == EPI_BCE) {
+    // sum softplus(z) - sum y*z,  softplus(z) = max(z,0) + log(1 + exp(-|z|))   (loss.py:150-157;
+    // torch's kernel also evaluates log(1+e) with a plain log, so tiny e drop out identically)
+    const float off = P.offset;
+    float amax = 0.f, alg = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (FULL || c < nvalid) {
+        const float z = __uint_as_float(v[c]) + off;
+        const float e = fast_ex2(-fabsf(z) * LOG2E);
+        alg += __log2f(1.0f + e);
+        amax += fmaxf(z, 0.f);
+      }
+    }
+    st.a += fmaf(alg, LN2, amax);
+    if (P.label_dense) {
+      const float* __restrict__ y = P.label_dense + row * P.ldl + c0;
+      float b = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (FULL || c < nvalid) b = fmaf(__ldg(y + c), __uint_as_float(v[c]) + off, b);
+      st.b += b;
+    } else {
+      const int rel = __float_as_int(aux) - (int)c0;      // one-hot label relative to this chunk
+      if ((unsigned)rel < (unsigned)nvalid) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c == rel) st.b += __uint_as_float(v[c]) + off;
+      }
+    }
+  } else if constexpr (EPI == EPI_KL) {
+    // online logsumexp: chunk max first, then ONE exp per element   (loss.py:198-213)
+    float cm = B2K_NEG_HUGE;
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (FULL || c < nvalid) cm = fmaxf(cm, __uint_as_float(v[c]));
+    const float mn = fmaxf(st.m, cm);
+    const float mn2 = mn * LOG2E;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (FULL || c < nvalid) acc += fast_ex2(fmaf(__uint_as_float(v[c]), LOG2E, -mn2));
+    st.s = fmaf(st.s, fast_ex2((st.m - mn) * LOG2E), acc);
+    st.m = mn;
+    if (P.label_dense) {
+      const float* __restrict__ y = P.label_dense + row * P.ldl + c0;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        if (FULL || c < nvalid) {
+          const float yy = __ldg(y + c);
+          if (yy != 0.f) {
+            st.y_sum += yy;
+            st.yx = fmaf(yy, __uint_as_float(v[c]), st.yx);
+            st.ylogy = fmaf(yy, __logf(yy), st.ylogy);
+          }
+        }
+      }
+    } else {
+      const int rel = __float_as_int(aux) - (int)c0;
+      if ((unsigned)rel < (unsigned)nvalid) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c == rel) { st.y_sum += 1.0f; st.yx += __uint_as_float(v[c]); }
+      }
+    }
+  } else if constexpr (EPI == EPI_RANK) {
+    // eval_entity_ranking.py:561-596; `allowed` depends on the row only -> hoisted
+    const float t = aux;
+    const float allowed = __fadd_rn(P.atol, fabsf(__fmul_rn(P.rtol, t)));
+    const float* __restrict__ f = P.filter ? P.filter + row * P.ldf + c0 : nullptr;
+    unsigned int gt = 0, cl = 0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (FULL || c < nvalid) {
+        float x = __uint_as_float(v[c]);
+        if (f) x = __fsub_rn(x, __ldg(f + c));
+        if (isnan(x)) x = -INFINITY;
+        const float actual = fabsf(__fsub_rn(x, t));
+        const bool close = (x == t) || (isfinite(actual) && actual <= allowed);
+        cl += close ? 1u : 0u;
+        gt += (!close && x > t) ? 1u : 0u;
+      }
+    }
+    st.greater += gt;
+    st.close += cl;
+  }
+}
+
+// Epilogue of NCH 32-column chunks of one accumulator for the warp owning TMEM lanes
+// [32*quadrant, +32) and columns [col_first, col_first + 32*NCH) of the tile.
+template <int EPI, int NCH>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& P, RowState<EPI>& st, float aux,
+                                              uint32_t tmem_acc /* base + lane<<16 + first column */,
+                                              int64_t tile_row0 /* first row of this warp's 32 */,
+                                              int64_t e0 /* global column of the first chunk */, int64_t nq,
+                                              int64_t m, float* my_stg, int lane) {
+  const int64_t row = tile_row0 + lane;
+  const bool row_ok = row < nq;
+#pragma unroll 1
+  for (int j = 0; j < NCH; ++j) {
+    const int64_t c0 = e0 + j * 32;
+    if (c0 >= m) break;                                   // warp-uniform: chunk entirely out of range
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(tmem_acc + (uint32_t)(j * 32), v);
+    ptx::tmem_ld_wait();
+    if constexpr (EPI == EPI_STORE) {
+      // transpose a 32x32 block through smem: each store instruction then writes 32 consecutive
+      // entities of ONE query row (coalesced 128 B) whatever the row stride is
+#pragma unroll
+      for (int c = 0; c < 32; ++c) my_stg[lane * STG_LD + c] = __uint_as_float(v[c]);
+      __syncwarp();
+      const int64_t col = c0 + lane;
+      // rows of this warp map to consecutive output rows unless the block straddles the sp|po seam
+      const bool seam = P.n_rows_out > 0 && tile_row0 < P.n_rows_out && tile_row0 + 32 > P.n_rows_out;
+      if (!seam) {
+        int64_t r0 = tile_row0, cb = 0;
+        if (P.n_rows_out > 0 && r0 >= P.n_rows_out) { r0 -= P.n_rows_out; cb = P.col_block; }
+        float* __restrict__ p = P.out + r0 * P.ldo + cb + col;
+        const int nrows = (int)((nq - tile_row0) < 32 ? (nq - tile_row0) : 32);
+        float t[32];
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) t[rr] = my_stg[rr * STG_LD + lane];
+        if (col < m) {
+          if (nrows == 32) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) p[rr * P.ldo] = t[rr];
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              if (rr < nrows) p[rr * P.ldo] = t[rr];
+          }
+        }
+      } else if (col < m) {
+        for (int rr = 0; rr < 32; ++rr) {
+          int64_t r = tile_row0 + rr;
+          if (r < nq) {
+            int64_t cb = 0;
+            if (r >= P.n_rows_out) { r -= P.n_rows_out; cb = P.col_block; }
+            P.out[r * P.ldo + cb + col] = my_stg[rr * STG_LD + lane];
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+      if (row_ok) {
+        if (c0 + 32 <= m) epi_chunk32<EPI, true>(P, st, row, aux, v, c0, m);
+        else              epi_chunk32<EPI, false>(P, st, row, aux, v, c0, m);
+      }
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map over [rows, cols] with row stride ld floats; box = box_cols x box_rows,
+// swizzle = box_cols*4 bytes (64 or 128).
+inline int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                    int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return B200KGE_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = (box_cols * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows,
+              (long long)cols, (long long)ld);
+    return B200KGE_ERR_CUDA;
+  }
+  return 0;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace tc
+
+// 2-CTA kernel (pairwise_tc2.cu)
+int tc2_nchunks(int64_t nq, int64_t m);
+int launch_pairwise_tc2(int epi_kind, int passes, const float* Q, int64_t ldq,
+                        int64_t nq, const float* T, int64_t ldt, int64_t m, int K,
+                        const EpiParams& P, cudaStream_t st);
+
+}  // namespace b200kge

@@ -104,6 +104,7 @@ CASES = {
     "tc3_step": lambda: case_1vsall("complex", 14541, 237, 512, 1024, "3xtf32", "step"),
     "tc3_store": lambda: case_1vsall("complex", 14541, 237, 512, 1024, "3xtf32", "store"),
     "tc3_kl": lambda: case_1vsall("complex", 14541, 237, 512, 1024, "3xtf32", "kl"),
+    "tc3_store_n512": lambda: case_1vsall("complex", 14541, 237, 512, 512, "3xtf32", "store"),
     "tc1_step": lambda: case_1vsall("complex", 14541, 237, 512, 1024, "tf32", "step"),
     "tc1_store": lambda: case_1vsall("complex", 14541, 237, 512, 1024, "tf32", "store"),
     "fp32_step": lambda: case_1vsall("complex", 14541, 237, 512, 1024, "fp32", "step"),
