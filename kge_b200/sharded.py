@@ -1,0 +1,199 @@
+"""Entity-sharded scoring across GPUs (one process per GPU, torch.distributed / NCCL over NVLink).
+
+The reference has no distributed path; its natural seam is the entity-chunk loop of
+entity ranking, whose per-chunk rank/tie counts are additive (eval_entity_ranking.py:222-229,
+310-313).  For graphs whose entity table outgrows one GPU (Wikidata5M: 4.8 M x 512 fp32 = 9.8 GB,
+plus optimizer state) rank g owns rows [g*ceil(E/G), (g+1)*ceil(E/G)); the relation table is
+replicated (<= 6 MB).  One call =
+
+  1. query-row exchange: each rank fills the s/o rows it owns into a zeroed [n, D] buffer
+     -> all-reduce(sum)                                        (2 * n * D * 4 bytes)
+  2. local-shard scoring with the same single-GPU kernels     ([n, E/G] per direction, fused epilogues)
+  3. result exchange, by consumer:
+       score_sp_po   -> all-gather of per-shard logits         (north_star)
+       rank_sp_po    -> all-reduce(sum) of int64 rank/tie counts  (integer => bit-exact, 4*n*8 bytes)
+       loss_1vsall   -> all-reduce(sum) of per-rank BCE partial sums
+       topk_sp       -> local top-k, all-gather of [n,k] (value,index), merge (lowest index wins ties)
+
+Small tables (FB15k-237, YAGO3-10) are better served by replicas + batch split (no collective);
+that is what bench.py --gpus N runs.
+
+The local scorer is pluggable: `EngineBackend` (CUDA kernels through the C ABI) in production;
+the CPU gloo tests inject an oracle-based backend to exercise the host logic without a GPU.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+class EngineBackend:
+    """Local-shard scoring on the GPU through libb200kge."""
+
+    def score_1vsN(self, model, combine, q_emb, p_emb, cand, l_norm, precision):
+        from . import engine
+        return engine.score_1vsN(model, combine, q_emb, p_emb, cand, l_norm=l_norm, precision=precision)
+
+    def score_spo(self, model, s_emb, p_emb, o_emb, l_norm):
+        from . import engine
+        return engine.score_spo(model, s_emb, p_emb, o_emb, l_norm=l_norm)
+
+    def rank_1vsN(self, model, combine, q_emb, p_emb, cand, true_scores, filter_labels, rtol, atol, l_norm,
+                  precision):
+        from . import engine
+        return engine.score_1vsN_rank(model, combine, q_emb, p_emb, cand, true_scores, None, None, None,
+                                      filter_labels, rtol, atol, l_norm, precision)
+
+    def bce_1vsN(self, model, combine, q_emb, p_emb, cand, local_labels, offset, l_norm, precision):
+        from . import engine
+        return engine.score_1vsN_loss(model, combine, q_emb, p_emb, cand, local_labels, None, None, None,
+                                      "bce", offset, l_norm, precision)
+
+
+class ShardedKgeModel:
+    def __init__(self, model: str, ent_shard: torch.Tensor, rel: torch.Tensor, num_entities: int,
+                 rank: Optional[int] = None, world: Optional[int] = None, group=None,
+                 l_norm: float = 1.0, precision: str = "auto", backend=None):
+        self.model, self.l_norm, self.precision = model, l_norm, precision
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.E = int(num_entities)
+        self.per = (self.E + self.world - 1) // self.world
+        self.lo = min(self.rank * self.per, self.E)
+        self.hi = min(self.lo + self.per, self.E)
+        if ent_shard.shape[0] != self.hi - self.lo:
+            raise ValueError(f"rank {self.rank} must hold rows [{self.lo},{self.hi}) of the entity table, "
+                             f"got {ent_shard.shape[0]} rows")
+        self.ent, self.rel = ent_shard, rel
+        self.backend = backend or EngineBackend()
+
+    # -- ownership ---------------------------------------------------------------------------------
+    @staticmethod
+    def shard_bounds(num_entities: int, world: int, rank: int):
+        per = (num_entities + world - 1) // world
+        lo = min(rank * per, num_entities)
+        return lo, min(lo + per, num_entities)
+
+    def _all_reduce(self, t, op=dist.ReduceOp.SUM):
+        if self.world > 1:
+            dist.all_reduce(t, op=op, group=self.group)
+        return t
+
+    # -- step 1: query-row exchange ------------------------------------------------------------------
+    def gather_entity_rows(self, idx: torch.Tensor) -> torch.Tensor:
+        """[n, D] rows of the GLOBAL entity table for global ids `idx`, on every rank."""
+        idx = idx.long()
+        out = torch.zeros((idx.numel(), self.ent.shape[1]), dtype=self.ent.dtype, device=self.ent.device)
+        mine = (idx >= self.lo) & (idx < self.hi)
+        if bool(mine.any()):
+            out[mine] = self.ent[idx[mine] - self.lo]
+        return self._all_reduce(out)          # every other rank contributed exact zeros: sum == copy
+
+    def _queries(self, s, p, o):
+        both = self.gather_entity_rows(torch.cat([s.long(), o.long()]))
+        n = s.numel()
+        return both[:n], self.rel[p.long()], both[n:]
+
+    # -- full logits ---------------------------------------------------------------------------------
+    def score_sp_po(self, s, p, o) -> torch.Tensor:
+        """[n, 2E] = [score_sp | score_po] (kge_model.py:749-789) assembled from per-shard logits."""
+        s_emb, p_emb, o_emb = self._queries(s, p, o)
+        n = s.numel()
+        loc = torch.zeros((2, n, self.per), dtype=torch.float32, device=self.ent.device)
+        m = self.hi - self.lo
+        if m > 0:
+            loc[0, :, :m] = self.backend.score_1vsN(self.model, "sp_", s_emb, p_emb, self.ent, self.l_norm, self.precision)
+            loc[1, :, :m] = self.backend.score_1vsN(self.model, "_po", o_emb, p_emb, self.ent, self.l_norm, self.precision)
+        if self.world > 1:
+            parts = [torch.empty_like(loc) for _ in range(self.world)]
+            dist.all_gather(parts, loc, group=self.group)
+        else:
+            parts = [loc]
+        sp = torch.cat([q[0] for q in parts], 1)[:, : self.E]
+        po = torch.cat([q[1] for q in parts], 1)[:, : self.E]
+        return torch.cat([sp, po], 1)
+
+    # -- ranking -------------------------------------------------------------------------------------
+    def true_scores(self, s, p, o):
+        """Scores of the true triples, identical on every rank (computed from the exchanged rows)."""
+        s_emb, p_emb, o_emb = self._queries(s, p, o)
+        t = self.backend.score_spo(self.model, s_emb, p_emb, o_emb, self.l_norm)
+        return t, (s_emb, p_emb, o_emb)
+
+    def rank_sp_po(self, s, p, o, filter_sp=None, filter_po=None, rtol=1e-4, atol=1e-5):
+        """(s_rank, s_ties, o_rank, o_ties) over ALL entities; filter_* are this rank's column slices
+        [n, E_local] of the reference's +inf label matrix (eval_entity_ranking.py:287-290,561-566).
+        Integer all-reduce => bit-exact and 8*n bytes per counter instead of moving logits."""
+        t, (s_emb, p_emb, o_emb) = self.true_scores(s, p, o)
+        n = s.numel()
+        dev = self.ent.device
+        counts = torch.zeros((4, n), dtype=torch.int64, device=dev)
+        if self.hi > self.lo:
+            o_rank, o_ties = self.backend.rank_1vsN(self.model, "sp_", s_emb, p_emb, self.ent, t, filter_sp, rtol,
+                                                    atol, self.l_norm, self.precision)
+            s_rank, s_ties = self.backend.rank_1vsN(self.model, "_po", o_emb, p_emb, self.ent, t, filter_po, rtol,
+                                                    atol, self.l_norm, self.precision)
+            counts[0], counts[1], counts[2], counts[3] = s_rank, s_ties, o_rank, o_ties
+        self._all_reduce(counts)
+        return counts[0], counts[1], counts[2], counts[3]
+
+    # -- 1vsAll BCE ------------------------------------------------------------------------------------
+    def loss_1vsall_bce(self, s, p, o, offset: float = 0.0):
+        """(BCE(score_sp, o) + BCE(score_po, s)) / n with sum reductions (train_1vsAll.py:48-82): BCE is
+        additive over columns, so each rank reduces its shard and one scalar is all-reduced."""
+        s_emb, p_emb, o_emb = self._queries(s, p, o)
+        n = s.numel()
+
+        def local(idx):
+            idx = idx.long()
+            l = idx - self.lo
+            return torch.where((idx >= self.lo) & (idx < self.hi), l, torch.full_like(l, -1))
+
+        tot = torch.zeros((), dtype=torch.float32, device=self.ent.device)
+        if self.hi > self.lo:
+            tot = tot + self.backend.bce_1vsN(self.model, "sp_", s_emb, p_emb, self.ent, local(o), offset,
+                                              self.l_norm, self.precision)
+            tot = tot + self.backend.bce_1vsN(self.model, "_po", o_emb, p_emb, self.ent, local(s), offset,
+                                              self.l_norm, self.precision)
+        return self._all_reduce(tot) / n
+
+    # -- top-k -----------------------------------------------------------------------------------------
+    def topk_sp(self, s, p, k: int):
+        """Global top-k objects per (s,p): local top-k on the shard's logits, all-gather of the [n,k]
+        (value, global index) pairs, merge; ties broken towards the lowest entity id."""
+        s_emb = self.gather_entity_rows(s)
+        p_emb = self.rel[p.long()]
+        n = s.numel()
+        dev = self.ent.device
+        vals = torch.full((n, k), float("-inf"), dtype=torch.float32, device=dev)
+        idxs = torch.full((n, k), self.E, dtype=torch.int64, device=dev)
+        m = self.hi - self.lo
+        if m > 0:
+            loc = self.backend.score_1vsN(self.model, "sp_", s_emb, p_emb, self.ent, self.l_norm, self.precision)
+            kk = min(k, m)
+            v, i = _topk_lowest_index(loc, kk)
+            vals[:, :kk], idxs[:, :kk] = v, i + self.lo
+        if self.world > 1:
+            vs = [torch.empty_like(vals) for _ in range(self.world)]
+            is_ = [torch.empty_like(idxs) for _ in range(self.world)]
+            dist.all_gather(vs, vals, group=self.group)
+            dist.all_gather(is_, idxs, group=self.group)
+            vals, idxs = torch.cat(vs, 1), torch.cat(is_, 1)
+        v, pos = _topk_lowest_index(vals, k, idxs)
+        return v, torch.gather(idxs, 1, pos)
+
+
+def _topk_lowest_index(values: torch.Tensor, k: int, ids: Optional[torch.Tensor] = None):
+    """top-k by value, ties broken by the lowest id (column position if ids is None): a stable sort
+    on -value after ordering columns by id gives a deterministic, shard-count-independent result."""
+    if ids is None:
+        order = torch.sort(-values, dim=1, stable=True).indices[:, :k]
+        return torch.gather(values, 1, order), order
+    by_id = torch.sort(ids, dim=1, stable=True).indices
+    v = torch.gather(values, 1, by_id)
+    order = torch.sort(-v, dim=1, stable=True).indices[:, :k]
+    pos = torch.gather(by_id, 1, order)
+    return torch.gather(values, 1, pos), pos

@@ -1,0 +1,34 @@
+"""Sharded model on the GPU backend.  world=1 runs under plain pytest; the multi-rank case is
+launched by scripts/sharded_check.py under torchrun."""
+import pytest
+import torch
+
+from oracle import kge_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("model,D", [("transe", 64), ("complex", 64)])
+def test_sharded_world1_matches_oracle(model, D):
+    from kge_b200.sharded import ShardedKgeModel
+
+    E, R, n = 3001, 5, 40
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.5)
+    tri = orc.make_triples(E, R, n)
+    m = ShardedKgeModel(model, ent.cuda(), rel.cuda(), E, rank=0, world=1)
+    t = tri.cuda()
+    s, p, o = t[:, 0], t[:, 1], t[:, 2]
+    full = m.score_sp_po(s, p, o).cpu()
+    ref = orc.score_sp_po(model, ent, rel, tri[:, 0], tri[:, 1], tri[:, 2])
+    assert float((full - ref).abs().max()) <= 1e-4 * float(ref.pow(2).mean().sqrt())
+    s_rank, s_ties, o_rank, o_ties = m.rank_sp_po(s, p, o)
+    tt, _ = m.true_scores(s, p, o)
+    rr, ti = orc.ranks_and_ties(full[:, :E], tt.cpu())
+    # fused rank kernel vs rank arithmetic on the dense kernel's scores: identical kernels => exact
+    assert torch.equal(o_rank.cpu(), rr) and torch.equal(o_ties.cpu(), ti)
+    got = float(m.loss_1vsall_bce(s, p, o))
+    want = float(orc.train_1vsall_forward(model, ent, rel, tri, "bce"))
+    assert abs(got - want) <= 1e-4 * abs(want)
+    v, i = m.topk_sp(s, p, 5)
+    order = torch.sort(-full[:, :E], dim=1, stable=True).indices[:, :5]
+    assert torch.equal(i.cpu(), order)
