@@ -107,10 +107,22 @@ def _cpu_reference_value(steps: int, warmup: int, budget_s: float = 25.0):
     from oracle import kge_oracle as orc
 
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     ent, rel = orc.make_tables(MODEL, E, R, D, sigma=1.0)
     tri = orc.make_triples(E, R, N_BATCH, seed=0)
     with torch.no_grad():
+        # give the reference its best shot: oversubscribing a many-core host slows MKL/ATen down, so
+        # probe a few thread counts (1 untimed + 1 timed step each) and keep the fastest
+        best_t, best_thr = None, cores
+        for thr in sorted({cores, max(1, cores // 2), 32, 16, 8} & set(range(1, cores + 1)), reverse=True):
+            torch.set_num_threads(thr)
+            orc.train_1vsall_forward(MODEL, ent, rel, tri, LOSS)
+            t0 = time.perf_counter()
+            orc.train_1vsall_forward(MODEL, ent, rel, tri, LOSS)
+            dt = time.perf_counter() - t0
+            if best_t is None or dt < best_t:
+                best_t, best_thr = dt, thr
+        cores = best_thr
+        torch.set_num_threads(cores)
         for _ in range(max(1, min(warmup, 2))):
             orc.train_1vsall_forward(MODEL, ent, rel, tri, LOSS)
         times, t_begin = [], time.perf_counter()
@@ -123,7 +135,8 @@ def _cpu_reference_value(steps: int, warmup: int, budget_s: float = 25.0):
     per = sum(times) / len(times)
     return {"value": 2.0 * N_BATCH * E / per, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{len(times)} x one 1vsAll forward step (n={N_BATCH}, E={E}, D={D}, BCE) with the "
-                      f"oracle's torch-CPU restatement of the reference path, {cores} threads",
+                      f"oracle's torch-CPU restatement of the reference path, {cores} threads "
+                      f"(fastest of the probed thread counts on {os.cpu_count()} host cores)",
             "ms_per_step": per * 1e3}, len(times)
 
 
@@ -257,7 +270,7 @@ def run_ours(args):
                 "executed-pipe fraction = 6 x frac",
         "tensor_pipe_frac_executed": 6.0 * achieved / peak,
     }
-    cpu, _ = _cpu_reference_value(20, 1, budget_s=20.0)
+    cpu, _ = _cpu_reference_value(40, 1, budget_s=15.0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -282,7 +295,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
