@@ -74,7 +74,7 @@ __device__ __forceinline__ void fetch8(const float* __restrict__ rowp, bool row_
 }
 
 template <int PAIR, int EPI, bool VEC>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT)   // (NT, 2) was measured: spills in the fused epilogues, no net gain
 pairwise_simt_kernel(const float* __restrict__ Q, int64_t ldq, int64_t nq, Rows cand, int col_off,
                      int K, float p_norm, int col_tiles, EpiParams P) {
   __shared__ __align__(16) float As[2][BK][LDS_];
