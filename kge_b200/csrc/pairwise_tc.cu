@@ -22,7 +22,7 @@
 //   warp 1      MMA issuer     (one elected lane)     empty[s]  <- tcgen05.commit ; tmem_full[b]
 //   warps 4-11  epilogue       tcgen05.ld -> regs -> {transposed coalesced store | BCE | KL | rank}
 //                              (2 warps per TMEM lane quadrant, each takes 128 of the 256 columns)
-//   warps 12-15 splitters      split[s] <- one arrival per warp
+//   warps 2-3 / 12-15 splitters (query tile / table tile)      split[s] <- one arrival per warp
 // Tile = 128 queries (UMMA M, TMEM lanes) x 256 entities (UMMA N, TMEM columns), K in chunks of 32
 // floats (one 128-byte swizzle atom), 2 smem stages of 96 KB, 2 TMEM accumulators of 256 columns
 // so the epilogue of tile i overlaps the MMAs of tile i+1.  TMEM lane = query row, so every
@@ -52,12 +52,19 @@ struct TcParams {
   int64_t nq, m;
   int K;            // reduction length (floats)
   int q_tiles, e_tiles, echunks;
+  int q_groups;     // work is (q group) x (e chunk): a group is one q tile, or a pair of q tiles when the
+                    // table tile is multicast across a 2-CTA cluster (MC)
   int tn;           // entities per tile actually used (multiple of 16, <= TN): chosen per problem so that
                     // ceil(tiles / SMs) * tn — the makespan in columns — is minimal
   EpiParams epi;
 };
 
-template <int EPI, int PASSES>
+// MC: launched as clusters of 2 CTAs that walk the SAME entity tiles with DIFFERENT query tiles; each CTA
+// fetches half of every table tile and TMA-multicasts it into both CTAs' shared memory, so the table
+// bytes cross the L2->SM fabric once per pair (-33 % TMA traffic per SM: the TMA phase is on the
+// critical path of the 2-stage pipeline).  MMAs stay cta_group::1 and per-CTA; only the stage-free
+// signal is shared (each CTA's commit arrives on both CTAs' empty barriers).
+template <int EPI, int PASSES, bool MC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmT,
                    const TcParams prm) {
@@ -74,15 +81,18 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = (prm.K + TK - 1) / TK;
-  const int total_work = prm.q_tiles * prm.echunks;
+  const int total_work = prm.q_groups * prm.echunks;
+  const uint32_t rank = MC ? ptx::cluster_ctarank() : 0u;
+  const int wstart = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int wstep = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmQ);
     ptx::prefetch_tensormap(&tmT);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&split[s], SPLIT_WARPS);
-      ptx::mbar_init(&empty[s], 1);
+      ptx::mbar_init(&split[s], SPLIT_WARPS + 2);   // B splitters (4 warps) + A splitters (2 warps)
+      ptx::mbar_init(&empty[s], MC ? 2 : 1);   // MC: both CTAs of the pair must have retired the stage
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tfull[b], 1);
@@ -92,15 +102,16 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
   ptx::tc_fence_before();
-  __syncthreads();
+  if (MC) ptx::cluster_sync_all(); else __syncthreads();   // MC: the peer's barriers must be initialised too
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   auto stage_ptr = [&](int s) { return smem + s * STAGE_BYTES; };
   // e-tile range of work item w
   auto work_range = [&](int w, int& qt, int& et0, int& et1, int& ec) {
-    qt = w / prm.echunks;
-    ec = w - qt * prm.echunks;
+    const int qg = w / prm.echunks;
+    qt = MC ? 2 * qg + (int)rank : qg;
+    ec = w - qg * prm.echunks;
     const int base = prm.e_tiles / prm.echunks, rem = prm.e_tiles % prm.echunks;
     et0 = ec * base + (ec < rem ? ec : rem);
     et1 = et0 + base + (ec < rem ? 1 : 0);
@@ -110,18 +121,25 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ================================ TMA producer =========================================
     if (lane == 0) {
       uint32_t c = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = wstart; w < total_work; w += wstep) {
         int qt, et0, et1, ec;
         work_range(w, qt, et0, et1, ec);
         for (int et = et0; et < et1; ++et) {
           for (int kc = 0; kc < nk; ++kc, ++c) {
             const int s = c % STAGES;
             const uint32_t ph = (c / STAGES) & 1;
-            ptx::mbar_wait(&empty[s], ph ^ 1);
+            if (MC) ptx::mbar_wait_cluster(&empty[s], ph ^ 1); else ptx::mbar_wait(&empty[s], ph ^ 1);
             uint8_t* sp = stage_ptr(s);
             ptx::mbar_arrive_expect_tx(&full[s], A_BYTES + prm.tn * TK * 4);
             ptx::tma_load_2d(sp, &tmQ, &full[s], kc * TK, qt * TM);                 // raw queries
-            ptx::tma_load_2d(sp + 2 * A_BYTES, &tmT, &full[s], kc * TK, et * prm.tn);   // raw table tile
+            if (MC) {
+              // this CTA's half of the table tile, delivered to both CTAs (box = tn/2 rows)
+              const int hrows = prm.tn >> 1;
+              ptx::tma_load_2d_mc(sp + 2 * A_BYTES + (int)rank * hrows * TK * 4, &tmT, &full[s], kc * TK,
+                                  et * prm.tn + (int)rank * hrows, (uint16_t)0b11);
+            } else {
+              ptx::tma_load_2d(sp + 2 * A_BYTES, &tmT, &full[s], kc * TK, et * prm.tn);   // raw table tile
+            }
           }
         }
       }
@@ -131,7 +149,7 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (lane == 0) {
       const uint32_t idesc = ptx::umma_idesc_tf32(TM, prm.tn);
       uint32_t c = 0, it = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = wstart; w < total_work; w += wstep) {
         int qt, et0, et1, ec;
         work_range(w, qt, et0, et1, ec);
         for (int et = et0; et < et1; ++et, ++it) {
@@ -162,18 +180,22 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 ptx::umma_tf32(d_tmem, ptx::umma_desc_sw128(a_hi + k4 * 32), ptx::umma_desc_sw128(b_lo + k4 * 32), idesc, 1u);
               }
             }
-            ptx::umma_commit(&empty[s]);           // smem stage free once these MMAs retire
+            if (MC) ptx::umma_commit_mc(&empty[s], (uint16_t)0b11);   // frees the stage in BOTH CTAs
+            else    ptx::umma_commit(&empty[s]);                      // smem stage free once these MMAs retire
           }
           ptx::umma_commit(&tfull[b]);             // accumulator complete
         }
       }
     }
-  } else if (warp >= 12) {
+  } else if (warp >= 12 || warp == 2 || warp == 3) {
     // ================================ splitters =============================================
+    // warps 12-15 derive T_lo from the raw table tile, warps 2-3 derive Q_lo from the raw query tile
+    // (16 float4 per thread each: the split phase is on the critical path with only two stages)
     if (PASSES == 3) {
-      const int t = threadIdx.x - 12 * 32;  // 0..127
+      const bool is_b = warp >= 12;
+      const int t = is_b ? threadIdx.x - 12 * 32 : threadIdx.x - 2 * 32;
       uint32_t c = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = wstart; w < total_work; w += wstep) {
         int qt, et0, et1, ec;
         work_range(w, qt, et0, et1, ec);
         for (int et = et0; et < et1; ++et) {
@@ -183,8 +205,8 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             ptx::mbar_wait(&full[s], ph);
             // raw tile = hi operand; write lo next to it, for the table tile AND the query tile
             const uint32_t sp = ptx::smem_u32(stage_ptr(s));
-            tc::split_tile<A_BYTES, SPLIT_WARPS * 32>(sp, sp + A_BYTES, t);
-            tc::split_tile<B_BYTES, SPLIT_WARPS * 32>(sp + 2 * A_BYTES, sp + 2 * A_BYTES + B_BYTES, t);
+            if (is_b) tc::split_tile<B_BYTES, SPLIT_WARPS * 32>(sp + 2 * A_BYTES, sp + 2 * A_BYTES + B_BYTES, t);
+            else      tc::split_tile<A_BYTES, 2 * 32>(sp, sp + A_BYTES, t);
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&split[s]);
@@ -199,7 +221,7 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float* my_stg = stg + (warp - 4) * 32 * STG_LD;
     const EpiParams& P = prm.epi;
     uint32_t it = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+    for (int w = wstart; w < total_work; w += wstep) {
       int qt, et0, et1, ec;
       work_range(w, qt, et0, et1, ec);
       const int64_t row = (int64_t)qt * TM + quad * 32 + lane;   // this thread's query row
@@ -228,7 +250,7 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (MC) ptx::cluster_sync_all(); else __syncthreads();   // MC: the peer may still signal this CTA's barriers
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -237,45 +259,69 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // ---------------------------------------------------------------------------------------------
 using tc::num_sms;
 
-void plan(int64_t nq, int64_t m, int& q_tiles, int& e_tiles, int& echunks, int& tn) {
+// mc: pairs of q tiles share table tiles (2-CTA clusters); groups = q pairs, CTAs available = sms/2 clusters
+void plan(int64_t nq, int64_t m, bool mc, int& q_tiles, int& q_groups, int& e_tiles, int& echunks, int& tn) {
   q_tiles = (int)((nq + TM - 1) / TM);
   if (q_tiles < 1) q_tiles = 1;
-  const int sms = num_sms();
+  q_groups = mc ? (q_tiles + 1) / 2 : q_tiles;
+  const int units = mc ? num_sms() / 2 : num_sms();
   // pick the tile width (multiple of 16 in [128, 256]) minimising the per-SM makespan in columns
   int64_t best_cost = -1;
   tn = TN;
   for (int cand = TN; cand >= 128; cand -= 16) {
     const int64_t et = (m + cand - 1) / cand;
-    int per = sms / q_tiles; if (per < 1) per = 1; if (per > et) per = (int)et;
-    const int64_t tiles_per_cta = (et + per - 1) / per;                 // largest e-range of a work item
-    const int64_t waves = ((int64_t)q_tiles * per + sms - 1) / sms;     // work items per CTA
+    int per = units / q_groups; if (per < 1) per = 1; if (per > et) per = (int)et;
+    const int64_t tiles_per_cta = (et + per - 1) / per;                   // largest e-range of a work item
+    const int64_t waves = ((int64_t)q_groups * per + units - 1) / units;  // work items per CTA
     const int64_t cost = waves * tiles_per_cta * cand + tiles_per_cta * 24;   // + per-tile fixed overhead
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; tn = cand; }
   }
   e_tiles = (int)((m + tn - 1) / tn);
-  int per = sms / q_tiles;
+  int per = units / q_groups;
   if (per < 1) per = 1;
   if (per > e_tiles) per = e_tiles;
   echunks = per;
 }
 
-template <int EPI>
-int launch_e(int passes, const CUtensorMap& a, const CUtensorMap& c, const TcParams& prm, int grid,
-             cudaStream_t st) {
-  cudaError_t e;
+bool use_mc(int64_t nq) {
+  // Table-tile multicast across 2-CTA clusters is parity-green and cuts L2->SM traffic by a third, but
+  // measured no faster on B200 (the 1-CTA kernel is bound by shared-memory bandwidth: UMMA operand
+  // reads 144 KB + TMA writes 46 KB + split 92 KB per K-chunk ~ 2200 of the 2750 cycles at 128 B/clk).
+  // Off by default; B200KGE_TC_MC=1 enables it.
+  const char* e = getenv("B200KGE_TC_MC");
+  return e && atoi(e) != 0 && nq > TM;
+}
+
+template <int EPI, int PASSES, bool MC>
+int launch_k(const CUtensorMap& a, const CUtensorMap& c, const TcParams& prm, int grid, cudaStream_t st) {
+  auto kern = pairwise_tc_kernel<EPI, PASSES, MC>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pairwise_tc_kernel)");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = MC ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   profile_begin(st);
-  if (passes == 3) {
-    e = cudaFuncSetAttribute(pairwise_tc_kernel<EPI, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pairwise_tc_kernel)");
-    pairwise_tc_kernel<EPI, 3><<<grid, NTHREADS, SMEM_BYTES, st>>>(a, c, prm);
-  } else {
-    e = cudaFuncSetAttribute(pairwise_tc_kernel<EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pairwise_tc_kernel)");
-    pairwise_tc_kernel<EPI, 1><<<grid, NTHREADS, SMEM_BYTES, st>>>(a, c, prm);
-  }
+  e = cudaLaunchKernelEx(&cfg, kern, a, c, prm);
   profile_end(st);
-  B2K_LAUNCH_CHECK("pairwise_tc_kernel");
-  return 0;
+  count_launch();
+  if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(pairwise_tc_kernel)");
+  return check_cuda(cudaGetLastError(), "pairwise_tc_kernel");
+}
+
+template <int EPI>
+int launch_e(int passes, bool mc, const CUtensorMap& a, const CUtensorMap& c, const TcParams& prm, int grid,
+             cudaStream_t st) {
+  if (passes == 3) return mc ? launch_k<EPI, 3, true>(a, c, prm, grid, st) : launch_k<EPI, 3, false>(a, c, prm, grid, st);
+  return mc ? launch_k<EPI, 1, true>(a, c, prm, grid, st) : launch_k<EPI, 1, false>(a, c, prm, grid, st);
 }
 
 }  // namespace
@@ -290,8 +336,8 @@ bool tc_supported(int pair_op, int K, const Rows& cand, int col_off) {
 }
 
 int tc_nchunks(int64_t nq, int64_t m) {
-  int qt, et, ec, tn;
-  plan(nq, m, qt, et, ec, tn);
+  int qt, qg, et, ec, tn;
+  plan(nq, m, use_mc(nq), qt, qg, et, ec, tn);
   return 2 * ec;
 }
 
@@ -299,22 +345,24 @@ int launch_pairwise_tc(int epi_kind, int passes, const float* Q, int64_t ldq,
                        int64_t nq, const float* T, int64_t ldt, int64_t m, int K,
                        const EpiParams& P, cudaStream_t st) {
   if (nq == 0 || m == 0) return 0;
+  const bool mc = use_mc(nq);
   CUtensorMap mQ, mT;
   int rc;
   if ((rc = tc::make_map(&mQ, Q, nq, K, ldq, TK, TM))) return rc;
   TcParams prm;
   prm.nq = nq; prm.m = m; prm.K = K;
-  plan(nq, m, prm.q_tiles, prm.e_tiles, prm.echunks, prm.tn);
-  if ((rc = tc::make_map(&mT, T, m, K, ldt, TK, prm.tn))) return rc;
+  plan(nq, m, mc, prm.q_tiles, prm.q_groups, prm.e_tiles, prm.echunks, prm.tn);
+  if ((rc = tc::make_map(&mT, T, m, K, ldt, TK, mc ? prm.tn / 2 : prm.tn))) return rc;
   prm.epi = P;
   prm.epi.nchunks = 2 * prm.echunks;   // two epilogue warps (column halves) per row
-  const int total = prm.q_tiles * prm.echunks;
-  const int grid = total < num_sms() ? total : num_sms();
+  const int total = prm.q_groups * prm.echunks;
+  const int units = mc ? num_sms() / 2 : num_sms();
+  const int grid = (mc ? 2 : 1) * (total < units ? total : units);
   switch (epi_kind) {
-    case EPI_STORE: return launch_e<EPI_STORE>(passes, mQ, mT, prm, grid, st);
-    case EPI_BCE:   return launch_e<EPI_BCE>(passes, mQ, mT, prm, grid, st);
-    case EPI_KL:    return launch_e<EPI_KL>(passes, mQ, mT, prm, grid, st);
-    case EPI_RANK:  return launch_e<EPI_RANK>(passes, mQ, mT, prm, grid, st);
+    case EPI_STORE: return launch_e<EPI_STORE>(passes, mc, mQ, mT, prm, grid, st);
+    case EPI_BCE:   return launch_e<EPI_BCE>(passes, mc, mQ, mT, prm, grid, st);
+    case EPI_KL:    return launch_e<EPI_KL>(passes, mc, mQ, mT, prm, grid, st);
+    case EPI_RANK:  return launch_e<EPI_RANK>(passes, mc, mQ, mT, prm, grid, st);
   }
   set_error("bad epilogue kind %d", epi_kind);
   return B200KGE_ERR_INVALID;
