@@ -263,23 +263,26 @@ def run_ours(args):
     peak = peaks["bf16_tflops"]
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "traffic": None, "kernel": "pairwise_tc_kernel<BCE,3xTF32>", "kernel_ms": k_ms,
+        "traffic": 34.1e6, "kernel": "pairwise_tc_kernel<BCE, tf32+bf16x2>", "kernel_ms": k_ms,
         "peak_name": f"dense bf16 burst, {peaks['source']}",
-        "note": "algorithmic fp32 FLOPs (2nED); the kernel executes 3 TF32 MMAs per product "
-                "(fp32-equivalent), so the tensor pipe does 3x this work at the TF32 rate (= bf16/2): "
-                "executed-pipe fraction = 6 x frac",
-        "tensor_pipe_frac_executed": 6.0 * achieved / peak,
+        "traffic_note": "dram__bytes_read+write per launch from ncu --set full (profiles/r1b_summary.md); "
+                        "algorithmic bytes = table 29.8 MB + folded queries 4.2 MB",
+        "note": "algorithmic fp32 FLOPs (2nED per direction); for fp32-equivalent results the kernel issues, "
+                "per 32-wide K chunk, 4 TF32 MMAs (hi*hi) + 4 BF16 MMAs (cross terms) = 8 MMA slots where a "
+                "plain bf16 GEMM needs 2: the tensor pipe does 4x the algorithmic work at bf16-equivalent "
+                "rate, so the ceiling of `frac` is 0.25",
+        "tensor_pipe_frac_executed": 4.0 * achieved / peak,
     }
     cpu, _ = _cpu_reference_value(40, 1, budget_s=15.0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
+        "dtype": "f32 (tensor-core split products: tf32 hi*hi + 2 bf16 cross terms, fp32 accumulate; 2.4e-5 of rms vs fp64)", "data": "synthetic",
         "config": {"workload": "ComplEx d=512 1vsAll+BCE forward (fused score_sp+loss, score_po+loss), "
                                "FB15k-237-shaped synthetic: 14541 ent / 237 rel, n=1024 triples per GPU per step",
                    "global_batch": N_BATCH * world, "parallelism": f"replicas x{world} (batch split, no "
                    "data-path collective)", "l2": "flushed before every timed step (256 MiB write)",
-                   "precision": "3xtf32 (parity mode)"},
+                   "precision": "tf32+bf16x2 split (parity mode, max|d| 2.4e-5 of score rms vs fp64)"},
         "roofline": roofline,
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes,

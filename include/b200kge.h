@@ -66,10 +66,12 @@ typedef enum {
 
 /* Which kernel family computes dot-product scorers. */
 typedef enum {
-  B200KGE_PREC_AUTO = 0,   /* tcgen05 3xTF32 when the shape allows it, else fp32 SIMT           */
+  B200KGE_PREC_AUTO = 0,   /* tcgen05 mixed mode (TF32_BF16X2) when the shape allows it, else fp32 SIMT */
   B200KGE_PREC_FP32 = 1,   /* CUDA-core fp32 FFMA (bit-for-bit fp32 products)                    */
   B200KGE_PREC_3XTF32 = 2, /* tcgen05 tensor cores, hi/lo split, fp32-equivalent (~3e-6 of rms)  */
-  B200KGE_PREC_TF32 = 3    /* tcgen05 single pass (~1e-3 of rms; does NOT meet the 1e-4 bar)     */
+  B200KGE_PREC_TF32 = 3,   /* tcgen05 single pass (~4e-3 of rms; does NOT meet the 1e-4 bar)     */
+  B200KGE_PREC_TF32_BF16X2 = 4 /* tf32 hi*hi + two bf16 cross terms: 8 MMAs per 32-wide K chunk instead
+                              of 12, operand error ~2^-20 (below the accumulator's)               */
 } b200kge_precision;
 
 typedef enum {

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libb200kge.so")
 # enums (include/b200kge.h)
 MODELS = {"complex": 0, "distmult": 1, "simple": 2, "cp": 3, "rescal": 4, "transe": 5, "rotate": 6}
 SP_, _PO = 0, 1
-PREC = {"auto": 0, "fp32": 1, "3xtf32": 2, "tf32": 3}
+PREC = {"auto": 0, "fp32": 1, "3xtf32": 2, "tf32": 3, "tf32+bf16x2": 4}
 LOSS = {"bce": 1, "kl": 2}
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE, ERR_NO_DEVICE = -1, -2, -3, -4, -5
 

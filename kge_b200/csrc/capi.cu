@@ -114,7 +114,7 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
       if (!ok) { set_error("tensor-core path needs K>=32, 16-byte aligned tables with ld%%4==0"); return B200KGE_ERR_UNSUPPORTED; }
       use_tc = true;
     }
-  } else if (precision == B200KGE_PREC_3XTF32 || precision == B200KGE_PREC_TF32) {
+  } else if (precision == B200KGE_PREC_3XTF32 || precision == B200KGE_PREC_TF32 || precision == B200KGE_PREC_TF32_BF16X2) {
     if (f0.pair_op != PAIR_DOT) { set_error("tensor-core precision modes apply to dot-product scorers only"); return B200KGE_ERR_UNSUPPORTED; }
   }
 
@@ -133,7 +133,9 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
 
   if (used_tc_out) *used_tc_out = use_tc ? 1 : 0;
   if (use_tc) {
-    const int passes = (precision == B200KGE_PREC_TF32) ? 1 : 3;
+    // AUTO = mixed mode (tf32 hi*hi + bf16 cross terms): measured both more accurate (2.4e-5 vs 3.0e-5 of
+    // rms: fewer accumulation steps) and faster (8 MMAs per K-chunk instead of 12) than 3xTF32 on B200
+    const int passes = (precision == B200KGE_PREC_TF32) ? 1 : (precision == B200KGE_PREC_3XTF32 ? 3 : 2);
     int rc = 0;
     const float* Q = B.Qpre;
     if (!Q) {
@@ -157,7 +159,7 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
     // kernel at every batch size once the epilogue stopped being the bottleneck
     // (profiles/r1_notes.md).  B200KGE_TC_VERSION=2 selects the pair kernel (kept for experiments).
     const char* env_v = getenv("B200KGE_TC_VERSION");
-    const bool pair = env_v && atoi(env_v) == 2;
+    const bool pair = env_v && atoi(env_v) == 2 && passes != 2;   // the mixed mode exists in the 1-CTA kernel only
     const int nch = pair ? tc2_nchunks(nq, m) : tc_nchunks(nq, m);
     if (epi_kind == EPI_BCE || epi_kind == EPI_KL) {
       const int F = (epi_kind == EPI_BCE) ? 2 : 5;

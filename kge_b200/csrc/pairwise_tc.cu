@@ -179,6 +179,19 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 ptx::umma_tf32(d_tmem, ptx::umma_desc_sw128(a_lo + k4 * 32), ptx::umma_desc_sw128(b_hi + k4 * 32), idesc, 1u);
                 ptx::umma_tf32(d_tmem, ptx::umma_desc_sw128(a_hi + k4 * 32), ptx::umma_desc_sw128(b_lo + k4 * 32), idesc, 1u);
               }
+            } else if (PASSES == 2) {
+              // cross terms in bf16 (K = 16 per MMA, 64-B swizzled tiles written by the splitters):
+              //   Q_lo16 * T_hi16 + Q_hi16 * T_lo16        (operand error ~2^-20, below the accumulator's)
+              ptx::mbar_wait(&split[s], ph);
+              ptx::tc_fence_after();
+              const uint32_t idesc16 = ptx::umma_idesc_bf16(TM, prm.tn);
+              const uint32_t a16h = a_hi + A_BYTES, a16l = a16h + A_BYTES / 2;
+              const uint32_t b16h = b_hi + B_BYTES, b16l = b16h + B_BYTES / 2;
+#pragma unroll
+              for (int k2 = 0; k2 < TK / 16; ++k2) {
+                ptx::umma_bf16(d_tmem, ptx::umma_desc_sw64(a16l + k2 * 32), ptx::umma_desc_sw64(b16h + k2 * 32), idesc16, 1u);
+                ptx::umma_bf16(d_tmem, ptx::umma_desc_sw64(a16h + k2 * 32), ptx::umma_desc_sw64(b16l + k2 * 32), idesc16, 1u);
+              }
             }
             if (MC) ptx::umma_commit_mc(&empty[s], (uint16_t)0b11);   // frees the stage in BOTH CTAs
             else    ptx::umma_commit(&empty[s]);                      // smem stage free once these MMAs retire
@@ -191,7 +204,7 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ================================ splitters =============================================
     // warps 12-15 derive T_lo from the raw table tile, warps 2-3 derive Q_lo from the raw query tile
     // (16 float4 per thread each: the split phase is on the critical path with only two stages)
-    if (PASSES == 3) {
+    if (PASSES != 1) {
       const bool is_b = warp >= 12;
       const int t = is_b ? threadIdx.x - 12 * 32 : threadIdx.x - 2 * 32;
       uint32_t c = 0;
@@ -205,8 +218,15 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             ptx::mbar_wait(&full[s], ph);
             // raw tile = hi operand; write lo next to it, for the table tile AND the query tile
             const uint32_t sp = ptx::smem_u32(stage_ptr(s));
-            if (is_b) tc::split_tile<B_BYTES, SPLIT_WARPS * 32>(sp + 2 * A_BYTES, sp + 2 * A_BYTES + B_BYTES, t);
-            else      tc::split_tile<A_BYTES, 2 * 32>(sp, sp + A_BYTES, t);
+            if (PASSES == 3) {
+              if (is_b) tc::split_tile<B_BYTES, SPLIT_WARPS * 32>(sp + 2 * A_BYTES, sp + 2 * A_BYTES + B_BYTES, t);
+              else      tc::split_tile<A_BYTES, 2 * 32>(sp, sp + A_BYTES, t);
+            } else {
+              // mixed mode: the fp32 lo buffers hold two bf16 tiles (hi16 | lo16) instead
+              if (is_b) tc::split_tile_bf16<TN, SPLIT_WARPS * 32>(sp + 2 * A_BYTES, sp + 2 * A_BYTES + B_BYTES,
+                                                                  sp + 2 * A_BYTES + B_BYTES + B_BYTES / 2, t);
+              else      tc::split_tile_bf16<TM, 2 * 32>(sp, sp + A_BYTES, sp + A_BYTES + A_BYTES / 2, t);
+            }
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&split[s]);
@@ -321,6 +341,7 @@ template <int EPI>
 int launch_e(int passes, bool mc, const CUtensorMap& a, const CUtensorMap& c, const TcParams& prm, int grid,
              cudaStream_t st) {
   if (passes == 3) return mc ? launch_k<EPI, 3, true>(a, c, prm, grid, st) : launch_k<EPI, 3, false>(a, c, prm, grid, st);
+  if (passes == 2) return mc ? launch_k<EPI, 2, true>(a, c, prm, grid, st) : launch_k<EPI, 2, false>(a, c, prm, grid, st);
   return mc ? launch_k<EPI, 1, true>(a, c, prm, grid, st) : launch_k<EPI, 1, false>(a, c, prm, grid, st);
 }
 

@@ -52,6 +52,44 @@ __device__ __forceinline__ void split_tile(uint32_t src, uint32_t dst, int t) {
   for (int i = 0; i < PER; ++i) sts128(dst + (uint32_t)(t + i * NTHR) * 16u, split_lo4(v[i]));
 }
 
+// Mixed mode (tf32 hi*hi + bf16 cross terms): from a raw fp32 K-major tile [ROWS][32] in the 128-B
+// swizzled layout, derive two bf16 K-major tiles [ROWS][32] in the 64-B swizzled layout:
+//   hi16 = bf16_rn(x)            (hi operand of the cross terms)
+//   lo16 = bf16_rn(x - trunc_tf32(x))   (remainder w.r.t. what the tf32 MMA uses as hi)
+// One item = (row r, group c of 8 consecutive k): reads fp32 16-B chunks 2c, 2c+1 of row r (physical
+// chunk = logical ^ (r & 7)), writes bf16 16-B chunk c of row r (physical = c ^ ((r >> 1) & 3)).
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half <- a, high half <- b
+  return r;
+}
+template <int ROWS, int NTHR>
+__device__ __forceinline__ void split_tile_bf16(uint32_t src, uint32_t dst_hi, uint32_t dst_lo, int t) {
+  constexpr int ITEMS = ROWS * 4, PER = ITEMS / NTHR;
+  static_assert(PER * NTHR == ITEMS, "tile must divide evenly");
+  float4 v0[PER], v1[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int it = t + i * NTHR, r = it >> 2, c = it & 3;
+    const uint32_t rowb = src + (uint32_t)r * 128u;
+    v0[i] = lds128(rowb + (uint32_t)(((2 * c) ^ (r & 7)) * 16));
+    v1[i] = lds128(rowb + (uint32_t)(((2 * c + 1) ^ (r & 7)) * 16));
+  }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int it = t + i * NTHR, r = it >> 2, c = it & 3;
+    const float x[8] = {v0[i].x, v0[i].y, v0[i].z, v0[i].w, v1[i].x, v1[i].y, v1[i].z, v1[i].w};
+    float lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) lo[k] = x[k] - __uint_as_float(__float_as_uint(x[k]) & 0xFFFFE000u);
+    const uint32_t off = (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) * 16);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_hi + off), "r"(pack_bf16x2(x[0], x[1])),
+                 "r"(pack_bf16x2(x[2], x[3])), "r"(pack_bf16x2(x[4], x[5])), "r"(pack_bf16x2(x[6], x[7])) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_lo + off), "r"(pack_bf16x2(lo[0], lo[1])),
+                 "r"(pack_bf16x2(lo[2], lo[3])), "r"(pack_bf16x2(lo[4], lo[5])), "r"(pack_bf16x2(lo[6], lo[7])) : "memory");
+  }
+}
+
 // Epilogue.  TMEM lane = query row, so one thread owns one row and walks 32-column chunks.
 // The first version fed every element through the generic epi_elem functor: ~43 SASS instructions
 // per element (64-bit bounds/label compares, per-element null checks of optional operands) on ONE

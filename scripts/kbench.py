@@ -93,7 +93,7 @@ def case_parity():
     rms = float(ref.pow(2).mean().sqrt())
     e, r, t = ent.to(dev), rel.to(dev), tri.to(dev)
     out = {}
-    for prec in ("fp32", "3xtf32", "tf32"):
+    for prec in ("fp32", "3xtf32", "tf32+bf16x2", "tf32"):
         got = engine.score_1vsN(model, "sp_", e, r, e, t[:, 0].contiguous(), t[:, 1].contiguous(), None, 1.0, prec)
         out[prec] = float((got.cpu().double() - ref).abs().max()) / rms
     print(json.dumps({"case": "parity vs fp64 (max|d|/rms)", "split_lo_only": os.environ.get("B200KGE_SPLIT_LO_ONLY", "0"), **out}), flush=True)
@@ -105,6 +105,11 @@ CASES = {
     "tc3_store": lambda: case_1vsall("complex", 14541, 237, 512, 1024, "3xtf32", "store"),
     "tc3_kl": lambda: case_1vsall("complex", 14541, 237, 512, 1024, "3xtf32", "kl"),
     "tc3_store_n512": lambda: case_1vsall("complex", 14541, 237, 512, 512, "3xtf32", "store"),
+    "mix_step": lambda: case_1vsall("complex", 14541, 237, 512, 1024, "tf32+bf16x2", "step"),
+    "mix_store": lambda: case_1vsall("complex", 14541, 237, 512, 1024, "tf32+bf16x2", "store"),
+    "mix_kl": lambda: case_1vsall("complex", 14541, 237, 512, 1024, "tf32+bf16x2", "kl"),
+    "mix_step_n4096": lambda: case_1vsall("complex", 14541, 237, 512, 4096, "tf32+bf16x2", "step"),
+    "mix_rescal": lambda: case_1vsall("rescal", 123182, 37, 200, 1024, "tf32+bf16x2", "step"),
     "tc1_step": lambda: case_1vsall("complex", 14541, 237, 512, 1024, "tf32", "step"),
     "tc1_store": lambda: case_1vsall("complex", 14541, 237, 512, 1024, "tf32", "store"),
     "fp32_step": lambda: case_1vsall("complex", 14541, 237, 512, 1024, "fp32", "step"),

@@ -74,6 +74,7 @@ def test_golden_scores_tensor_core(eng):
         _assert_close(eng.score_1vsN(model, "sp_", ent, rel, ent, s, p, None, precision="3xtf32"), g["sp"], fname + " sp tc")
         _assert_close(eng.score_1vsN(model, "_po", ent, rel, ent, o, p, sub, precision="3xtf32"), g["po_subset"], fname + " po_subset tc")
         _assert_close(eng.score_sp_po(model, ent, rel, s, p, o, None, precision="3xtf32"), g["sp_po"], fname + " sp_po tc")
+        _assert_close(eng.score_sp_po(model, ent, rel, s, p, o, None, precision="tf32+bf16x2"), g["sp_po"], fname + " sp_po mixed")
 
 
 MEDIUM = [("complex", 128), ("distmult", 128), ("simple", 128), ("cp", 128), ("rescal", 48),
@@ -89,7 +90,7 @@ def test_oracle_medium(eng, model, D, sigma):
     ref = orc.score_sp_po(model, ent, rel, tri[:, S], tri[:, P], tri[:, O])
     ce, cr, ct = ent.cuda(), rel.cuda(), tri.cuda()
     s, p, o = ct[:, S].contiguous(), ct[:, P].contiguous(), ct[:, O].contiguous()
-    precs = ["auto", "fp32"] + (["3xtf32"] if model in ("complex", "distmult", "simple", "rescal") else [])
+    precs = ["auto", "fp32"] + (["3xtf32", "tf32+bf16x2"] if model in ("complex", "distmult", "simple", "rescal") else [])
     for prec in precs:
         got = eng.score_sp_po(model, ce, cr, s, p, o, precision=prec)
         _assert_close(got, ref, f"{model} sp_po {prec}")
