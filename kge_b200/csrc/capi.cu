@@ -159,7 +159,7 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
     // kernel at every batch size once the epilogue stopped being the bottleneck
     // (profiles/r1_notes.md).  B200KGE_TC_VERSION=2 selects the pair kernel (kept for experiments).
     const char* env_v = getenv("B200KGE_TC_VERSION");
-    const bool pair = env_v && atoi(env_v) == 2 && passes != 2;   // the mixed mode exists in the 1-CTA kernel only
+    const bool pair = env_v && atoi(env_v) == 2;
     const int nch = pair ? tc2_nchunks(nq, m) : tc_nchunks(nq, m);
     if (epi_kind == EPI_BCE || epi_kind == EPI_KL) {
       const int F = (epi_kind == EPI_BCE) ? 2 : 5;

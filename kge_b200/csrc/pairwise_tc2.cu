@@ -156,7 +156,7 @@ pairwise_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const uint32_t b_lo = a_hi + 3 * C::A_BYTES;
             // raw tiles are the hi operands: the hi*hi products start as soon as both CTAs' TMA
             // data has landed, overlapping the splitters' work on the same stage
-            if ((prm.dbg & 8) && PASSES == 3) ptx::mbar_wait_cluster(&split[s], ph);   // experiment: no early issue
+            if ((prm.dbg & 8) && PASSES != 1) ptx::mbar_wait_cluster(&split[s], ph);   // experiment: no early issue
             ptx::mbar_wait_cluster(&landed[s], ph);
             ptx::tc_fence_after();
             if (!(prm.dbg & 4)) {
@@ -173,6 +173,21 @@ pairwise_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 for (int k8 = 0; k8 < TK / 8; ++k8) {
                   ptx::umma_tf32_2cta(d_tmem, make_desc<TK>(a_lo + k8 * 32), make_desc<TK>(b_hi + k8 * 32), idesc, 1u);
                   ptx::umma_tf32_2cta(d_tmem, make_desc<TK>(a_hi + k8 * 32), make_desc<TK>(b_lo + k8 * 32), idesc, 1u);
+                }
+              }
+            } else if (PASSES == 2) {
+              // mixed mode (TK == 32 only): cross terms in bf16 on 64-B swizzled tiles (hi16 | lo16) that
+              // the splitters wrote where the fp32 lo tiles would be
+              ptx::mbar_wait_cluster(&split[s], ph);
+              ptx::tc_fence_after();
+              constexpr uint32_t idesc16 = ptx::umma_idesc_bf16(256, TN);
+              const uint32_t a16h = a_lo, a16l = a_lo + C::A_BYTES / 2;
+              const uint32_t b16h = b_lo, b16l = b_lo + C::A_BYTES / 2;
+              if (!(prm.dbg & 4)) {
+#pragma unroll
+                for (int k2 = 0; k2 < TK / 16; ++k2) {
+                  ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw64(a16l + k2 * 32), ptx::umma_desc_sw64(b16h + k2 * 32), idesc16, 1u);
+                  ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw64(a16h + k2 * 32), ptx::umma_desc_sw64(b16l + k2 * 32), idesc16, 1u);
                 }
               }
             }
@@ -196,20 +211,26 @@ pairwise_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           ptx::mbar_wait(&full[s], ph);
           // tell the leader this CTA's stage has landed (its hi*hi MMAs may start)
           if (t == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&landed[s]), 0));
-          if (PASSES == 3) {
+          if (PASSES != 1) {
             if (!(prm.dbg & 2)) {
               // both operands are split here (raw tile = hi; write lo next to it): nothing derivable
               // on chip is fetched over the L2->SM fabric
               const uint32_t sp = ptx::smem_u32(stage_ptr(s));
-              tc::split_tile<C::A_BYTES, SPLIT_WARPS * 32>(sp, sp + C::A_BYTES, t);
-              tc::split_tile<C::A_BYTES, SPLIT_WARPS * 32>(sp + 2 * C::A_BYTES, sp + 3 * C::A_BYTES, t);
+              if (PASSES == 3) {
+                tc::split_tile<C::A_BYTES, SPLIT_WARPS * 32>(sp, sp + C::A_BYTES, t);
+                tc::split_tile<C::A_BYTES, SPLIT_WARPS * 32>(sp + 2 * C::A_BYTES, sp + 3 * C::A_BYTES, t);
+              } else if (TK == 32) {
+                tc::split_tile_bf16<TM, SPLIT_WARPS * 32>(sp, sp + C::A_BYTES, sp + C::A_BYTES + C::A_BYTES / 2, t);
+                tc::split_tile_bf16<TNH, SPLIT_WARPS * 32>(sp + 2 * C::A_BYTES, sp + 3 * C::A_BYTES,
+                                                           sp + 3 * C::A_BYTES + C::A_BYTES / 2, t);
+              }
             }
             ptx::fence_proxy_async_smem();
           }
           // one remote arrive per WARP (128 per-thread DSMEM arrives per chunk serialise on the
           // leader's barrier and were the bottleneck): every lane fenced its own writes to the
           // async proxy, __syncwarp orders them before lane 0's cluster-scope release.
-          if (PASSES == 3) {
+          if (PASSES != 1) {
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&split[s]), 0));
           }
@@ -287,6 +308,7 @@ template <int EPI>
 int launch_e(int passes, int tk, const CUtensorMap& a, const CUtensorMap& c, const Tc2Params& prm, int grid,
              cudaStream_t st) {
   if (passes == 3) return tk == 32 ? launch_k<EPI, 3, 32>(a, c, prm, grid, st) : launch_k<EPI, 3, 16>(a, c, prm, grid, st);
+  if (passes == 2) return launch_k<EPI, 2, 32>(a, c, prm, grid, st);   // mixed mode: 32-wide chunks only
   return tk == 32 ? launch_k<EPI, 1, 32>(a, c, prm, grid, st) : launch_k<EPI, 1, 16>(a, c, prm, grid, st);
 }
 
@@ -302,7 +324,7 @@ int launch_pairwise_tc2(int epi_kind, int passes, const float* Q, int64_t ldq,
                         int64_t nq, const float* T, int64_t ldt, int64_t m, int K,
                         const EpiParams& P, cudaStream_t st) {
   if (nq == 0 || m == 0) return 0;
-  const int tk = tk_choice();
+  const int tk = (passes == 2) ? 32 : tk_choice();
   CUtensorMap mQ, mT;
   int rc;
   if ((rc = tc::make_map(&mQ, Q, nq, K, ldq, tk, TM))) return rc;

@@ -106,26 +106,27 @@ def test_tensor_core_kernel_variants(eng, monkeypatch, version, tk, mc):
     monkeypatch.setenv("B200KGE_TC_VERSION", version)
     monkeypatch.setenv("B200KGE_TC2_TK", tk)
     monkeypatch.setenv("B200KGE_TC_MC", mc)
-    for model, D in (("complex", 192), ("distmult", 64), ("rescal", 40)):
+    for model, D, prec in (("complex", 192, "3xtf32"), ("complex", 192, "tf32+bf16x2"), ("distmult", 64, "tf32+bf16x2"),
+                           ("rescal", 40, "3xtf32"), ("rescal", 40, "tf32+bf16x2")):
         E, R, n = 6007, 7, 389
         ent, rel = orc.make_tables(model, E, R, D, sigma=0.5)
         tri = orc.make_triples(E, R, n)
         ce, cr, ct = ent.cuda(), rel.cuda(), tri.cuda()
         s, p, o = ct[:, S].contiguous(), ct[:, P].contiguous(), ct[:, O].contiguous()
         ref = orc.score_sp_po(model, ent, rel, tri[:, S], tri[:, P], tri[:, O])
-        got = eng.score_sp_po(model, ce, cr, s, p, o, precision="3xtf32")
-        _assert_close(got, ref, f"{model} sp_po v{version} tk{tk}")
+        got = eng.score_sp_po(model, ce, cr, s, p, o, precision=prec)
+        _assert_close(got, ref, f"{model} sp_po v{version} tk{tk} {prec}")
         sub = torch.randperm(E, generator=torch.Generator().manual_seed(1))[:1500]
-        got = eng.score_1vsN(model, "_po", ce, cr, ce, o, p, sub.cuda(), precision="3xtf32")
-        _assert_close(got, orc.score_po(model, ent, rel, tri[:, P], tri[:, O], sub), f"{model} po subset")
+        got = eng.score_1vsN(model, "_po", ce, cr, ce, o, p, sub.cuda(), precision=prec)
+        _assert_close(got, orc.score_po(model, ent, rel, tri[:, P], tri[:, O], sub), f"{model} po subset {prec}")
         for loss, fn in (("bce", orc.bce_loss), ("kl", orc.kl_loss)):
             refl = float(orc.train_1vsall_forward(model, ent, rel, tri, loss))
-            gotl = float(eng.train_1vsall_forward(model, ce, cr, ct, loss, precision="3xtf32"))
-            assert abs(gotl - refl) <= 1e-4 * abs(refl), (model, loss, gotl, refl)
-        dense = eng.score_1vsN(model, "sp_", ce, cr, ce, s, p, precision="3xtf32")
+            gotl = float(eng.train_1vsall_forward(model, ce, cr, ct, loss, precision=prec))
+            assert abs(gotl - refl) <= 1e-4 * abs(refl), (model, loss, prec, gotl, refl)
+        dense = eng.score_1vsN(model, "sp_", ce, cr, ce, s, p, precision=prec)
         true = dense[torch.arange(n, device="cuda"), o].clone()
         rr, tt = orc.ranks_and_ties(dense.cpu(), true.cpu())
-        r, t = eng.score_1vsN_rank(model, "sp_", ce, cr, ce, true, s, p, precision="3xtf32")
+        r, t = eng.score_1vsN_rank(model, "sp_", ce, cr, ce, true, s, p, precision=prec)
         assert torch.equal(r.cpu(), rr) and torch.equal(t.cpu(), tt)
 
 
