@@ -266,9 +266,9 @@ size_t b200kge_workspace_bytes(int model, int64_t n, int64_t m, int32_t D, int c
   b += 2 * ((size_t)nq * ldq * 4 + 256);                 // Qhi/Qlo (or Q)
   if (cand_has_idx) b += (size_t)m * ldq * 4 + 256;      // gathered candidate subset
   int64_t nch = pairwise_simt_nchunks(nq, m);
-  if (nch < 160) nch = 160;
+  if (nch < 320) nch = 320;                              // tensor-core kernels: <= 2 * #SMs chunks per row
   b += (size_t)nq * nch * 5 * 4 + 256;                   // loss partials
-  b += (size_t)n * 3 * 8 + (size_t)n * 5 * 8 + 2048;     // host entry: triples, s/p/o, labels, scalar
+  b += (size_t)n * 3 * 8 + (size_t)n * 5 * 8 + 4096;     // host entry: triples, s/p/o, labels, scalar, finaliser scratch
   return b + 4096;
 }
 

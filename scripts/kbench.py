@@ -62,6 +62,20 @@ def case_1vsall(model, E, R, D, n, prec, epi, l_norm=1.0):
                       "alg_TFLOPs": round(pairs * 2 * D / k_avg / 1e9, 2)}), flush=True)
 
 
+def case_kvsall(model, E, R, D, n, loss):
+    """Fused score_sp + loss with DENSE multi-hot labels (KvsAll, train_KvsAll.py:242-289)."""
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.3)
+    tri = orc.make_triples(E, R, n).to(dev)
+    ent, rel = ent.to(dev), rel.to(dev)
+    lab = (torch.rand((n, E), device=dev) < 2e-4).float()
+    s, p = tri[:, 0].contiguous(), tri[:, 1].contiguous()
+    fn = lambda: engine.score_1vsN_loss(model, "sp_", ent, rel, ent, lab, s, p, None, loss)
+    k_avg, k_min, t_avg = timeit(fn)
+    print(json.dumps({"case": f"kvsall {model} E={E} D={D} n={n} {loss} dense labels", "kernel_ms": round(k_avg, 4),
+                      "call_ms": round(t_avg, 4), "label_GB": round(n * E * 4 / 1e9, 3),
+                      "label_GBps": round(n * E * 4 / k_avg / 1e6, 1)}), flush=True)
+
+
 def case_ns(model, E, R, D, n, K):
     ent, rel = orc.make_tables(model, E, R, D)
     tri = orc.make_triples(E, R, n).to(dev)
@@ -121,6 +135,8 @@ CASES = {
     "transe_store": lambda: case_1vsall("transe", 14541, 237, 512, 1024, "auto", "store"),
     "rotate_step": lambda: case_1vsall("rotate", 14541, 237, 512, 1024, "auto", "step"),
     "transe_wiki_shard": lambda: case_1vsall("transe", 600000, 822, 512, 128, "auto", "store"),
+    "kvsall_rescal": lambda: case_kvsall("rescal", 123182, 37, 200, 512, "bce"),
+    "kvsall_rescal_kl": lambda: case_kvsall("rescal", 123182, 37, 200, 512, "kl"),
     "ns_rotate": lambda: case_ns("rotate", 40943, 11, 512, 512, 1000),
     "ns_complex": lambda: case_ns("complex", 40943, 11, 512, 512, 1000),
 }

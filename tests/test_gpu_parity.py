@@ -319,6 +319,27 @@ def test_edge_cases(eng):
         eng.score_1vsN("complex", "sp_", ce[:, :31].contiguous(), cr, ce[:, :31].contiguous(), one, one)
     with pytest.raises(RuntimeError):  # CPU tensors are refused, never routed to a fallback
         eng.score_1vsN("complex", "sp_", ent, rel, ent, one.cpu(), one.cpu())
+    # table widths that are not multiples of 4 floats: no TMA (16-byte alignment) -> scalar SIMT loads
+    for model, D in (("complex", 66), ("distmult", 33), ("transe", 35), ("rotate", 70)):
+        e2, r2 = orc.make_tables(model, 517, 3, D)
+        t2 = orc.make_triples(517, 3, 40)
+        got = eng.score_sp_po(model, e2.cuda(), r2.cuda(), t2[:, 0].cuda(), t2[:, 1].cuda(), t2[:, 2].cuda())
+        _assert_close(got, orc.score_sp_po(model, e2, r2, t2[:, 0], t2[:, 1], t2[:, 2]), f"{model} D={D}")
+        with pytest.raises(NotImplementedError):
+            if model in ("transe", "rotate"):
+                eng.score_1vsN(model, "sp_", e2.cuda(), r2.cuda(), e2.cuda(), t2[:, 0].cuda(), t2[:, 1].cuda(),
+                               precision="3xtf32")
+            else:
+                eng.score_1vsN(model, "sp_", e2.cuda(), r2.cuda(), e2.cuda(), t2[:, 0].cuda(), t2[:, 1].cuda(),
+                               precision="tf32+bf16x2")
+    # negative sampling: empty batch, K = 1, duplicate negatives
+    tri0 = torch.zeros((0, 3), dtype=torch.int64, device="cuda")
+    assert eng.ns_score("complex", ce, cr, tri0, torch.zeros((0, 5), dtype=torch.int64, device="cuda"), 2).shape == (0, 5)
+    tri1 = torch.tensor([[1, 2, 3], [4, 0, 5]], device="cuda")
+    neg1 = torch.tensor([[7], [7]], device="cuda")
+    got = eng.ns_score("complex", ce, cr, tri1, neg1, 0, True)
+    ref = orc.ns_scores_with_positive("complex", ent, rel, tri1.cpu(), neg1.cpu(), 0)
+    _assert_close(got, ref, "ns K=1")
     # non-contiguous score output rows (ldo > m) and int32 indexes
     big = torch.full((1, 300), -7.0, device="cuda")
     eng.score_1vsN("complex", "sp_", ce, cr, ce, one.int(), (one % 3).int(), out=big[:, :100])
