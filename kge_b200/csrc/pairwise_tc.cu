@@ -54,6 +54,8 @@ struct TcParams {
   int q_tiles, e_tiles, echunks;
   int q_groups;     // work is (q group) x (e chunk): a group is one q tile, or a pair of q tiles when the
                     // table tile is multicast across a 2-CTA cluster (MC)
+  int dbg;          // experiments (B200KGE_DBG bit-mask): 1 = skip TMA after the first fills, 2 = skip split
+                    // math, 4 = skip MMAs — isolates the pipeline phases (results are garbage)
   int tn;           // entities per tile actually used (multiple of 16, <= TN): chosen per problem so that
                     // ceil(tiles / SMs) * tn — the makespan in columns — is minimal
   EpiParams epi;
@@ -130,6 +132,7 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint32_t ph = (c / STAGES) & 1;
             if (MC) ptx::mbar_wait_cluster(&empty[s], ph ^ 1); else ptx::mbar_wait(&empty[s], ph ^ 1);
             uint8_t* sp = stage_ptr(s);
+            if ((prm.dbg & 1) && c >= (uint32_t)STAGES) { ptx::mbar_arrive(&full[s]); continue; }
             ptx::mbar_arrive_expect_tx(&full[s], A_BYTES + prm.tn * TK * 4);
             ptx::tma_load_2d(sp, &tmQ, &full[s], kc * TK, qt * TM);                 // raw queries
             if (MC) {
@@ -167,15 +170,18 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             // raw tiles are the hi operands: hi*hi starts when the TMA data lands, overlapping the split
             ptx::mbar_wait(&full[s], ph);
             ptx::tc_fence_after();
+            const bool do_mma = !(prm.dbg & 4);
 #pragma unroll
             for (int k4 = 0; k4 < TK / 8; ++k4)
-              ptx::umma_tf32(d_tmem, ptx::umma_desc_sw128(a_hi + k4 * 32), ptx::umma_desc_sw128(b_hi + k4 * 32), idesc,
-                             (kc > 0 || k4 > 0) ? 1u : 0u);
+              if (do_mma)
+                ptx::umma_tf32(d_tmem, ptx::umma_desc_sw128(a_hi + k4 * 32), ptx::umma_desc_sw128(b_hi + k4 * 32), idesc,
+                               (kc > 0 || k4 > 0) ? 1u : 0u);
             if (PASSES == 3) {
               ptx::mbar_wait(&split[s], ph);
               ptx::tc_fence_after();
 #pragma unroll
               for (int k4 = 0; k4 < TK / 8; ++k4) {
+                if (!do_mma) break;
                 ptx::umma_tf32(d_tmem, ptx::umma_desc_sw128(a_lo + k4 * 32), ptx::umma_desc_sw128(b_hi + k4 * 32), idesc, 1u);
                 ptx::umma_tf32(d_tmem, ptx::umma_desc_sw128(a_hi + k4 * 32), ptx::umma_desc_sw128(b_lo + k4 * 32), idesc, 1u);
               }
@@ -189,6 +195,7 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               const uint32_t b16h = b_hi + B_BYTES, b16l = b16h + B_BYTES / 2;
 #pragma unroll
               for (int k2 = 0; k2 < TK / 16; ++k2) {
+                if (!do_mma) break;
                 ptx::umma_bf16(d_tmem, ptx::umma_desc_sw64(a16l + k2 * 32), ptx::umma_desc_sw64(b16h + k2 * 32), idesc16, 1u);
                 ptx::umma_bf16(d_tmem, ptx::umma_desc_sw64(a16h + k2 * 32), ptx::umma_desc_sw64(b16l + k2 * 32), idesc16, 1u);
               }
@@ -218,7 +225,9 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             ptx::mbar_wait(&full[s], ph);
             // raw tile = hi operand; write lo next to it, for the table tile AND the query tile
             const uint32_t sp = ptx::smem_u32(stage_ptr(s));
-            if (PASSES == 3) {
+            if (prm.dbg & 2) {
+              // experiment: no split work
+            } else if (PASSES == 3) {
               if (is_b) tc::split_tile<B_BYTES, SPLIT_WARPS * 32>(sp + 2 * A_BYTES, sp + 2 * A_BYTES + B_BYTES, t);
               else      tc::split_tile<A_BYTES, 2 * 32>(sp, sp + A_BYTES, t);
             } else {
@@ -376,6 +385,7 @@ int launch_pairwise_tc(int epi_kind, int passes, const float* Q, int64_t ldq,
   if ((rc = tc::make_map(&mT, T, m, K, ldt, TK, mc ? prm.tn / 2 : prm.tn))) return rc;
   prm.epi = P;
   prm.epi.nchunks = 2 * prm.echunks;   // two epilogue warps (column halves) per row
+  { const char* e = getenv("B200KGE_DBG"); prm.dbg = e ? atoi(e) : 0; }
   const int total = prm.q_groups * prm.echunks;
   const int units = mc ? num_sms() / 2 : num_sms();
   const int grid = (mc ? 2 : 1) * (total < units ? total : units);

@@ -110,9 +110,12 @@ __device__ __forceinline__ float fast_ex2(float x) {
 }
 
 // 32 columns [c0, c0+32) of row `row`; v = raw accumulator bits.  FULL: all 32 columns < m.
+// `side`: this row's 32 entries of the dense label matrix (BCE/KL) or of the filter matrix (rank),
+// already staged in shared memory by the warp (coalesced loads), or nullptr.
 template <int EPI, bool FULL>
 __device__ __forceinline__ void epi_chunk32(const EpiParams& P, RowState<EPI>& st, int64_t row, float aux,
-                                            const uint32_t (&v)[32], int64_t c0, int64_t m) {
+                                            const uint32_t (&v)[32], int64_t c0, int64_t m,
+                                            const float* __restrict__ side) {
   const int nvalid = FULL ? 32 : (int)(m - c0);   // > 0 by construction
   if constexpr (EPI == EPI_BCE) {
     // sum softplus(z) - sum y*z,  softplus(z) = max(z,0) + log(1 + exp(-|z|))   (loss.py:150-157;
@@ -129,12 +132,11 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& P, RowState<EPI>& s
       }
     }
     st.a += fmaf(alg, LN2, amax);
-    if (P.label_dense) {
-      const float* __restrict__ y = P.label_dense + row * P.ldl + c0;
+    if (side) {
       float b = 0.f;
 #pragma unroll
       for (int c = 0; c < 32; ++c)
-        if (FULL || c < nvalid) b = fmaf(__ldg(y + c), __uint_as_float(v[c]) + off, b);
+        if (FULL || c < nvalid) b = fmaf(side[c], __uint_as_float(v[c]) + off, b);
       st.b += b;
     } else {
       const int rel = __float_as_int(aux) - (int)c0;      // one-hot label relative to this chunk
@@ -158,12 +160,11 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& P, RowState<EPI>& s
       if (FULL || c < nvalid) acc += fast_ex2(fmaf(__uint_as_float(v[c]), LOG2E, -mn2));
     st.s = fmaf(st.s, fast_ex2((st.m - mn) * LOG2E), acc);
     st.m = mn;
-    if (P.label_dense) {
-      const float* __restrict__ y = P.label_dense + row * P.ldl + c0;
+    if (side) {
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         if (FULL || c < nvalid) {
-          const float yy = __ldg(y + c);
+          const float yy = side[c];
           if (yy != 0.f) {
             st.y_sum += yy;
             st.yx = fmaf(yy, __uint_as_float(v[c]), st.yx);
@@ -183,13 +184,13 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& P, RowState<EPI>& s
     // eval_entity_ranking.py:561-596; `allowed` depends on the row only -> hoisted
     const float t = aux;
     const float allowed = __fadd_rn(P.atol, fabsf(__fmul_rn(P.rtol, t)));
-    const float* __restrict__ f = P.filter ? P.filter + row * P.ldf + c0 : nullptr;
+    const float* __restrict__ f = side;
     unsigned int gt = 0, cl = 0;
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
       if (FULL || c < nvalid) {
         float x = __uint_as_float(v[c]);
-        if (f) x = __fsub_rn(x, __ldg(f + c));
+        if (f) x = __fsub_rn(x, f[c]);
         if (isnan(x)) x = -INFINITY;
         const float actual = fabsf(__fsub_rn(x, t));
         const bool close = (x == t) || (isfinite(actual) && actual <= allowed);
@@ -258,10 +259,30 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& P, RowState<EPI>&
       }
       __syncwarp();
     } else {
-      if (row_ok) {
-        if (c0 + 32 <= m) epi_chunk32<EPI, true>(P, st, row, aux, v, c0, m);
-        else              epi_chunk32<EPI, false>(P, st, row, aux, v, c0, m);
+      // dense side matrix (labels / filter): the warp stages its 32x32 block through shared memory
+      // with coalesced 128-B row reads; each thread then reads its own row from smem (reading the
+      // matrix directly would touch 32 different rows per load instruction)
+      const float* gside = nullptr;
+      int64_t gld = 0;
+      if constexpr (EPI == EPI_RANK) { gside = P.filter; gld = P.ldf; }
+      else { gside = P.label_dense; gld = P.ldl; }
+      const float* side = nullptr;
+      if (gside) {
+        const int64_t col = c0 + lane;
+        const bool col_ok = col < m;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+          const int64_t r = tile_row0 + rr;
+          my_stg[rr * STG_LD + lane] = (col_ok && r < nq) ? __ldg(gside + r * gld + col) : 0.f;
+        }
+        __syncwarp();
+        side = my_stg + lane * STG_LD;
       }
+      if (row_ok) {
+        if (c0 + 32 <= m) epi_chunk32<EPI, true>(P, st, row, aux, v, c0, m, side);
+        else              epi_chunk32<EPI, false>(P, st, row, aux, v, c0, m, side);
+      }
+      if (gside) __syncwarp();
     }
   }
 }
