@@ -400,6 +400,7 @@ int b200kge_ns_score(int model, float l_norm, const b200kge_rows_t* s, const b20
                      const b200kge_rows_t* o, const b200kge_rows_t* slot_table, int slot,
                      const int64_t* neg, int64_t n, int64_t K, int with_positive, float* out,
                      int64_t ldo, b200kge_stream_t stream) {
+  if (n == 0 || (K == 0 && !with_positive)) return 0;          // nothing to score
   if (!s || !p || !o || !slot_table || (!neg && n * K > 0) || !out) { set_error("null operand"); return B200KGE_ERR_INVALID; }
   if (slot < 0 || slot > 2) { set_error("slot must be 0 (S), 1 (P) or 2 (O)"); return B200KGE_ERR_INVALID; }
   int rc = validate_model(model, to_rows(s), to_rows(p)); if (rc) return rc;

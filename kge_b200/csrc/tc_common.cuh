@@ -65,24 +65,28 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 template <int ROWS, int NTHR>
 __device__ __forceinline__ void split_tile_bf16(uint32_t src, uint32_t dst_hi, uint32_t dst_lo, int t) {
-  constexpr int ITEMS = ROWS * 4, PER = ITEMS / NTHR;
-  static_assert(PER * NTHR == ITEMS, "tile must divide evenly");
+  constexpr int ITEMS = ROWS * 4, PER = ITEMS / NTHR, RSTEP = NTHR / 4;
+  static_assert(PER * NTHR == ITEMS && RSTEP % 8 == 0, "tile must divide evenly; row step keeps the swizzle phase");
+  // item i of thread t: row r = (t >> 2) + i * RSTEP, k-group c = t & 3.  RSTEP is a multiple of 8, so
+  // the swizzle terms (r & 7) and ((r >> 1) & 3) are per-thread constants and all addresses are
+  // base + i * constant.
+  const int r0 = t >> 2, c = t & 3;
+  const uint32_t s0 = src + (uint32_t)r0 * 128u + (uint32_t)(((2 * c) ^ (r0 & 7)) * 16);
+  const uint32_t s1 = src + (uint32_t)r0 * 128u + (uint32_t)(((2 * c + 1) ^ (r0 & 7)) * 16);
+  const uint32_t doff = (uint32_t)r0 * 64u + (uint32_t)((c ^ ((r0 >> 1) & 3)) * 16);
   float4 v0[PER], v1[PER];
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
-    const int it = t + i * NTHR, r = it >> 2, c = it & 3;
-    const uint32_t rowb = src + (uint32_t)r * 128u;
-    v0[i] = lds128(rowb + (uint32_t)(((2 * c) ^ (r & 7)) * 16));
-    v1[i] = lds128(rowb + (uint32_t)(((2 * c + 1) ^ (r & 7)) * 16));
+    v0[i] = lds128(s0 + (uint32_t)(i * RSTEP * 128));
+    v1[i] = lds128(s1 + (uint32_t)(i * RSTEP * 128));
   }
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
-    const int it = t + i * NTHR, r = it >> 2, c = it & 3;
     const float x[8] = {v0[i].x, v0[i].y, v0[i].z, v0[i].w, v1[i].x, v1[i].y, v1[i].z, v1[i].w};
     float lo[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) lo[k] = x[k] - __uint_as_float(__float_as_uint(x[k]) & 0xFFFFE000u);
-    const uint32_t off = (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) * 16);
+    const uint32_t off = doff + (uint32_t)(i * RSTEP * 64);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_hi + off), "r"(pack_bf16x2(x[0], x[1])),
                  "r"(pack_bf16x2(x[2], x[3])), "r"(pack_bf16x2(x[4], x[5])), "r"(pack_bf16x2(x[6], x[7])) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_lo + off), "r"(pack_bf16x2(lo[0], lo[1])),

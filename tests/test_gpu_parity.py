@@ -98,14 +98,13 @@ def test_oracle_medium(eng, model, D, sigma):
     _assert_close(eng.score_spo(model, ce, cr, ce, s, p, o), ref_spo, f"{model} spo")
 
 
-@pytest.mark.parametrize("version,tk,mc", [("1", "32", "0"), ("1", "32", "1"), ("2", "32", "0"), ("2", "16", "0")])
-def test_tensor_core_kernel_variants(eng, monkeypatch, version, tk, mc):
-    """1-CTA kernel (plain and with the table tile TMA-multicast across 2-CTA clusters) and the
-    CTA-pair (cta_group::2) kernel in both K-chunk/swizzle configurations: dense scores, fused BCE/KL,
-    fused rank counting; ragged sizes (tiles cut in both dimensions, odd number of query tiles)."""
+@pytest.mark.parametrize("version,tk", [("1", "32"), ("2", "32"), ("2", "16")])
+def test_tensor_core_kernel_variants(eng, monkeypatch, version, tk):
+    """1-CTA kernel and the CTA-pair (cta_group::2) kernel in both K-chunk/swizzle configurations, in the
+    3xTF32 and the mixed split modes: dense scores, fused BCE/KL, fused rank counting; ragged sizes
+    (tiles cut in both dimensions, odd number of query tiles)."""
     monkeypatch.setenv("B200KGE_TC_VERSION", version)
     monkeypatch.setenv("B200KGE_TC2_TK", tk)
-    monkeypatch.setenv("B200KGE_TC_MC", mc)
     for model, D, prec in (("complex", 192, "3xtf32"), ("complex", 192, "tf32+bf16x2"), ("distmult", 64, "tf32+bf16x2"),
                            ("rescal", 40, "3xtf32"), ("rescal", 40, "tf32+bf16x2")):
         E, R, n = 6007, 7, 389
