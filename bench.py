@@ -265,7 +265,7 @@ def run_ours(args):
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": 34.1e6, "kernel": "pairwise_tc_kernel<BCE, tf32+bf16x2>", "kernel_ms": k_ms,
         "peak_name": f"dense bf16 burst, {peaks['source']}",
-        "traffic_note": "dram__bytes_read+write per launch from ncu --set full (profiles/r1b_summary.md); "
+        "traffic_note": "dram__bytes_read+write per launch from ncu --set full (profiles/r1d_summary.md); "
                         "algorithmic bytes = table 29.8 MB + folded queries 4.2 MB",
         "note": "algorithmic fp32 FLOPs (2nED per direction); for fp32-equivalent results the kernel issues, "
                 "per 32-wide K chunk, 4 TF32 MMAs (hi*hi) + 4 BF16 MMAs (cross terms) = 8 MMA slots where a "

@@ -336,7 +336,7 @@ int b200kge_score_1vsN_loss(int model, int combine, float l_norm, int precision,
   // the partial buffer is the LAST thing run_block took from the arena
   const size_t part_bytes = (size_t)n * nch * F * 4;
   float* part = (float*)(ws.base + (ws.off - part_bytes));
-  void* scratch = ws.take(512);
+  void* scratch = ws.take(1024);
   if (!scratch) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
   return launch_loss_finalize(loss_kind, part, nch, n, loss_out, row_loss_out, 1.0f, 0, scratch, 0, st);
 }
@@ -378,7 +378,7 @@ int b200kge_loss_dense(const float* scores, int64_t lds, int64_t n, int64_t m,
   P.nchunks = nch;
   P.part = (float*)ws.take((size_t)n * nch * F * 4);
   if (!P.part) { set_error("workspace too small for loss partials (need %zu bytes)", (size_t)n * nch * F * 4); return B200KGE_ERR_WORKSPACE; }
-  void* scratch = ws.take(512);
+  void* scratch = ws.take(1024);
   if (!scratch) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
   int rc = launch_loss_dense(loss_kind, scores, lds, n, m, P, st);
   if (rc) return rc;
@@ -441,9 +441,9 @@ int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
     const int64_t ldq = round_up(f0.K, 32);
     float* Q = (float*)ws.take((size_t)(2 * n) * ldq * 4);
     int64_t* lab = (int64_t*)ws.take((size_t)n * 2 * 8);
-    uint8_t* scratch = (uint8_t*)ws.take(512);       // finaliser scratch: block sums + ticket (+256)
+    uint8_t* scratch = (uint8_t*)ws.take(1024);      // finaliser scratch: block sums + ticket (+512)
     if (!Q || !lab || !scratch) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
-    rc = launch_prep_1vsall(model, E, R, triples, n, Q, ldq, lab, reinterpret_cast<unsigned int*>(scratch + 256), st);
+    rc = launch_prep_1vsall(model, E, R, triples, n, Q, ldq, lab, reinterpret_cast<unsigned int*>(scratch + 512), st);
     if (rc) return rc;
     Rows S = E; S.idx = lab; S.rows = n;           // placeholders: operands are pre-folded
     Rows Pr = R; Pr.idx = lab; Pr.rows = n;
@@ -482,7 +482,7 @@ int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
     if (rc) return rc;
     const size_t part_bytes = (size_t)n * nch * F * 4;
     float* part = (float*)(w2.base + (w2.off - part_bytes));
-    void* scratch = w2.take(512);
+    void* scratch = w2.take(1024);
     if (!scratch) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
     rc = launch_loss_finalize(loss_kind, part, nch, n, loss_out, nullptr, scale, dir, scratch, 0, st);
     if (rc) return rc;

@@ -310,8 +310,8 @@ int tc_nchunks(int64_t nq, int64_t m);
 int launch_pairwise_tc(int epi_kind, int passes, const float* Q, int64_t ldq,
                        int64_t nq, const float* T, int64_t ldt, int64_t m, int K,
                        const EpiParams& P, cudaStream_t st);
-// scratch: >= 512 bytes of device memory (block sums + ticket); ticket_zeroed: the caller already
-// zeroed the ticket word at scratch+256 on this stream (else a 4-byte memset is enqueued)
+// scratch: >= 1024 bytes of device memory (128 block sums + ticket); ticket_zeroed: the caller already
+// zeroed the ticket word at scratch+512 on this stream (else a 4-byte memset is enqueued)
 int launch_loss_finalize(int loss_kind, const float* part, int nchunks, int64_t n, float* loss_out,
                          float* row_loss_out, float scale, int accumulate, void* scratch,
                          int ticket_zeroed, cudaStream_t st);

@@ -59,7 +59,7 @@ dense_epilogue_kernel(const float* __restrict__ scores, int64_t lds, int64_t m, 
 // One warp per row: lanes hold the row's chunk partials (coalesced), a fixed shuffle tree combines
 // them; lane 0 accumulates the warp's rows in order.  Blocks publish their sums; the last block to
 // finish adds them in index order.
-constexpr int FIN_BLOCKS = 64, FIN_THREADS = 256;
+constexpr int FIN_BLOCKS = 128, FIN_THREADS = 256;
 
 template <int LOSS>
 __global__ void __launch_bounds__(FIN_THREADS)
@@ -111,12 +111,18 @@ loss_finalize_kernel(FinalizeArgs A) {
     is_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
+  if (is_last && warp == 0) {
+    // last block: warp 0 adds the (<= 128) block sums — lane l takes blocks l, l+32, ... in order, then a
+    // fixed shuffle tree: deterministic
     __threadfence();
     float tot = 0.f;
-    for (unsigned b = 0; b < gridDim.x; ++b) tot += reinterpret_cast<volatile float*>(A.block_sums)[b];
-    A.loss_out[0] = (A.accumulate ? A.loss_out[0] : 0.f) + A.scale * tot;
-    *A.ticket = 0u;
+    for (unsigned b = lane; b < gridDim.x; b += 32) tot += __ldcg(A.block_sums + b);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+    if (lane == 0) {
+      A.loss_out[0] = (A.accumulate ? A.loss_out[0] : 0.f) + A.scale * tot;
+      *A.ticket = 0u;
+    }
   }
 }
 
@@ -150,7 +156,7 @@ int launch_loss_finalize(int loss_kind, const float* part, int nchunks, int64_t 
                          float* row_loss_out, float scale, int accumulate, void* scratch,
                          int ticket_zeroed, cudaStream_t st) {
   float* block_sums = reinterpret_cast<float*>(scratch);
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(scratch) + 256);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(scratch) + 512);
   if (!ticket_zeroed) B2K_CUDA(cudaMemsetAsync(ticket, 0, 4, st));
   int64_t want = (n + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32);
   const int grid = (int)(want < 1 ? 1 : (want > FIN_BLOCKS ? FIN_BLOCKS : want));
