@@ -106,9 +106,7 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
 
   bool use_tc = false;
   if (f0.pair_op == PAIR_DOT && precision != B200KGE_PREC_FP32 && !cols_differ) {
-    Rows c = *B.cand;
-    bool ok = (K >= 32) && (c.ld % 4 == 0) && (f0.col_off % 4 == 0) &&
-              ((reinterpret_cast<uintptr_t>(c.base) & 15) == 0) && (m < (1ll << 31));
+    const bool ok = tc_supported(f0.pair_op, K, *B.cand, f0.col_off);
     if (precision == B200KGE_PREC_AUTO) use_tc = ok && nq >= 16;
     else {
       if (!ok) { set_error("tensor-core path needs K>=32, 16-byte aligned tables with ld%%4==0"); return B200KGE_ERR_UNSUPPORTED; }
