@@ -69,3 +69,13 @@ def test_reciprocal_relations_model_uses_plugin_scorer():
     m, _ = _create("reciprocal_relations_model",
                    {"reciprocal_relations_model.base_model.type": "b200_distmult"})
     assert type(m._base_model.get_scorer()).__name__ == "B200DistMultScorer"
+
+
+def test_plugin_options_propagate():
+    m, _ = _create("b200_transe", {"b200_transe.l_norm": 2.0, "b200_transe.precision": "3xtf32"})
+    sc = m.get_scorer()
+    assert sc._b200_l_norm() == 2.0 and sc._b200_precision() == "3xtf32" and sc._b200_name == "transe"
+    r, _ = _create("b200_rotate")
+    w = r.get_p_embedder()._embeddings.weight
+    assert float(w.abs().max()) <= 3.1416 and r.get_scorer()._b200_l_norm() == 1.0     # uniform(-pi, pi) phases
+    assert r._normalize_phases is True
