@@ -93,8 +93,10 @@ struct Block {
   const float* Qpre = nullptr;   // already-folded queries [nq, round_up(K,32)] (skips the fold launches)
 };
 
+// nchunks_out / part_out (optional): number of per-row partial chunks and the partial buffer the loss
+// epilogues wrote (input of launch_loss_finalize).
 int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiParams P, Arena& ws,
-              cudaStream_t st, int* nchunks_out, int* used_tc_out = nullptr) {
+              cudaStream_t st, int* nchunks_out, float** part_out = nullptr) {
   const int64_t n = B.n, nq = B.q1 ? 2 * n : n, m = B.cand->rows;
   const int D = B.q0->dim;
   Folded f0 = folded_problem(B.model, B.combine, D, l_norm);
@@ -129,7 +131,6 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
     return run_block(h1, l_norm, precision, epi_kind, P1, ws, st, nchunks_out);
   }
 
-  if (used_tc_out) *used_tc_out = use_tc ? 1 : 0;
   if (use_tc) {
     // AUTO = mixed mode (tf32 hi*hi + bf16 cross terms): measured both more accurate (2.4e-5 vs 3.0e-5 of
     // rms: fewer accumulation steps) and faster (8 MMAs per K-chunk instead of 12) than 3xTF32 on B200
@@ -163,6 +164,7 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
       const int F = (epi_kind == EPI_BCE) ? 2 : 5;
       P.part = (float*)ws.take((size_t)nq * nch * F * 4);
       if (!P.part) { set_error("workspace too small for loss partials"); return B200KGE_ERR_WORKSPACE; }
+      if (part_out) *part_out = P.part;
     }
     P.nchunks = nch;
     if (nchunks_out) *nchunks_out = nch;
@@ -185,6 +187,7 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
     const int F = (epi_kind == EPI_BCE) ? 2 : 5;
     P.part = (float*)ws.take((size_t)nq * nch * F * 4);
     if (!P.part) { set_error("workspace too small for loss partials"); return B200KGE_ERR_WORKSPACE; }
+    if (part_out) *part_out = P.part;
   }
   P.nchunks = nch;
   if (nchunks_out) *nchunks_out = nch;
@@ -327,13 +330,10 @@ int b200kge_score_1vsN_loss(int model, int combine, float l_norm, int precision,
   Block B{model, combine, &Q, nullptr, &Pr, &C, n};
   int nch = 0;
   const int epi = (loss_kind == B200KGE_LOSS_BCE) ? EPI_BCE : EPI_KL;
-  rc = run_block(B, l_norm, precision, epi, P, ws, st, &nch);
+  float* part = nullptr;
+  rc = run_block(B, l_norm, precision, epi, P, ws, st, &nch, &part);
   if (rc) return rc;
   if (n == 0 || C.rows == 0) { B2K_CUDA(cudaMemsetAsync(loss_out, 0, 4, st)); return 0; }
-  const int F = (epi == EPI_BCE) ? 2 : 5;
-  // the partial buffer is the LAST thing run_block took from the arena
-  const size_t part_bytes = (size_t)n * nch * F * 4;
-  float* part = (float*)(ws.base + (ws.off - part_bytes));
   void* scratch = ws.take(1024);
   if (!scratch) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
   return launch_loss_finalize(loss_kind, part, nch, n, loss_out, row_loss_out, 1.0f, 0, scratch, 0, st);
@@ -430,7 +430,6 @@ int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
   Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
   Rows E = to_rows(ent), R = to_rows(rel);
   const int epi = (loss_kind == B200KGE_LOSS_BCE) ? EPI_BCE : EPI_KL;
-  const int F = (epi == EPI_BCE) ? 2 : 5;
   const float scale = 1.0f / (float)n;       // "/ batch_size"   train_1vsAll.py:65,76
   Folded f0 = folded_problem(model, B200KGE_SP_, E.dim, l_norm), f1 = folded_problem(model, B200KGE__PO, E.dim, l_norm);
   if (f0.col_off == f1.col_off) {
@@ -451,10 +450,9 @@ int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
     Block B{model, B200KGE_SP_, &S, &S, &Pr, &E, n};
     B.Qpre = Q;
     int nch = 0;
-    rc = run_block(B, l_norm, precision, epi, P, ws, st, &nch);
+    float* part = nullptr;
+    rc = run_block(B, l_norm, precision, epi, P, ws, st, &nch, &part);
     if (rc) return rc;
-    const size_t part_bytes = (size_t)(2 * n) * nch * F * 4;
-    float* part = (float*)(ws.base + (ws.off - part_bytes));
     return launch_loss_finalize(loss_kind, part, nch, 2 * n, loss_out, nullptr, scale, 0, scratch, 1, st);
   }
   int64_t* sidx = (int64_t*)ws.take((size_t)n * 8);
@@ -476,10 +474,9 @@ int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
     Pd.label_idx = lab + dir * n;
     Block B{model, dir, dir == 0 ? &S : &O, nullptr, &Pr, &E, n};
     int nch = 0;
-    rc = run_block(B, l_norm, precision, epi, Pd, w2, st, &nch);
+    float* part = nullptr;
+    rc = run_block(B, l_norm, precision, epi, Pd, w2, st, &nch, &part);
     if (rc) return rc;
-    const size_t part_bytes = (size_t)n * nch * F * 4;
-    float* part = (float*)(w2.base + (w2.off - part_bytes));
     void* scratch = w2.take(1024);
     if (!scratch) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
     rc = launch_loss_finalize(loss_kind, part, nch, n, loss_out, nullptr, scale, dir, scratch, 0, st);

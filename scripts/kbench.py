@@ -110,7 +110,7 @@ def case_parity():
     for prec in ("fp32", "3xtf32", "tf32+bf16x2", "tf32"):
         got = engine.score_1vsN(model, "sp_", e, r, e, t[:, 0].contiguous(), t[:, 1].contiguous(), None, 1.0, prec)
         out[prec] = float((got.cpu().double() - ref).abs().max()) / rms
-    print(json.dumps({"case": "parity vs fp64 (max|d|/rms)", "split_lo_only": os.environ.get("B200KGE_SPLIT_LO_ONLY", "0"), **out}), flush=True)
+    print(json.dumps({"case": "parity vs fp64 (max|d|/rms)", **out}), flush=True)
 
 
 CASES = {
