@@ -165,6 +165,66 @@ def gen_ns(model, E, R, D, n, K, l_norm, tag):
     print("wrote ns", tag)
 
 
+def gen_jobs(model, tag):
+    """Run the reference's OWN jobs (TrainingJob1vsAll forward-only epoch, EntityRankingJob) on an
+    in-memory synthetic graph with seeded tables; record the trace values the oracle must reproduce."""
+    import tempfile
+
+    ref_shim.import_reference()
+    from kge import Config, Dataset
+    from kge.job import Job
+
+    E, R, D = 60, 5, 16
+
+    def triples(n, seed):
+        g = torch.Generator().manual_seed(seed)
+        return torch.stack([torch.randint(0, E, (n,), generator=g), torch.randint(0, R, (n,), generator=g),
+                            torch.randint(0, E, (n,), generator=g)], 1).int()
+
+    out = {}
+    splits = {"train": triples(50, 1), "valid": triples(12, 2), "test": triples(10, 3)}
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.5)
+    for loss in ("bce", "kl"):
+        config = Config()
+        config.folder = tempfile.mkdtemp()
+        config.set("console.quiet", True)
+        config.set("model", model)
+        config._import(model)
+        config.set("dataset.name", "synthetic")
+        config.set("dataset.num_entities", E)
+        config.set("dataset.num_relations", R)
+        config.set("dataset.pickle", False)
+        config.set("job.device", "cpu")
+        config.set("job.type", "train")
+        config.set("train.type", "1vsAll")
+        config.set("train.loss", loss)
+        config.set("train.batch_size", 16)
+        config.set("eval.batch_size", 8)
+        config.set_all({"lookup_embedder.dim": D})
+        ds = Dataset(config, None)
+        ds._triples = dict(splits)
+        ds._meta = {"entity_ids": [f"e{i}" for i in range(E)], "relation_ids": [f"r{i}" for i in range(R)]}
+        job = Job.create(config, ds)
+        with torch.no_grad():
+            job.model.get_s_embedder()._embeddings.weight.copy_(ent)
+            job.model.get_p_embedder()._embeddings.weight.copy_(rel)
+        job.is_forward_only = True
+        job._prepare()
+        out[f"avg_loss_{loss}"] = np.float64(job.run_epoch()["avg_loss"])
+        if loss == "bce":
+            ev = job.valid_job
+            ev._prepare()
+            tr = ev._run()
+            for k in ("mean_rank", "mean_reciprocal_rank", "hits_at_1", "hits_at_3", "hits_at_10",
+                      "mean_rank_filtered", "mean_reciprocal_rank_filtered", "hits_at_1_filtered",
+                      "hits_at_3_filtered", "hits_at_10_filtered"):
+                out["valid_" + k] = np.float64(tr[k])
+    out.update(ent=_np(ent), rel=_np(rel), train=_np(splits["train"]), valid=_np(splits["valid"]),
+               test=_np(splits["test"]))
+    np.savez_compressed(os.path.join(HERE, f"jobs_{tag}.npz"), **out)
+    print("wrote jobs", tag, {k: float(v) for k, v in out.items() if np.ndim(v) == 0})
+
+
 def main():
     torch.manual_seed(0)
     E, R, n = 97, 7, 13
@@ -178,6 +238,8 @@ def main():
     gen_ranks()
     for model in ("complex", "rotate", "transe", "rescal"):
         gen_ns(model, 61, 5, 16 if model == "rescal" else 32, 6, 10, 1.0, model)
+    for model in ("complex", "transe"):
+        gen_jobs(model, model)
 
 
 if __name__ == "__main__":

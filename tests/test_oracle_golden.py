@@ -98,3 +98,27 @@ def test_fp64_mode_is_consistent():
         b = orc.score_sp_po(model, ent.double(), rel.double(), tri[:, 0], tri[:, 1], tri[:, 2])
         rms = float(b.pow(2).mean().sqrt())
         assert float((a.double() - b).abs().max()) <= 1e-5 * max(rms, 1.0)
+
+
+@pytest.mark.parametrize("model", ["complex", "transe"])
+def test_job_traces_match_reference(model):
+    """Trace values of the reference's own jobs (TrainingJob1vsAll forward-only epoch and
+    EntityRankingJob on the valid split; tests/golden/gen_golden.py:gen_jobs) re-derived by the oracle."""
+    g = _load(f"jobs_{model}.npz")
+    ent, rel = g["ent"], g["rel"]
+    train, valid, test = g["train"].long(), g["valid"].long(), g["test"].long()
+    # epoch avg_loss = sum_batches(avg_loss_b * size_b) / num_examples (train.py:405-420,536-548) and
+    # avg_loss_b * size_b = loss_sp + loss_po summed over the batch (train_1vsAll.py:48-82): the
+    # batch split cancels, leaving one forward over the whole split.
+    for loss in ("bce", "kl"):
+        got = float(orc.train_1vsall_forward(model, ent, rel, train, loss=loss))
+        want = float(g[f"avg_loss_{loss}"])
+        assert abs(got - want) <= 1e-5 * abs(want), (loss, got, want)
+        batched = sum(float(orc.train_1vsall_forward(model, ent, rel, train[i:i + 16], loss=loss)) * len(train[i:i + 16])
+                      for i in range(0, len(train), 16)) / len(train)
+        assert abs(batched - want) <= 1e-5 * abs(want), (loss, batched, want)
+    # default eval.filter_splits = [train, valid] (+ test only for *_filtered_with_test)
+    met = orc.entity_ranking_metrics(model, ent, rel, valid, [train, valid])
+    for k, v in met.items():
+        want = float(g["valid_" + k])
+        assert abs(v - want) <= 1e-6 * max(1.0, abs(want)), (k, v, want)
