@@ -145,6 +145,34 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
       if (B.q1) { rc = launch_fold_queries(B.model, 1 - B.combine, *B.q1, *B.p, n, n, Qw, ldq, st); if (rc) return rc; }
       Q = Qw;
     }
+    const char* env_v = getenv("B200KGE_TC_VERSION");
+    const int tc_version = env_v ? atoi(env_v) : 1;
+    if (tc_version == 3 && passes == 2) {
+      // EXPERIMENTAL pre-split fp16 path (presplit.cu + pairwise_tc3.cu): one launch derives the hi/lo
+      // planes of the folded queries and of the (gathered) candidate rows, one launch scores them.
+      const int Kp = (int)round_up(K, 64);
+      SplitSet SQ{Q, ldq, nullptr, 0, nq, nq, K, Kp, nullptr, nullptr, nullptr};
+      SplitSet ST{B.cand->base, B.cand->ld, B.cand->idx, f0.col_off, m, m + 32, K, Kp, nullptr, nullptr, nullptr};
+      SQ.hi = ws.take((size_t)nq * Kp * 2); SQ.lo = ws.take((size_t)nq * Kp * 2);
+      SQ.inv_scale = (float*)ws.take((size_t)nq * 4);
+      ST.hi = ws.take((size_t)m * Kp * 2); ST.lo = ws.take((size_t)m * Kp * 2);
+      ST.inv_scale = (float*)ws.take((size_t)(m + 32) * 4);
+      if (!SQ.hi || !SQ.lo || !SQ.inv_scale || !ST.hi || !ST.lo || !ST.inv_scale) {
+        set_error("workspace too small for the pre-split operand planes");
+        return B200KGE_ERR_WORKSPACE;
+      }
+      const int nch3 = tc3_nchunks(nq, m);
+      if (epi_kind == EPI_BCE || epi_kind == EPI_KL) {
+        const int F = (epi_kind == EPI_BCE) ? 2 : 5;
+        P.part = (float*)ws.take((size_t)nq * nch3 * F * 4);
+        if (!P.part) { set_error("workspace too small for loss partials"); return B200KGE_ERR_WORKSPACE; }
+        if (part_out) *part_out = P.part;
+      }
+      P.nchunks = nch3;
+      if (nchunks_out) *nchunks_out = nch3;
+      if ((rc = launch_presplit(ST, SQ, st))) return rc;
+      return launch_pairwise_tc3(epi_kind, SQ, ST, P, st);
+    }
     const float* T = B.cand->base + f0.col_off;
     int64_t ldt = B.cand->ld;
     if (B.cand->idx) {
@@ -157,8 +185,7 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
     // The 1-CTA kernel is the default: on B200 it measured faster than the CTA-pair (cta_group::2)
     // kernel at every batch size once the epilogue stopped being the bottleneck
     // (profiles/r1_notes.md).  B200KGE_TC_VERSION=2 selects the pair kernel (kept for experiments).
-    const char* env_v = getenv("B200KGE_TC_VERSION");
-    const bool pair = env_v && atoi(env_v) == 2;
+    const bool pair = tc_version == 2;
     const int nch = pair ? tc2_nchunks(nq, m) : tc_nchunks(nq, m);
     if (epi_kind == EPI_BCE || epi_kind == EPI_KL) {
       const int F = (epi_kind == EPI_BCE) ? 2 : 5;
@@ -270,6 +297,11 @@ size_t b200kge_workspace_bytes(int model, int64_t n, int64_t m, int32_t D, int c
   if (nch < 320) nch = 320;                              // tensor-core kernels: <= 2 * #SMs chunks per row
   b += (size_t)nq * nch * 5 * 4 + 256;                   // loss partials
   b += (size_t)n * 3 * 8 + (size_t)n * 5 * 8 + 4096;     // host entry: triples, s/p/o, labels, scalar, finaliser scratch
+  { const char* env_v = getenv("B200KGE_TC_VERSION");
+    if (env_v && atoi(env_v) == 3) {                     // experimental pre-split fp16 planes + row scales
+      const int64_t Kp = round_up(D, 64);
+      b += 2 * ((size_t)nq * Kp * 2 + 256) + 2 * ((size_t)m * Kp * 2 + 256) + (size_t)(nq + m + 32) * 4 + 512;
+    } }
   return b + 4096;
 }
 

@@ -1,0 +1,284 @@
+// pairwise_tc3.cu — tcgen05 1-vs-N scorer on PRE-SPLIT fp16 operand planes.  EXPERIMENTAL: selected with
+// B200KGE_TC_VERSION=3 (the default is pairwise_tc.cu); same scores, losses and rank counts, different
+// operand path.
+//
+//   S[q, e] = qs[q] * ts[e] * sum_k (Qh[q,k]*Th[e,k] + Qh[q,k]*Tl[e,k] + Ql[q,k]*Th[e,k])
+//
+// Qh/Ql, Th/Tl: fp16 hi/lo planes of the row-scaled folded queries / entity table written once per call by
+// presplit.cu (qs, ts: per-row powers of two).  Why (analysis of the default kernel, profiles/r1_notes.md):
+// at M=128 x N=256 every tcgen05.mma streams 12 KB of operands from shared memory in 128 clk (96 of the
+// SM's 128 B/clk), so the in-kernel split of pairwise_tc.cu (raw tile written by TMA, read and re-written
+// by the splitter warps: 144 KB of extra shared-memory traffic per 32-wide K chunk on top of the MMAs'
+// 96 KB) is what bounds it.  Each table tile is consumed by every query tile (16x at n=1024, both
+// directions), so the split is done ONCE in HBM instead (presplit.cu: 4 B read + 4 B written per element,
+// the planes take exactly the bytes of the raw table) and this kernel is a pure TMA -> MMA -> epilogue
+// pipeline: per 64-wide K chunk 96 KB land by TMA and 12 MMAs (6 f16 slots per 32 elements instead of 8)
+// read 144 KB; nothing else touches shared memory in the main loop.
+//
+// Pipeline: ring of 4 slots of 48 KB = (query plane box 16 KB | table plane box 32 KB).  K chunk c uses
+// slots 2c%4 (hi planes) and 2c%4+1 (lo planes): the hi*hi MMAs start when only the hi half has landed.
+//   full[s]   TMA bytes landed                          -> MMA
+//   free[s]   MMAs reading slot s retired (commit)      -> TMA producer
+// CTA = 12 warps, one CTA per SM, persistent over (query tile, range of entity tiles):
+//   warp 0 TMA producer | warp 1 MMA issuer + TMEM alloc | warps 2-3 idle | warps 4-11 epilogue
+// (warp numbering as in pairwise_tc.cu so the epilogue code is shared verbatim).  Tile = 128 queries x <=256
+// entities, 2 TMEM accumulators of 256 columns.
+#include "tc_common.cuh"
+
+namespace b200kge {
+
+namespace {
+
+constexpr int TM = 128;             // queries per tile  (UMMA M)
+constexpr int TN = 256;             // max entities per tile (UMMA N)
+constexpr int TKH = 64;             // halfs per K chunk (128 B swizzle atom)
+constexpr int NSLOT = 4;
+constexpr int A_BYTES = TM * TKH * 2;   // 16 KB
+constexpr int B_BYTES = TN * TKH * 2;   // 32 KB
+constexpr int SLOT_BYTES = A_BYTES + B_BYTES;
+using tc::EPI_WARPS;
+using tc::STG_LD;
+constexpr int NTHREADS3 = 12 * 32;
+constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + NSLOT * SLOT_BYTES + STG_BYTES + 256 /*barriers*/;
+constexpr int TMEM_COLS = 512;
+
+struct Tc3Params {
+  int64_t nq, m;
+  int nk;           // K chunks of 64 halfs (planes are zero padded to nk * 64)
+  int q_tiles, e_tiles, echunks;
+  int tn;           // entities per tile (multiple of 16, <= TN)
+  const float* q_scale;   // [nq]
+  const float* t_scale;   // [m + 32], zero beyond m
+  EpiParams epi;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(NTHREADS3, 1)
+pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+                    const __grid_constant__ CUtensorMap tmTh, const __grid_constant__ CUtensorMap tmTl,
+                    const Tc3Params prm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* stg = reinterpret_cast<float*>(smem + NSLOT * SLOT_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSLOT * SLOT_BYTES + STG_BYTES);
+  uint64_t* full = bars;                  // [NSLOT]
+  uint64_t* free_ = bars + NSLOT;         // [NSLOT]
+  uint64_t* tfull = bars + 2 * NSLOT;     // [2]
+  uint64_t* tempty = tfull + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk = prm.nk;
+  const int total_work = prm.q_tiles * prm.echunks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmQh);
+    ptx::prefetch_tensormap(&tmQl);
+    ptx::prefetch_tensormap(&tmTh);
+    ptx::prefetch_tensormap(&tmTl);
+    for (int s = 0; s < NSLOT; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&free_[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tfull[b], 1);
+      ptx::mbar_init(&tempty[b], EPI_WARPS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto work_range = [&](int w, int& qt, int& et0, int& et1, int& ec) {
+    qt = w / prm.echunks;
+    ec = w - qt * prm.echunks;
+    const int base = prm.e_tiles / prm.echunks, rem = prm.e_tiles % prm.echunks;
+    et0 = ec * base + (ec < rem ? ec : rem);
+    et1 = et0 + base + (ec < rem ? 1 : 0);
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer =========================================
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)(A_BYTES + prm.tn * TKH * 2);
+      uint32_t c = 0;      // K-chunk counter; chunk c owns slots 2*(c&1) and 2*(c&1)+1, use number c>>1
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int qt, et0, et1, ec;
+        work_range(w, qt, et0, et1, ec);
+        for (int et = et0; et < et1; ++et) {
+          for (int kc = 0; kc < nk; ++kc, ++c) {
+            const uint32_t par = ((c >> 1) & 1) ^ 1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int s = 2 * (int)(c & 1) + h;
+              ptx::mbar_wait(&free_[s], par);
+              uint8_t* sp = smem + s * SLOT_BYTES;
+              ptx::mbar_arrive_expect_tx(&full[s], tx);
+              ptx::tma_load_2d(sp, h ? &tmQl : &tmQh, &full[s], kc * TKH, qt * TM);
+              ptx::tma_load_2d(sp + A_BYTES, h ? &tmTl : &tmTh, &full[s], kc * TKH, et * prm.tn);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ============================================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_f16(TM, prm.tn);
+      uint32_t c = 0, it = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int qt, et0, et1, ec;
+        work_range(w, qt, et0, et1, ec);
+        for (int et = et0; et < et1; ++et, ++it) {
+          const int b = it & 1;
+          ptx::mbar_wait(&tempty[b], ((it >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(b * TN);
+          for (int kc = 0; kc < nk; ++kc, ++c) {
+            const int sh = 2 * (int)(c & 1), sl = sh + 1;
+            const uint32_t par = (c >> 1) & 1;
+            const uint32_t a_hi = ptx::smem_u32(smem + sh * SLOT_BYTES), b_hi = a_hi + A_BYTES;
+            const uint32_t a_lo = ptx::smem_u32(smem + sl * SLOT_BYTES), b_lo = a_lo + A_BYTES;
+            ptx::mbar_wait(&full[sh], par);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < TKH / 16; ++k)
+              ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
+                             (kc > 0 || k > 0) ? 1u : 0u);
+            ptx::mbar_wait(&full[sl], par);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < TKH / 16; ++k) {
+              ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_lo + k * 32), idesc, 1u);
+              ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(a_lo + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+            }
+            ptx::umma_commit(&free_[sh]);
+            ptx::umma_commit(&free_[sl]);
+          }
+          ptx::umma_commit(&tfull[b]);             // accumulator complete
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ==============================================
+    const int quad = warp & 3;                // TMEM lanes [32*quad, +32)
+    const int half = (warp - 4) >> 2;         // columns [128*half, +128) of the accumulator
+    float* my_stg = stg + (warp - 4) * 32 * STG_LD;
+    const EpiParams& P = prm.epi;
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      int qt, et0, et1, ec;
+      work_range(w, qt, et0, et1, ec);
+      const int64_t row = (int64_t)qt * TM + quad * 32 + lane;   // this thread's query row
+      const bool row_ok = row < prm.nq;
+      RowState<EPI> st;
+      st.init();
+      const float aux = row_ok ? epi_row_aux<EPI>(P, row) : 0.f;
+      const float qs = row_ok ? __ldg(prm.q_scale + row) : 0.f;
+      for (int et = et0; et < et1; ++et, ++it) {
+        const int b = it & 1;
+        ptx::mbar_wait(&tfull[b], (it >> 1) & 1);
+        ptx::tc_fence_after();
+        const int64_t tile_end = (int64_t)(et + 1) * prm.tn;
+        tc::epilogue_tile<EPI, 4, true>(P, st, aux,
+                                        tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TN + half * 128),
+                                        (int64_t)qt * TM + quad * 32, (int64_t)et * prm.tn + half * 128, prm.nq,
+                                        tile_end < prm.m ? tile_end : prm.m, my_stg, lane, qs, prm.t_scale);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[b]);
+      }
+      if constexpr (EPI != EPI_STORE) {
+        if (row_ok) epi_flush<EPI>(P, st, row, ec * 2 + half);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+using tc::num_sms;
+
+// same tiling policy as pairwise_tc.cu: tile width (multiple of 16 in [128, 256]) minimising the per-SM
+// makespan in columns, entity tiles split into `echunks` ranges so that q_tiles * echunks ~ #SMs
+void plan3(int64_t nq, int64_t m, int& q_tiles, int& e_tiles, int& echunks, int& tn) {
+  q_tiles = (int)((nq + TM - 1) / TM);
+  if (q_tiles < 1) q_tiles = 1;
+  const int units = num_sms();
+  int64_t best_cost = -1;
+  tn = TN;
+  for (int cand = TN; cand >= 128; cand -= 16) {
+    const int64_t et = (m + cand - 1) / cand;
+    int per = units / q_tiles; if (per < 1) per = 1; if (per > et) per = (int)et;
+    const int64_t tiles_per_cta = (et + per - 1) / per;
+    const int64_t waves = ((int64_t)q_tiles * per + units - 1) / units;
+    const int64_t cost = waves * tiles_per_cta * cand + tiles_per_cta * 24;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; tn = cand; }
+  }
+  e_tiles = (int)((m + tn - 1) / tn);
+  int per = units / q_tiles;
+  if (per < 1) per = 1;
+  if (per > e_tiles) per = e_tiles;
+  echunks = per;
+}
+
+template <int EPI>
+int launch_k3(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& th, const CUtensorMap& tl,
+              const Tc3Params& prm, int grid, cudaStream_t st) {
+  auto kern = pairwise_tc3_kernel<EPI>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pairwise_tc3_kernel)");
+  profile_begin(st);
+  kern<<<grid, NTHREADS3, SMEM_BYTES, st>>>(qh, ql, th, tl, prm);
+  profile_end(st);
+  B2K_LAUNCH_CHECK("pairwise_tc3_kernel");
+  return 0;
+}
+
+}  // namespace
+
+int tc3_nchunks(int64_t nq, int64_t m) {
+  int qt, et, ec, tn;
+  plan3(nq, m, qt, et, ec, tn);
+  return 2 * ec;
+}
+
+int launch_pairwise_tc3(int epi_kind, const SplitSet& Q, const SplitSet& T, const EpiParams& P, cudaStream_t st) {
+  const int64_t nq = Q.rows, m = T.rows;
+  if (nq == 0 || m == 0) return 0;
+  if (Q.Kp != T.Kp || Q.Kp % TKH != 0) { set_error("operand planes disagree on the padded reduction length"); return B200KGE_ERR_INVALID; }
+  Tc3Params prm;
+  prm.nq = nq; prm.m = m; prm.nk = Q.Kp / TKH;
+  plan3(nq, m, prm.q_tiles, prm.e_tiles, prm.echunks, prm.tn);
+  prm.q_scale = Q.inv_scale; prm.t_scale = T.inv_scale;
+  CUtensorMap mQh, mQl, mTh, mTl;
+  int rc;
+  if ((rc = tc::make_map_f16(&mQh, Q.hi, nq, Q.Kp, Q.Kp, TM))) return rc;
+  if ((rc = tc::make_map_f16(&mQl, Q.lo, nq, Q.Kp, Q.Kp, TM))) return rc;
+  if ((rc = tc::make_map_f16(&mTh, T.hi, m, T.Kp, T.Kp, prm.tn))) return rc;
+  if ((rc = tc::make_map_f16(&mTl, T.lo, m, T.Kp, T.Kp, prm.tn))) return rc;
+  prm.epi = P;
+  prm.epi.nchunks = 2 * prm.echunks;   // two epilogue warps (column halves) per row
+  const int total = prm.q_tiles * prm.echunks;
+  const int grid = total < num_sms() ? total : num_sms();
+  switch (epi_kind) {
+    case EPI_STORE: return launch_k3<EPI_STORE>(mQh, mQl, mTh, mTl, prm, grid, st);
+    case EPI_BCE:   return launch_k3<EPI_BCE>(mQh, mQl, mTh, mTl, prm, grid, st);
+    case EPI_KL:    return launch_k3<EPI_KL>(mQh, mQl, mTh, mTl, prm, grid, st);
+    case EPI_RANK:  return launch_k3<EPI_RANK>(mQh, mQl, mTh, mTl, prm, grid, st);
+  }
+  set_error("bad epilogue kind %d", epi_kind);
+  return B200KGE_ERR_INVALID;
+}
+
+}  // namespace b200kge

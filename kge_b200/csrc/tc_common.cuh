@@ -209,12 +209,16 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& P, RowState<EPI>& s
 
 // Epilogue of NCH 32-column chunks of one accumulator for the warp owning TMEM lanes
 // [32*quadrant, +32) and columns [col_first, col_first + 32*NCH) of the tile.
-template <int EPI, int NCH>
+// SCALED (pre-split fp16 kernel, pairwise_tc3.cu): the accumulator holds the product of row-scaled
+// operands; score = acc * row_scale * col_scale[column] (both exact powers of two).  col_scale must be
+// readable (and 16-byte aligned) for 32 floats from any chunk start < m.
+template <int EPI, int NCH, bool SCALED = false>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& P, RowState<EPI>& st, float aux,
                                               uint32_t tmem_acc /* base + lane<<16 + first column */,
                                               int64_t tile_row0 /* first row of this warp's 32 */,
                                               int64_t e0 /* global column of the first chunk */, int64_t nq,
-                                              int64_t m, float* my_stg, int lane) {
+                                              int64_t m, float* my_stg, int lane, float row_scale = 1.f,
+                                              const float* __restrict__ col_scale = nullptr) {
   const int64_t row = tile_row0 + lane;
   const bool row_ok = row < nq;
 #pragma unroll 1
@@ -223,7 +227,21 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& P, RowState<EPI>&
     if (c0 >= m) break;                                   // warp-uniform: chunk entirely out of range
     uint32_t v[32];
     ptx::tmem_ld_32x32(tmem_acc + (uint32_t)(j * 32), v);
-    ptx::tmem_ld_wait();
+    if constexpr (SCALED) {
+      float4 cs[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) cs[g] = __ldg(reinterpret_cast<const float4*>(col_scale + c0) + g);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        v[4 * g + 0] = __float_as_uint(__uint_as_float(v[4 * g + 0]) * (row_scale * cs[g].x));
+        v[4 * g + 1] = __float_as_uint(__uint_as_float(v[4 * g + 1]) * (row_scale * cs[g].y));
+        v[4 * g + 2] = __float_as_uint(__uint_as_float(v[4 * g + 2]) * (row_scale * cs[g].z));
+        v[4 * g + 3] = __float_as_uint(__uint_as_float(v[4 * g + 3]) * (row_scale * cs[g].w));
+      }
+    } else {
+      ptx::tmem_ld_wait();
+    }
     if constexpr (EPI == EPI_STORE) {
       // transpose a 32x32 block through smem: each store instruction then writes 32 consecutive
       // entities of ONE query row (coalesced 128 B) whatever the row stride is
@@ -330,6 +348,26 @@ inline int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
   return 0;
 }
 
+// 2-D fp16 tensor map over [rows, cols] halfs with row stride ld halfs; box = 64 x box_rows (128-byte
+// rows, 128-byte swizzle).
+inline int make_map_f16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return B200KGE_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(f16) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows,
+              (long long)cols, (long long)ld);
+    return B200KGE_ERR_CUDA;
+  }
+  return 0;
+}
+
 inline int num_sms() {
   static int n = 0;
   if (!n) {
@@ -348,5 +386,19 @@ int tc2_nchunks(int64_t nq, int64_t m);
 int launch_pairwise_tc2(int epi_kind, int passes, const float* Q, int64_t ldq,
                         int64_t nq, const float* T, int64_t ldt, int64_t m, int K,
                         const EpiParams& P, cudaStream_t st);
+
+// Pre-split fp16 kernel (presplit.cu + pairwise_tc3.cu), experimental: B200KGE_TC_VERSION=3.
+// One row set of the operand split: rows of `src` (optionally gathered through idx, starting at column
+// col_off, K columns) -> hi/lo fp16 planes [rows, Kp] (Kp = round_up(K, 64), zero padded) and the
+// per-row power-of-two factor inv_scale[rows_pad] that undoes the row scaling (0 beyond `rows`).
+struct SplitSet {
+  const float* src; int64_t ld; const int64_t* idx; int col_off;
+  int64_t rows, rows_pad;
+  int K, Kp;
+  void* hi; void* lo; float* inv_scale;
+};
+int launch_presplit(const SplitSet& A, const SplitSet& B, cudaStream_t st);   // B.rows may be 0
+int tc3_nchunks(int64_t nq, int64_t m);
+int launch_pairwise_tc3(int epi_kind, const SplitSet& Q, const SplitSet& T, const EpiParams& P, cudaStream_t st);
 
 }  // namespace b200kge
