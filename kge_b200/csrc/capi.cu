@@ -147,8 +147,8 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
     }
     const char* env_v = getenv("B200KGE_TC_VERSION");
     const int tc_version = env_v ? atoi(env_v) : 1;
-    if (tc_version == 3 && passes == 2) {
-      // EXPERIMENTAL pre-split fp16 path (presplit.cu + pairwise_tc3.cu): one launch derives the hi/lo
+    if ((tc_version == 3 || tc_version == 4) && passes == 2) {
+      // EXPERIMENTAL pre-split fp16 path (presplit.cu + pairwise_tc3.cu | pairwise_tc4.cu): one launch derives the hi/lo
       // planes of the folded queries and of the (gathered) candidate rows, one launch scores them.
       const int Kp = (int)round_up(K, 64);
       SplitSet SQ{Q, ldq, nullptr, 0, nq, nq, K, Kp, nullptr, nullptr, nullptr};
@@ -161,7 +161,7 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
         set_error("workspace too small for the pre-split operand planes");
         return B200KGE_ERR_WORKSPACE;
       }
-      const int nch3 = tc3_nchunks(nq, m);
+      const int nch3 = tc_version == 4 ? tc4_nchunks(nq, m) : tc3_nchunks(nq, m);
       if (epi_kind == EPI_BCE || epi_kind == EPI_KL) {
         const int F = (epi_kind == EPI_BCE) ? 2 : 5;
         P.part = (float*)ws.take((size_t)nq * nch3 * F * 4);
@@ -171,6 +171,7 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
       P.nchunks = nch3;
       if (nchunks_out) *nchunks_out = nch3;
       if ((rc = launch_presplit(ST, SQ, st))) return rc;
+      if (tc_version == 4) return launch_pairwise_tc4(epi_kind, SQ, ST, P, st);
       return launch_pairwise_tc3(epi_kind, SQ, ST, P, st);
     }
     const float* T = B.cand->base + f0.col_off;
@@ -298,7 +299,7 @@ size_t b200kge_workspace_bytes(int model, int64_t n, int64_t m, int32_t D, int c
   b += (size_t)nq * nch * 5 * 4 + 256;                   // loss partials
   b += (size_t)n * 3 * 8 + (size_t)n * 5 * 8 + 4096;     // host entry: triples, s/p/o, labels, scalar, finaliser scratch
   { const char* env_v = getenv("B200KGE_TC_VERSION");
-    if (env_v && atoi(env_v) == 3) {                     // experimental pre-split fp16 planes + row scales
+    if (env_v && (atoi(env_v) == 3 || atoi(env_v) == 4)) {   // experimental pre-split fp16 planes + row scales
       const int64_t Kp = round_up(D, 64);
       b += 2 * ((size_t)nq * Kp * 2 + 256) + 2 * ((size_t)m * Kp * 2 + 256) + (size_t)(nq + m + 32) * 4 + 512;
     } }

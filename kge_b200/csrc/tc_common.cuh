@@ -387,7 +387,7 @@ int launch_pairwise_tc2(int epi_kind, int passes, const float* Q, int64_t ldq,
                         int64_t nq, const float* T, int64_t ldt, int64_t m, int K,
                         const EpiParams& P, cudaStream_t st);
 
-// Pre-split fp16 kernel (presplit.cu + pairwise_tc3.cu), experimental: B200KGE_TC_VERSION=3.
+// Pre-split fp16 kernels (presplit.cu + pairwise_tc3.cu / pairwise_tc4.cu), experimental: B200KGE_TC_VERSION=3|4.
 // One row set of the operand split: rows of `src` (optionally gathered through idx, starting at column
 // col_off, K columns) -> hi/lo fp16 planes [rows, Kp] (Kp = round_up(K, 64), zero padded) and the
 // per-row power-of-two factor inv_scale[rows_pad] that undoes the row scaling (0 beyond `rows`).
@@ -400,5 +400,8 @@ struct SplitSet {
 int launch_presplit(const SplitSet& A, const SplitSet& B, cudaStream_t st);   // B.rows may be 0
 int tc3_nchunks(int64_t nq, int64_t m);
 int launch_pairwise_tc3(int epi_kind, const SplitSet& Q, const SplitSet& T, const EpiParams& P, cudaStream_t st);
+// CTA-pair version on the same planes (pairwise_tc4.cu), experimental: B200KGE_TC_VERSION=4.
+int tc4_nchunks(int64_t nq, int64_t m);
+int launch_pairwise_tc4(int epi_kind, const SplitSet& Q, const SplitSet& T, const EpiParams& P, cudaStream_t st);
 
 }  // namespace b200kge

@@ -1,0 +1,30 @@
+#!/bin/bash
+# Validate and time the EXPERIMENTAL tensor-core paths (B200KGE_TC_VERSION=3|4) on a B200:
+#   gpurun --timeout 900 -- 'bash scripts/exp_check.sh'
+# Every step runs under its own `timeout` so that a hanging kernel ends with its process, not with the box.
+# Results land in gpurun_out/exp_*.log / exp_summary.txt / bench_v*.json.
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+: > gpurun_out/exp_summary.txt
+export B200KGE_EXPERIMENTAL=1
+for v in tc3 tc4-forward tc4-direct; do
+  timeout 180 python -m pytest tests/test_gpu_experimental.py -x -q -k "$v" > "gpurun_out/exp_$v.log" 2>&1
+  echo "$v pytest rc=$?" >> gpurun_out/exp_summary.txt
+  tail -3 "gpurun_out/exp_$v.log" >> gpurun_out/exp_summary.txt
+done
+for cfg in "1 0" "3 0" "4 0" "4 1"; do
+  set -- $cfg
+  B200KGE_TC_VERSION=$1 B200KGE_TC4_DIRECT=$2 timeout 180 python bench.py --steps 100 --warmup 5 \
+    > "gpurun_out/bench_v$1_d$2.json" 2> "gpurun_out/bench_v$1_d$2.err"
+  echo "bench v$1 direct=$2 rc=$?" >> gpurun_out/exp_summary.txt
+  python - "gpurun_out/bench_v$1_d$2.json" >> gpurun_out/exp_summary.txt <<'PY'
+import json, sys
+try:
+    j = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print("  ms_per_step", j["ms_per_step"], "value", j["value"], "kernel_ms", j["roofline"].get("kernel_ms"), "e2e", j["e2e"]["value"])
+except Exception as ex:
+    print("  no bench line:", ex)
+PY
+done
+cat gpurun_out/exp_summary.txt

@@ -30,6 +30,20 @@ def eng():
     return engine
 
 
+VARIANTS = [("3", "0"), ("4", "0"), ("4", "1")]   # (B200KGE_TC_VERSION, B200KGE_TC4_DIRECT)
+
+
+@pytest.fixture(params=VARIANTS, ids=["tc3", "tc4-forward", "tc4-direct"])
+def variant(request, monkeypatch):
+    """Selects the experimental kernel for the duration of a test (the default path is restored afterwards)."""
+    ver, direct = request.param
+
+    def select():
+        monkeypatch.setenv("B200KGE_TC_VERSION", ver)
+        monkeypatch.setenv("B200KGE_TC4_DIRECT", direct)
+    return select
+
+
 def _load(name):
     z = np.load(os.path.join(GOLDEN, name))
     return {k: torch.from_numpy(z[k]) if z[k].ndim else z[k].item() for k in z.files}
@@ -44,8 +58,8 @@ def _assert_close(got, ref, what, tol=TOL):
     assert err <= tol * rms, f"{what}: max|d|={err:.3e} rms={rms:.3e} ratio={err / rms:.2e}"
 
 
-def test_presplit_fp16_golden(eng, monkeypatch):
-    monkeypatch.setenv("B200KGE_TC_VERSION", "3")
+def test_presplit_fp16_golden(eng, variant):
+    variant()
     for fname, model in (("scores_complex.npz", "complex"), ("scores_distmult.npz", "distmult"),
                          ("scores_simple.npz", "simple"), ("scores_complex_sigma01.npz", "complex")):
         g = _load(fname)
@@ -59,11 +73,11 @@ def test_presplit_fp16_golden(eng, monkeypatch):
 
 
 @pytest.mark.parametrize("sigma", [1.0, 1e-3])
-def test_presplit_fp16_medium(eng, monkeypatch, sigma):
+def test_presplit_fp16_medium(eng, variant, sigma):
     """Dense scores, gathered candidate subsets, fused BCE/KL, fused rank counting at ragged sizes (tiles cut in
     both dimensions, K not a multiple of the 64-wide chunk for RESCAL/CP), including tiny-valued tables that a
     fixed fp16 scale would flush."""
-    monkeypatch.setenv("B200KGE_TC_VERSION", "3")
+    variant()
     for model, D in (("complex", 192), ("distmult", 64), ("simple", 128), ("rescal", 40), ("cp", 200)):
         E, R, n = 6007, 7, 389
         ent, rel = orc.make_tables(model, E, R, D, sigma=sigma)
@@ -88,14 +102,14 @@ def test_presplit_fp16_medium(eng, monkeypatch, sigma):
         assert torch.equal(r.cpu(), rr) and torch.equal(t.cpu(), tt)
 
 
-def test_presplit_fp16_headline_shape(eng, monkeypatch):
+def test_presplit_fp16_headline_shape(eng, variant):
     """BASELINE configs[1] shape: loss of the experimental path == loss of the default path to 1e-5."""
     E, R, D, n = 14541, 237, 512, 1024
     ent, rel = orc.make_tables("complex", E, R, D)
     tri = orc.make_triples(E, R, n)
     ce, cr, ct = ent.cuda(), rel.cuda(), tri.cuda()
     base = float(eng.train_1vsall_forward("complex", ce, cr, ct, "bce"))
-    monkeypatch.setenv("B200KGE_TC_VERSION", "3")
+    variant()
     got = float(eng.train_1vsall_forward("complex", ce, cr, ct, "bce"))
     assert abs(got - base) <= 1e-5 * abs(base), (got, base)
     ref = orc.score_sp("complex", ent, rel, tri[:64, S], tri[:64, P])
