@@ -213,6 +213,37 @@ int b200kge_train_1vsall_forward_host(int model, float l_norm, int precision,
                                       float offset, float* loss_host, void* workspace,
                                       size_t workspace_bytes, b200kge_stream_t stream);
 
+/* ---- host-side label plumbing (CPU; no device involved) ------------------------------------------
+ * The key -> all-values index that KvsAll training and filtered entity ranking build their label and
+ * filter coordinates from, in CSR form (row offsets + column ids) — what the device epilogues take
+ * instead of coord_to_sparse_tensor(...).to_dense() (kge/job/util.py:32-60).
+ *
+ * b200kge_kvsall_index_build replaces KvsAllIndex.__init__ (kge/indexing.py:19-55,178-194):
+ *   triples [n,3] (host), key columns (key_col0, key_col1) and value column = a permutation of 0,1,2.
+ *   keys_out [n,2], offsets_out [n+1], values_out [n] are caller-allocated at capacity n;
+ *   *num_keys receives the number of distinct keys.  Keys ascend lexicographically (np.unique axis=0),
+ *   values ascend within a key, duplicate triples keep their duplicate values — element for element
+ *   the reference's _keys / _values_offset / _values. */
+int b200kge_kvsall_index_build(const int64_t* triples, int64_t n, int key_col0, int key_col1,
+                               int value_col, int64_t* keys_out, int64_t* offsets_out,
+                               int64_t* values_out, int64_t* num_keys);
+
+/* KvsAllIndex.get_all (kge/indexing.py:113-166) and get_sp_po_coords_from_spo_batch
+ * (kge/job/util.py:6-30): for each of nq query keys [nq,2] the values of that key (none if the key
+ * is absent), as CSR: offsets_out [nq+1] (offsets_out[nq] = nnz), cols_out [nnz] = value +
+ * col_shift (col_shift = num_entities for the po half of a [n, 2E] label matrix).  Call with
+ * cols_out = NULL to size, then again with the buffer. */
+int b200kge_kvsall_lookup(const int64_t* keys, const int64_t* offsets, const int64_t* values,
+                          int64_t num_keys, const int64_t* query_keys, int64_t nq,
+                          int64_t col_shift, int64_t* offsets_out, int64_t* cols_out);
+
+/* The collate step of KvsAll training for one query type (kge/job/train_KvsAll.py:116-203): example
+ * ids are key indexes; queries_out [nb,2] receives their keys, offsets_out [nb+1] / cols_out [nnz]
+ * their labels as CSR (cols_out = NULL to size). */
+int b200kge_kvsall_gather(const int64_t* keys, const int64_t* offsets, const int64_t* values,
+                          int64_t num_keys, const int64_t* examples, int64_t nb,
+                          int64_t* queries_out, int64_t* offsets_out, int64_t* cols_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,12 @@ SIGNATURES = {
     "b200kge_train_1vsall_forward_host": (C.c_int, [C.c_int, C.c_float, C.c_int, _RP, _RP, C.c_void_p,
                                                     C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                                     C.c_size_t, C.c_void_p]),
+    "b200kge_kvsall_index_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
+    "b200kge_kvsall_lookup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                        C.c_int64, C.c_void_p, C.c_void_p]),
+    "b200kge_kvsall_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

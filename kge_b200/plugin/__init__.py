@@ -203,3 +203,26 @@ B200TransE = _model("B200TransE", "transe", TransE, TransEScorer)
 B200RotatE = _model("B200RotatE", "rotate", RotatE, RotatEScorer)
 
 __all__ = ["B200ComplEx", "B200DistMult", "B200SimplE", "B200CP", "B200Rescal", "B200TransE", "B200RotatE"]
+
+
+def install_native_indexes(dataset, splits=("train", "valid", "test")):
+    """Serve the dataset's `{split}_{sp|po|so}_to_{o|s|p}` indexes (kge/indexing.py:197-235) from
+    kge_b200.indexing.KvsAllIndex — same attributes and accessors as the reference class (TrainingJobKvsAll's
+    collate and EntityRankingJob's label lookup use it unchanged), built by the native sort/unique/lookup code
+    instead of numpy + a numba dict.  Call once after the dataset is created."""
+    from ..indexing import KvsAllIndex
+
+    def make(split, key, cols, val, name):
+        def fn(ds):
+            if not ds._indexes.get(name):
+                ds._indexes[name] = KvsAllIndex(ds.split(split), cols, val, torch.IntTensor)
+            ds.config.log("{} distinct {} pairs in {}".format(len(ds._indexes[name]), key, split), prefix="  ")
+            return ds._indexes.get(name)
+        return fn
+
+    for split in splits:
+        for key, cols, val, v in (("sp", [0, 1], 2, "o"), ("po", [1, 2], 0, "s"), ("so", [0, 2], 1, "p")):
+            name = f"{split}_{key}_to_{v}"
+            dataset.index_functions[name] = make(split, key, cols, val, name)
+            dataset._indexes.pop(name, None)
+    return dataset

@@ -225,6 +225,37 @@ def gen_jobs(model, tag):
     print("wrote jobs", tag, {k: float(v) for k, v in out.items() if np.ndim(v) == 0})
 
 
+def gen_index():
+    """KvsAllIndex (kge/indexing.py) and the sp/po coordinate lookup (kge/job/util.py) of the live reference on
+    random triples with duplicate triples, duplicate keys and query keys absent from the index."""
+    ref_shim.import_reference()
+    from kge.indexing import KvsAllIndex
+    from kge.job.util import get_sp_po_coords_from_spo_batch
+
+    g = torch.Generator().manual_seed(21)
+    E, R, n = 23, 4, 300
+    tri = torch.stack([torch.randint(0, E, (n,), generator=g), torch.randint(0, R, (n,), generator=g),
+                       torch.randint(0, E, (n,), generator=g)], 1).int()
+    tri[10:20] = tri[0:10]                       # exact duplicate triples
+    out = dict(triples=_np(tri), num_entities=np.int64(E))
+    idx = {}
+    for key, (cols, val) in (("sp", ([S, P], O)), ("po", ([P, O], S)), ("so", ([S, O], P))):
+        ix = KvsAllIndex(tri, cols, val, list)
+        idx[key] = ix
+        out[f"{key}_keys"] = _np(ix._keys)
+        out[f"{key}_offsets"] = _np(ix._values_offset)
+        out[f"{key}_values"] = _np(ix._values)
+    batch = torch.stack([torch.randint(0, E + 3, (40,), generator=g), torch.randint(0, R, (40,), generator=g),
+                         torch.randint(0, E + 3, (40,), generator=g)], 1).int()   # some keys do not exist
+    batch[:8] = tri[:8]
+    out["batch"] = _np(batch)
+    out["sp_get_all"] = _np(idx["sp"].get_all(batch[:, [S, P]]))
+    out["po_get_all"] = _np(idx["po"].get_all(batch[:, [P, O]]))
+    out["sp_po_coords"] = _np(get_sp_po_coords_from_spo_batch(batch, E, idx["sp"], idx["po"]))
+    np.savez_compressed(os.path.join(HERE, "index.npz"), **out)
+    print("wrote index", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
+
+
 def main():
     torch.manual_seed(0)
     E, R, n = 97, 7, 13
@@ -240,6 +271,7 @@ def main():
         gen_ns(model, 61, 5, 16 if model == "rescal" else 32, 6, 10, 1.0, model)
     for model in ("complex", "transe"):
         gen_jobs(model, model)
+    gen_index()
 
 
 if __name__ == "__main__":

@@ -79,3 +79,61 @@ def test_plugin_options_propagate():
     w = r.get_p_embedder()._embeddings.weight
     assert float(w.abs().max()) <= 3.1416 and r.get_scorer()._b200_l_norm() == 1.0     # uniform(-pi, pi) phases
     assert r._normalize_phases is True
+
+
+def test_native_indexes_serve_the_reference_jobs():
+    """The reference's own KvsAll training job (collate + label construction) and entity-ranking job (filter
+    label lookup) run on kge_b200's native KvsAllIndex and produce the same traces as on their own index."""
+    import tempfile
+
+    ref_shim.import_reference()
+    from kge import Config, Dataset
+    from kge.job import Job
+    import kge_b200.plugin as plugin
+    from kge_b200.indexing import KvsAllIndex
+
+    E, R, D = 40, 4, 8
+    g = torch.Generator().manual_seed(4)
+    tri = lambda n: torch.stack([torch.randint(0, E, (n,), generator=g), torch.randint(0, R, (n,), generator=g),
+                                 torch.randint(0, E, (n,), generator=g)], 1).int()
+    splits = {"train": tri(120), "valid": tri(15), "test": tri(15)}
+
+    def run(native):
+        torch.manual_seed(0)
+        config = Config()
+        config.folder = tempfile.mkdtemp()
+        config.set("console.quiet", True)
+        config.set("model", "distmult")
+        config._import("distmult")
+        config.set("dataset.name", "synthetic")
+        config.set("dataset.num_entities", E)
+        config.set("dataset.num_relations", R)
+        config.set("dataset.pickle", False)
+        config.set("job.device", "cpu")
+        config.set("job.type", "train")
+        config.set("train.type", "KvsAll")
+        config.set("train.loss", "kl")
+        config.set("train.batch_size", 16)
+        config.set("KvsAll.label_smoothing", 0.1)
+        config.set("eval.batch_size", 8)
+        config.set_all({"lookup_embedder.dim": D})
+        ds = Dataset(config, None)
+        ds._triples = dict(splits)
+        ds._meta = {"entity_ids": [f"e{i}" for i in range(E)], "relation_ids": [f"r{i}" for i in range(R)]}
+        if native:
+            plugin.install_native_indexes(ds)
+        job = Job.create(config, ds)
+        job.is_forward_only = True
+        job._prepare()
+        if native:
+            assert all(isinstance(ix, KvsAllIndex) for ix in job.query_indexes)
+        torch.manual_seed(1)               # same shuffling of the batches
+        loss = job.run_epoch()["avg_loss"]
+        ev = job.valid_job
+        ev._prepare()
+        tr = ev._run()
+        return loss, tr["mean_reciprocal_rank_filtered"], tr["mean_rank_filtered"], tr["hits_at_10_filtered"]
+
+    a, b = run(False), run(True)
+    assert a[0] == pytest.approx(b[0], rel=1e-6)
+    assert a[1:] == b[1:]
