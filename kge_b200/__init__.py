@@ -5,7 +5,10 @@ One hot path of uma-pi1/kge (LibKGE), rebuilt as hand-written sm_100a CUDA behin
 CP / RESCAL (tcgen05 3xTF32) and TransE / RotatE (CUDA-core distance kernels), fused with BCE/KL
 loss, rank/tie counting and negative-sample gather+score.  No CPU fallback.
 """
-from . import _lib, engine  # noqa: F401
+from . import _lib, engine, indexing  # noqa: F401
 from .model import KgeModel, LookupEmbedder, RelationalScorer, KgeLoss, BatchNegativeSample  # noqa: F401
+from .evaluate import EntityRankingEvaluator  # noqa: F401
+from .indexing import KvsAllIndex  # noqa: F401
 
-__all__ = ["engine", "KgeModel", "LookupEmbedder", "RelationalScorer", "KgeLoss", "BatchNegativeSample"]
+__all__ = ["engine", "indexing", "KgeModel", "LookupEmbedder", "RelationalScorer", "KgeLoss", "BatchNegativeSample",
+           "EntityRankingEvaluator", "KvsAllIndex"]

@@ -402,31 +402,42 @@ def true_scores_sp_path(model, ent, rel, s, p, o, l_norm=1.0):
     return o_true, s_true
 
 
-def entity_ranking_metrics(model, ent, rel, eval_triples, filter_splits, l_norm=1.0,
+def entity_ranking_metrics(model, ent, rel, eval_triples, filter_splits, test_triples=None, l_norm=1.0,
                            tie_handling="rounded_mean_rank", hits_at_k=(1, 3, 10), rtol=1e-4, atol=1e-5):
     """EntityRankingJob._evaluate restated at small scale (eval_entity_ranking.py:103-487): for every
     evaluation triple rank the true object among all objects (sp_) and the true subject among all
-    subjects (_po); raw and filtered (known-true answers from `filter_splits` get +inf subtracted,
-    the query's own answer excepted :169-182,287-290); ranks are 0-based, metrics come from the rank
-    histogram over both directions (:620-649).  Returns {metric: value} with the reference's keys."""
+    subjects (_po); raw, filtered (known-true answers from `filter_splits` get +inf subtracted, the query's
+    own answer excepted :169-182,287-290) and, if `test_triples` is given, filtered_with_test (the test
+    split's answers filtered ON TOP of the already filtered scores :278-303).  Ranks are 0-based, metrics come
+    from the rank histogram over both directions (:620-649).  Returns {metric: value} with the reference's
+    keys."""
     E = ent.shape[0]
     s, p, o = eval_triples[:, S].long(), eval_triples[:, P].long(), eval_triples[:, O].long()
     n = len(s)
     scores = score_sp_po(model, ent, rel, s, p, o, None, l_norm)
     sp, po = scores[:, :E], scores[:, E:]
     o_true, s_true = sp[torch.arange(n), o], po[torch.arange(n), s]
-    known = torch.cat([t.long() for t in filter_splits], 0)
-    labels = torch.zeros((n, 2 * E), dtype=scores.dtype)
-    for i in range(n):
-        m_sp = (known[:, S] == s[i]) & (known[:, P] == p[i])
-        labels[i, known[m_sp, O]] = float("inf")
-        m_po = (known[:, P] == p[i]) & (known[:, O] == o[i])
-        labels[i, E + known[m_po, S]] = float("inf")
-    labels[torch.arange(n), o] = 0.0
-    labels[torch.arange(n), E + s] = 0.0
+
+    def label_matrix(known):
+        known = known.long()
+        labels = torch.zeros((n, 2 * E), dtype=scores.dtype)
+        for i in range(n):
+            m_sp = (known[:, S] == s[i]) & (known[:, P] == p[i])
+            labels[i, known[m_sp, O]] = float("inf")
+            m_po = (known[:, P] == p[i]) & (known[:, O] == o[i])
+            labels[i, E + known[m_po, S]] = float("inf")
+        labels[torch.arange(n), o] = 0.0
+        labels[torch.arange(n), E + s] = 0.0
+        return labels
+
+    rankings = [("", None), ("_filtered", label_matrix(torch.cat([t.long() for t in filter_splits], 0)))]
+    if test_triples is not None:
+        rankings.append(("_filtered_with_test", label_matrix(test_triples)))
     out = {}
-    for suffix, lab in (("", None), ("_filtered", labels)):
+    for suffix, lab in rankings:
         s_rank, s_ties, o_rank, o_ties = filter_and_rank(sp, po, lab, o_true, s_true, rtol, atol)
+        if lab is not None:          # "from now on, use filtered scores" :298-300
+            sp, po = sp - lab[:, :E], po - lab[:, E:]
         ranks = torch.cat([final_ranks(s_rank, s_ties, tie_handling), final_ranks(o_rank, o_ties, tie_handling)])
         r1 = (ranks + 1).double()
         out["mean_rank" + suffix] = float(r1.mean())

@@ -8,6 +8,8 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 : > gpurun_out/exp_summary.txt
 export B200KGE_EXPERIMENTAL=1
+timeout 120 python -m pytest tests/test_gpu_experimental.py -x -q -k evaluator > gpurun_out/exp_evaluator.log 2>&1
+echo "evaluator pytest rc=$?" >> gpurun_out/exp_summary.txt
 for v in tc3 tc4-forward tc4-direct; do
   timeout 180 python -m pytest tests/test_gpu_experimental.py -x -q -k "$v" > "gpurun_out/exp_$v.log" 2>&1
   echo "$v pytest rc=$?" >> gpurun_out/exp_summary.txt

@@ -174,7 +174,7 @@ def gen_jobs(model, tag):
     from kge import Config, Dataset
     from kge.job import Job
 
-    E, R, D = 60, 5, 16
+    E, R, D = 20, 3, 16          # dense enough that the filters change the ranks
 
     def triples(n, seed):
         g = torch.Generator().manual_seed(seed)
@@ -182,7 +182,7 @@ def gen_jobs(model, tag):
                             torch.randint(0, E, (n,), generator=g)], 1).int()
 
     out = {}
-    splits = {"train": triples(50, 1), "valid": triples(12, 2), "test": triples(10, 3)}
+    splits = {"train": triples(200, 1), "valid": triples(40, 2), "test": triples(40, 3)}
     ent, rel = orc.make_tables(model, E, R, D, sigma=0.5)
     for loss in ("bce", "kl"):
         config = Config()
@@ -215,10 +215,9 @@ def gen_jobs(model, tag):
             ev = job.valid_job
             ev._prepare()
             tr = ev._run()
-            for k in ("mean_rank", "mean_reciprocal_rank", "hits_at_1", "hits_at_3", "hits_at_10",
-                      "mean_rank_filtered", "mean_reciprocal_rank_filtered", "hits_at_1_filtered",
-                      "hits_at_3_filtered", "hits_at_10_filtered"):
-                out["valid_" + k] = np.float64(tr[k])
+            for suffix in ("", "_filtered", "_filtered_with_test"):
+                for k in ("mean_rank", "mean_reciprocal_rank", "hits_at_1", "hits_at_3", "hits_at_10"):
+                    out["valid_" + k + suffix] = np.float64(tr[k + suffix])
     out.update(ent=_np(ent), rel=_np(rel), train=_np(splits["train"]), valid=_np(splits["valid"]),
                test=_np(splits["test"]))
     np.savez_compressed(os.path.join(HERE, f"jobs_{tag}.npz"), **out)

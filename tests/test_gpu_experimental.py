@@ -115,3 +115,28 @@ def test_presplit_fp16_headline_shape(eng, variant):
     ref = orc.score_sp("complex", ent, rel, tri[:64, S], tri[:64, P])
     _assert_close(eng.score_1vsN("complex", "sp_", ce, cr, ce, ct[:64, S].contiguous(), ct[:64, P].contiguous()), ref,
                   "headline sp")
+
+
+@pytest.mark.parametrize("model", ["complex", "transe"])
+def test_evaluator_on_gpu_matches_reference_job(model):
+    """kge_b200.evaluate.EntityRankingEvaluator driving the fused rank kernels reproduces the reference
+    EntityRankingJob's trace (host logic is covered on CPU by tests/test_evaluate_cpu.py; this adds the device
+    side: chunked subsets, dense filter planes, accumulation into rank/ties).  To be promoted into
+    tests/test_gpu_model.py once it has run green on a B200."""
+    from kge_b200 import KgeModel
+    from kge_b200.evaluate import EntityRankingEvaluator
+
+    g = _load(f"jobs_{model}.npz")
+    E, D = g["ent"].shape
+    m = KgeModel(model, E, g["rel"].shape[0], D).cuda()
+    with torch.no_grad():
+        m.get_s_embedder().weight.copy_(g["ent"].cuda())
+        m.get_p_embedder().weight.copy_(g["rel"].cuda())
+    for bs, chunk in ((16, -1), (100, 7)):
+        ev = EntityRankingEvaluator(m, E, [g["train"], g["valid"]], g["test"], batch_size=bs, chunk_size=chunk,
+                                    hits_at_k_s=(1, 3, 10), device="cuda")
+        met = ev.evaluate(g["valid"])
+        for suffix in ("", "_filtered", "_filtered_with_test"):
+            for k in ("mean_rank", "mean_reciprocal_rank", "hits_at_1", "hits_at_3", "hits_at_10"):
+                want = float(g["valid_" + k + suffix])
+                assert abs(met[k + suffix] - want) <= 1e-6 * max(1.0, abs(want)), (k + suffix, met[k + suffix], want)

@@ -118,7 +118,7 @@ def test_job_traces_match_reference(model):
                       for i in range(0, len(train), 16)) / len(train)
         assert abs(batched - want) <= 1e-5 * abs(want), (loss, batched, want)
     # default eval.filter_splits = [train, valid] (+ test only for *_filtered_with_test)
-    met = orc.entity_ranking_metrics(model, ent, rel, valid, [train, valid])
+    met = orc.entity_ranking_metrics(model, ent, rel, valid, [train, valid], test_triples=test)
     for k, v in met.items():
         want = float(g["valid_" + k])
         assert abs(v - want) <= 1e-6 * max(1.0, abs(want)), (k, v, want)
