@@ -261,9 +261,15 @@ def run_ours(args):
     k_ms = sum(kern_ms) / len(kern_ms)
     achieved = flops_per_launch / (k_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops"]
+    tc_ver = os.environ.get("B200KGE_TC_VERSION", "1")
+    experimental = tc_ver in ("3", "4")       # pre-split fp16 planes: 6 f16 MMA slots per 32 K elements
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "traffic": 34.1e6, "kernel": "pairwise_tc_kernel<BCE, tf32+bf16x2>", "kernel_ms": k_ms,
+        "traffic": None if experimental else 34.1e6,
+        "kernel": {"3": "pairwise_tc3_kernel<BCE> (EXPERIMENTAL, pre-split fp16; presplit_kernel not included)",
+                   "4": "pairwise_tc4_kernel<BCE> (EXPERIMENTAL, CTA pair, pre-split fp16; presplit_kernel not "
+                        "included)"}.get(tc_ver, "pairwise_tc_kernel<BCE, tf32+bf16x2>"),
+        "kernel_ms": k_ms,
         "peak_name": f"dense bf16 burst, {peaks['source']}",
         "traffic_note": "dram__bytes_read+write per launch from ncu --set full (profiles/r1d_summary.md); "
                         "algorithmic bytes = table 29.8 MB + folded queries 4.2 MB",
@@ -271,8 +277,11 @@ def run_ours(args):
                 "per 32-wide K chunk, 4 TF32 MMAs (hi*hi) + 4 BF16 MMAs (cross terms) = 8 MMA slots where a "
                 "plain bf16 GEMM needs 2: the tensor pipe does 4x the algorithmic work at bf16-equivalent "
                 "rate, so the ceiling of `frac` is 0.25",
-        "tensor_pipe_frac_executed": 4.0 * achieved / peak,
+        "tensor_pipe_frac_executed": (3.0 if experimental else 4.0) * achieved / peak,
     }
+    if experimental:
+        roofline["note"] = ("EXPERIMENTAL operand path: hi/lo fp16 planes split once per call in HBM, 3 f16 MMAs per "
+                            "16 K elements = 6 slots per 32 where a plain bf16 GEMM needs 2: ceiling of `frac` is 1/3")
     cpu, _ = _cpu_reference_value(40, 1, budget_s=15.0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
