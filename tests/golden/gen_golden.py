@@ -255,6 +255,40 @@ def gen_index():
     print("wrote index", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
 
 
+def gen_grads(model, D, loss, tag):
+    """Entity / relation table gradients of one 1vsAll step of the LIVE reference: loss(score_sp, o)/n and
+    loss(score_po, s)/n with sum reduction, backward through the reference's own autograd graph
+    (train_1vsAll.py:59-82)."""
+    ref_shim.import_reference()
+    from kge import Config
+    from kge.util.loss import KgeLoss
+
+    E, R, n = 83, 5, 17
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.5)
+    tri = orc.make_triples(E, R, n, seed=9)
+    m, _, _ = ref_shim.make_reference_model(model, E, R, D, ent, rel, l_norm=1.0 if model in ("transe", "rotate") else None)
+    m.train()
+    c = Config()
+    c.folder = None
+    c.set("console.quiet", True)
+    c.set("job.device", "cpu")
+    c.set("train.loss", loss)
+    offset = 1.5 if loss == "bce" else float("nan")
+    c.set("train.loss_arg", offset)
+    fn = KgeLoss.create(c)
+    s, p, o = tri[:, S], tri[:, P], tri[:, O]
+    l_sp = fn(m.score_sp(s, p), o) / n
+    l_sp.backward()
+    l_po = fn(m.score_po(p, o), s) / n
+    l_po.backward()
+    out = dict(ent=_np(ent), rel=_np(rel), triples=_np(tri), loss=np.float64(float(l_sp) + float(l_po)),
+               offset=np.float64(0.0 if loss == "kl" else offset),
+               d_ent=_np(m.get_s_embedder()._embeddings.weight.grad),
+               d_rel=_np(m.get_p_embedder()._embeddings.weight.grad))
+    np.savez_compressed(os.path.join(HERE, f"grads_{tag}.npz"), **out)
+    print("wrote grads", tag, float(out["loss"]))
+
+
 def main():
     torch.manual_seed(0)
     E, R, n = 97, 7, 13
@@ -271,6 +305,10 @@ def main():
     for model in ("complex", "transe"):
         gen_jobs(model, model)
     gen_index()
+    for model in orc.MODELS:
+        gen_grads(model, 8 if model == "rescal" else 16, "bce", f"{model}_bce")
+    gen_grads("complex", 16, "kl", "complex_kl")
+    gen_grads("rescal", 8, "kl", "rescal_kl")
 
 
 if __name__ == "__main__":
