@@ -244,6 +244,28 @@ int b200kge_kvsall_gather(const int64_t* keys, const int64_t* offsets, const int
                           int64_t num_keys, const int64_t* examples, int64_t nb,
                           int64_t* queries_out, int64_t* offsets_out, int64_t* cols_out);
 
+/* ---- EXPERIMENTAL (prefix b200kge_x_) -------------------------------------------------------------
+ * Prepared for the next round, NOT validated on hardware yet and not used by any entry point above.
+ *
+ * b200kge_x_gemm_nt: C[M,N] = A[M,K] * B[N,K]^T, fp32 in / fp32 out, computed on the f16 tensor pipe from
+ * hi/lo fp16 planes split once in HBM (presplit.cu + pairwise_tc3.cu) — the building block of the
+ * backward GEMMs; fp32-equivalent (operand error ~5e-7 of the result's rms). */
+size_t b200kge_x_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int b200kge_x_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N,
+                      int64_t K, float* C, int64_t ldc, void* workspace, size_t workspace_bytes,
+                      b200kge_stream_t stream);
+
+/* Backward of b200kge_train_1vsall_forward (loss.backward() at kge/job/train_1vsAll.py:70,81) for the
+ * dot family with BCE: dense gradients of the entity table d_ent [E, lde] and of the relation table d_rel
+ * [R, ldr] of  (BCE(score_sp, o) + BCE(score_po, s)) / n.  Both buffers are overwritten (the reference
+ * accumulates into .grad; add them there).  Recompute-based: scores, G = sigmoid(z+off) - y, two tensor-core
+ * GEMMs (dT = G^T Q, dQ = G T), row-wise unfold of dQ through the relation fold (grad.cu). */
+size_t b200kge_x_train_1vsall_backward_workspace_bytes(int model, int64_t n, int64_t E, int32_t D);
+int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+                                    const int64_t* triples, int64_t n, int loss_kind, float offset,
+                                    float* d_ent, int64_t lde, float* d_rel, int64_t ldr,
+                                    void* workspace, size_t workspace_bytes, b200kge_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

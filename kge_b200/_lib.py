@@ -67,6 +67,14 @@ SIGNATURES = {
                                         C.c_int64, C.c_void_p, C.c_void_p]),
     "b200kge_kvsall_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    # experimental (not validated on hardware yet)
+    "b200kge_x_gemm_nt_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
+    "b200kge_x_gemm_nt": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200kge_x_train_1vsall_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int64, C.c_int32]),
+    "b200kge_x_train_1vsall_backward": (C.c_int, [C.c_int, _RP, _RP, C.c_void_p, C.c_int64, C.c_int, C.c_float,
+                                                  C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                                  C.c_size_t, C.c_void_p]),
 }
 
 _lib = None

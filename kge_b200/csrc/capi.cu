@@ -543,3 +543,165 @@ int b200kge_train_1vsall_forward_host(int model, float l_norm, int precision,
 }
 
 }  // extern "C"
+
+// ==================================================================================================
+// EXPERIMENTAL entry points (prefix b200kge_x_): pre-split fp16 GEMM and the analytic backward of the 1vsAll
+// step for the dot family (grad.cu).  Declared in include/b200kge.h under "experimental"; not validated on
+// hardware yet, not used by any default path.
+namespace {
+
+bool take_planes(Arena& ws, SplitSet& S) {
+  S.hi = ws.take((size_t)S.rows * S.Kp * 2);
+  S.lo = ws.take((size_t)S.rows * S.Kp * 2);
+  S.inv_scale = (float*)ws.take((size_t)S.rows_pad * 4);
+  return S.hi && S.lo && S.inv_scale;
+}
+size_t planes_bytes(int64_t rows, int64_t rows_pad, int64_t Kp) {
+  return 2 * ((size_t)rows * Kp * 2 + 256) + (size_t)rows_pad * 4 + 256;
+}
+
+// C[M,N] = A B^T on planes: A = "queries" (rows M), B = "table" (rows N, inv_scale padded to N+32)
+int gemm_planes(const SplitSet& A, const SplitSet& B, float* C, int64_t ldc, cudaStream_t st) {
+  EpiParams P = empty_epi();
+  P.out = C; P.ldo = ldc;
+  return launch_pairwise_tc3(EPI_STORE, A, B, P, st);
+}
+
+// One block of the backward up to dQ: nq folded query rows Q [nq, ldq] with one-hot labels lab [nq] against
+// the candidate columns [off, off+K) of the entity table; stores dT into those columns of d_ent and dQ
+// [nq, ldq] into the caller's buffer.  dir as in launch_unfold.
+int backward_block(int model, const Rows& E, const Rows& R, const int64_t* triples, int64_t n, int dir,
+                   const float* Q, int64_t ldq, const int64_t* lab, int col_off, int K, float offset,
+                   float* d_ent, int64_t lde, float* dQ, Arena ws, cudaStream_t st) {
+  const int64_t nq = dir < 0 ? 2 * n : n, m = E.rows;
+  const int64_t ldz = round_up(m, 4), Ep = round_up(m, 64), Np = round_up(nq, 64);
+  const int64_t ldE = round_up(m, 4), ldN = round_up(nq, 4);
+  int rc;
+  // 1. scores through the validated scorer (plain-store epilogue)
+  float* z = (float*)ws.take((size_t)nq * ldz * 4);
+  if (!z) { set_error("workspace too small for the score matrix"); return B200KGE_ERR_WORKSPACE; }
+  {
+    Rows S = E; S.idx = lab; S.rows = n;      // placeholders: operands are pre-folded
+    Rows Pr = R; Pr.idx = lab; Pr.rows = n;
+    EpiParams P = empty_epi();
+    P.out = z; P.ldo = ldz;
+    Block B{model, dir <= 0 ? B200KGE_SP_ : B200KGE__PO, &S, dir < 0 ? &S : nullptr, &Pr, &E, n};
+    B.Qpre = Q;
+    if ((rc = run_block(B, 1.0f, B200KGE_PREC_AUTO, EPI_STORE, P, ws, st, nullptr))) return rc;
+  }
+  // 2. G = sigmoid(z + off) - y as planes, both layouts
+  SplitSet SG{nullptr, 0, nullptr, 0, nq, nq, (int)m, (int)Ep, nullptr, nullptr, nullptr};
+  SplitSet SGT{nullptr, 0, nullptr, 0, m, m, (int)nq, (int)Np, nullptr, nullptr, nullptr};
+  if (!take_planes(ws, SG) || !take_planes(ws, SGT)) { set_error("workspace too small for the gradient planes"); return B200KGE_ERR_WORKSPACE; }
+  if ((rc = launch_grad_planes(z, ldz, nq, m, lab, nullptr, 0, offset, 1.0f / (float)n, SG.hi, SG.lo, Ep, SGT.hi,
+                               SGT.lo, Np, SG.inv_scale, SGT.inv_scale, st))) return rc;
+  // 3. transposed operands T^T [K, E] and Q^T [K, nq], then their planes
+  float* Tt = (float*)ws.take((size_t)K * ldE * 4);
+  float* Qt = (float*)ws.take((size_t)K * ldN * 4);
+  if (!Tt || !Qt) { set_error("workspace too small for the transposed operands"); return B200KGE_ERR_WORKSPACE; }
+  if ((rc = launch_transpose(E.base + col_off, E.ld, m, K, Tt, ldE, st))) return rc;
+  if ((rc = launch_transpose(Q, ldq, nq, K, Qt, ldN, st))) return rc;
+  SplitSet STt{Tt, ldE, nullptr, 0, K, K + 32, (int)m, (int)Ep, nullptr, nullptr, nullptr};
+  SplitSet SQt{Qt, ldN, nullptr, 0, K, K + 32, (int)nq, (int)Np, nullptr, nullptr, nullptr};
+  if (!take_planes(ws, STt) || !take_planes(ws, SQt)) { set_error("workspace too small for the operand planes"); return B200KGE_ERR_WORKSPACE; }
+  if ((rc = launch_presplit(STt, SQt, st))) return rc;
+  // 4. dT = G^T Q -> entity-table gradient columns [off, off+K) (overwrites);  dQ = G T
+  if ((rc = gemm_planes(SGT, SQt, d_ent + col_off, lde, st))) return rc;
+  return gemm_planes(SG, STt, dQ, ldq, st);
+  // 5. (caller) unfold dQ into the rows of the batch — after EVERY block has stored its dT columns
+}
+
+size_t backward_block_bytes(int64_t nq, int64_t m, int64_t K, int64_t ldq) {
+  const int64_t Ep = round_up(m, 64), Np = round_up(nq, 64);
+  size_t b = (size_t)nq * round_up(m, 4) * 4 + 256;
+  b += b200kge_workspace_bytes(0, nq, m, (int32_t)K, 0);
+  b += planes_bytes(nq, nq, Ep) + planes_bytes(m, m, Np);
+  b += (size_t)K * round_up(m, 4) * 4 + (size_t)K * round_up(nq, 4) * 4 + 2 * (size_t)nq * ldq * 4 + 4 * 256;
+  b += planes_bytes(K, K + 32, Ep) + planes_bytes(K, K + 32, Np);
+  return b;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t b200kge_x_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  const int64_t Kp = round_up(K, 64);
+  return planes_bytes(M, M, Kp) + planes_bytes(N, N + 32, Kp) + 1024;
+}
+
+int b200kge_x_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                      float* C, int64_t ldc, void* workspace, size_t workspace_bytes, b200kge_stream_t stream) {
+  if (!A || !B || !C) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  if (M < 0 || N < 0 || K <= 0 || N >= (1ll << 31)) { set_error("bad GEMM shape"); return B200KGE_ERR_INVALID; }
+  if (M == 0 || N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  const int Kp = (int)round_up(K, 64);
+  SplitSet SA{A, lda, nullptr, 0, M, M, (int)K, Kp, nullptr, nullptr, nullptr};
+  SplitSet SB{B, ldb, nullptr, 0, N, N + 32, (int)K, Kp, nullptr, nullptr, nullptr};
+  if (!take_planes(ws, SA) || !take_planes(ws, SB)) { set_error("workspace too small for the operand planes"); return B200KGE_ERR_WORKSPACE; }
+  int rc = launch_presplit(SB, SA, st);
+  if (rc) return rc;
+  return gemm_planes(SA, SB, C, ldc, st);
+}
+
+size_t b200kge_x_train_1vsall_backward_workspace_bytes(int model, int64_t n, int64_t E, int32_t D) {
+  const int64_t K = (model == B200KGE_CP) ? D / 2 : D;
+  const int64_t nq = 2 * n, ldq = round_up(K, 32);
+  return (size_t)nq * ldq * 4 + (size_t)n * 5 * 8 + 4096 + backward_block_bytes(nq, E, K, ldq);
+}
+
+int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+                                    const int64_t* triples, int64_t n, int loss_kind, float offset, float* d_ent,
+                                    int64_t lde, float* d_rel, int64_t ldr, void* workspace, size_t workspace_bytes,
+                                    b200kge_stream_t stream) {
+  if (!ent || !rel || !triples || !d_ent || !d_rel) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  if (ent->idx || rel->idx) { set_error("ent/rel must be plain tables"); return B200KGE_ERR_INVALID; }
+  int rc = validate_model(model, to_rows(ent), to_rows(rel)); if (rc) return rc;
+  if (model > B200KGE_RESCAL) { set_error("the analytic backward covers the dot family only (model %d)", model); return B200KGE_ERR_UNSUPPORTED; }
+  if (loss_kind != B200KGE_LOSS_BCE) { set_error("the analytic backward covers BCE only so far"); return B200KGE_ERR_UNSUPPORTED; }
+  if (lde < ent->dim || ldr < rel->dim) { set_error("gradient leading dimensions are smaller than the table widths"); return B200KGE_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Rows E = to_rows(ent), R = to_rows(rel);
+  B2K_CUDA(cudaMemsetAsync(d_rel, 0, (size_t)R.rows * ldr * 4, st));
+  if (n <= 0) { B2K_CUDA(cudaMemsetAsync(d_ent, 0, (size_t)E.rows * lde * 4, st)); return 0; }
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  Folded f0 = folded_problem(model, B200KGE_SP_, E.dim, 1.0f), f1 = folded_problem(model, B200KGE__PO, E.dim, 1.0f);
+  const int64_t ldq = round_up(f0.K, 32);
+  if (f0.col_off == f1.col_off) {
+    float* Q = (float*)ws.take((size_t)(2 * n) * ldq * 4);
+    int64_t* lab = (int64_t*)ws.take((size_t)n * 2 * 8);
+    if (!Q || !lab) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+    float* dQ = (float*)ws.take((size_t)(2 * n) * ldq * 4);
+    if (!dQ) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+    if ((rc = launch_prep_1vsall(model, E, R, triples, n, Q, ldq, lab, nullptr, st))) return rc;
+    if ((rc = backward_block(model, E, R, triples, n, -1, Q, ldq, lab, f0.col_off, f0.K, offset, d_ent, lde, dQ, ws, st))) return rc;
+    return launch_unfold(model, E, R, triples, n, -1, dQ, ldq, d_ent, lde, d_rel, ldr, st);
+  }
+  // CP: the two directions pair with different halves of the candidate columns
+  int64_t* sidx = (int64_t*)ws.take((size_t)n * 8);
+  int64_t* pidx = (int64_t*)ws.take((size_t)n * 8);
+  int64_t* oidx = (int64_t*)ws.take((size_t)n * 8);
+  int64_t* lab = (int64_t*)ws.take((size_t)n * 2 * 8);
+  float* Q = (float*)ws.take((size_t)n * ldq * 4);
+  float* dQ2 = (float*)ws.take((size_t)(2 * n) * ldq * 4);
+  if (!sidx || !pidx || !oidx || !lab || !Q || !dQ2) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+  unpack_triples_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(triples, n, sidx, pidx, oidx, lab);
+  B2K_LAUNCH_CHECK("unpack_triples_kernel");
+  Rows S = E; S.idx = sidx; S.rows = n;
+  Rows O = E; O.idx = oidx; O.rows = n;
+  Rows Pr = R; Pr.idx = pidx; Pr.rows = n;
+  for (int dir = 0; dir < 2; ++dir) {
+    const Folded& f = dir == 0 ? f0 : f1;
+    if ((rc = launch_fold_queries(model, dir, dir == 0 ? S : O, Pr, n, 0, Q, ldq, st))) return rc;
+    if ((rc = backward_block(model, E, R, triples, n, dir, Q, ldq, lab + dir * n, f.col_off, f.K, offset, d_ent, lde,
+                             dQ2 + (size_t)dir * n * ldq, ws, st))) return rc;
+  }
+  // both halves of the dense column gradient are stored: now add the batch rows' own gradients
+  for (int dir = 0; dir < 2; ++dir)
+    if ((rc = launch_unfold(model, E, R, triples, n, dir, dQ2 + (size_t)dir * n * ldq, ldq, d_ent, lde, d_rel, ldr, st))) return rc;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+// grad.cu — EXPERIMENTAL ("next"): device pieces of the backward of the fused 1vsAll step for
+// the dot family.  Not on any default path and not validated on hardware yet; the math is pinned on the CPU
+// (oracle/kge_fold.py against autograd and against gradients of the live reference,
+// tests/test_fold_algebra.py), the kernels below transcribe it.
+//
+//   z  = Q T^T                       recomputed with the validated scorer (plain-store epilogue)
+//   G  = sigmoid(z + off) - y        grad_planes_kernel: written ONCE as fp16 hi/lo planes in both layouts,
+//                                    G [nq, Ep] and G^T [E, Np] (scale 2^14; 1/n rides in the row scale)
+//   dT = G^T Q   [E, K]              pre-split fp16 GEMM (pairwise_tc3.cu, store epilogue) on G^T and Q^T planes
+//   dQ = G  T    [nq, K]             same on G and T^T planes
+//   (da, dp) = unfold(a, p, dQ)      unfold_kernel: row-wise vector-Jacobian products of the relation fold,
+//                                    atomically added into the entity / relation gradient tables
+// This first version trades HBM traffic for simplicity (scores and both G layouts are materialised, operands
+// are transposed through HBM); fusing the G pass into the scorer's epilogue and a split-K dQ are the
+// follow-ups once it is parity-green.
+#include <cuda_fp16.h>
+#include "fold.cuh"
+#include "tc_common.cuh"
+
+namespace b200kge {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// dst[c, r] = src[r, c]   (fp32, 32x32 tiles through shared memory); dst columns [R, ldd) are zeroed
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ src, int64_t lds, int64_t R, int64_t C, float* __restrict__ dst,
+                 int64_t ldd) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+  const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t r = r0 + ty + 8 * k, c = c0 + tx;
+    tile[ty + 8 * k][tx] = (r < R && c < C) ? __ldg(src + r * lds + c) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t c = c0 + ty + 8 * k, r = r0 + tx;
+    if (c < C && r < ldd) dst[c * ldd + r] = tile[tx][ty + 8 * k];   // r >= R carries the zeros loaded above
+  }
+}
+
+__device__ __forceinline__ void split_store(__half* __restrict__ hi, __half* __restrict__ lo, int64_t pos, float g) {
+  const float s = g * 16384.f;
+  const __half h = __float2half_rn(s);
+  hi[pos] = h;
+  lo[pos] = __float2half_rn(s - __half2float(h));
+}
+
+// G = sigmoid(z + off) - y as fp16 hi/lo planes, row-major [nq, Ep] and transposed [E, Np]; pads zeroed.
+// grid = (Ep/32, Np/32), block = 32 x 8.
+__global__ void __launch_bounds__(256)
+grad_planes_kernel(const float* __restrict__ z, int64_t ldz, int64_t nq, int64_t E,
+                   const int64_t* __restrict__ label_idx, const float* __restrict__ label_dense, int64_t ldl,
+                   float offset, float inv_n, __half* __restrict__ g_hi, __half* __restrict__ g_lo, int64_t Ep,
+                   __half* __restrict__ gt_hi, __half* __restrict__ gt_lo, int64_t Np,
+                   float* __restrict__ g_scale, float* __restrict__ gt_scale) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t e0 = (int64_t)blockIdx.x * 32, i0 = (int64_t)blockIdx.y * 32;
+  const float inv = inv_n * (1.0f / 16384.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t i = i0 + ty + 8 * k, e = e0 + tx;
+    float g = 0.f;
+    if (i < nq && e < E) {
+      const float x = __ldg(z + i * ldz + e) + offset;
+      const float y = label_idx ? ((label_idx[i] == e) ? 1.f : 0.f) : __ldg(label_dense + i * ldl + e);
+      g = 1.0f / (1.0f + expf(-x)) - y;
+    }
+    tile[ty + 8 * k][tx] = g;
+    if (i < nq) {
+      split_store(g_hi, g_lo, i * Ep + e, g);                 // e < Ep by construction of the grid
+      if (blockIdx.x == 0 && tx == 0) g_scale[i] = inv;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t e = e0 + ty + 8 * k, i = i0 + tx;
+    if (e < E) {
+      split_store(gt_hi, gt_lo, e * Np + i, tile[tx][ty + 8 * k]);   // i < Np by construction of the grid
+      if (blockIdx.y == 0 && tx == 0) gt_scale[e] = inv;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-wise unfold: block b handles query row b.  dir < 0: rows [0,n) are sp_ (a = subject), rows [n,2n) are
+// _po (a = object) — the stacked layout of prep_1vsall_kernel; dir = 0 / 1: all rows sp_ / _po.
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+unfold_kernel(Rows ent, Rows rel, const int64_t* __restrict__ tri, int64_t n, int dir,
+              const float* __restrict__ dQ, int64_t ldq, float* __restrict__ d_ent, int64_t lde,
+              float* __restrict__ d_rel, int64_t ldr) {
+  const int64_t b = blockIdx.x;
+  const bool sp = dir < 0 ? (b < n) : (dir == 0);
+  const int64_t i = (dir < 0 && b >= n) ? b - n : b;
+  const int64_t si = tri[3 * i], pi = tri[3 * i + 1], oi = tri[3 * i + 2];
+  const int64_t ai = sp ? si : oi;
+  const float* __restrict__ a = ent.base + ai * ent.ld;
+  const float* __restrict__ p = rel.base + pi * rel.ld;
+  const float* __restrict__ g = dQ + b * ldq;
+  float* __restrict__ da = d_ent + ai * lde;
+  float* __restrict__ dp = d_rel + pi * ldr;
+  const int D = ent.dim, h = D >> 1;
+
+  if constexpr (MODEL == B200KGE_RESCAL) {
+    // sp_: q = a^T M  => da_i = sum_j M[i,j] g_j,  dM[i,j] = a_i g_j
+    // _po: q = M a    => da_j = sum_i g_i M[i,j],  dM[i,j] = g_i a_j
+    extern __shared__ float sh[];
+    float* sa = sh;
+    float* sg = sh + D;
+    for (int k = threadIdx.x; k < D; k += blockDim.x) { sa[k] = a[k]; sg[k] = g[k]; }
+    __syncthreads();
+    if (sp) {
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+      for (int r = warp; r < D; r += nw) {
+        float acc = 0.f;
+        for (int j = lane; j < D; j += 32) acc = fmaf(p[(int64_t)r * D + j], sg[j], acc);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) atomicAdd(da + r, acc);
+      }
+    } else {
+      for (int j = threadIdx.x; j < D; j += blockDim.x) {
+        float acc = 0.f;
+        for (int r = 0; r < D; ++r) acc = fmaf(sg[r], p[(int64_t)r * D + j], acc);
+        atomicAdd(da + j, acc);
+      }
+    }
+    for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+      const int r = idx / D, j = idx - r * D;
+      atomicAdd(dp + idx, sp ? sa[r] * sg[j] : sg[r] * sa[j]);
+    }
+  } else if constexpr (MODEL == B200KGE_COMPLEX) {
+    for (int k = threadIdx.x; k < h; k += blockDim.x) {
+      const float a_re = a[k], a_im = a[k + h], p_re = p[k], p_im = p[k + h], g_re = g[k], g_im = g[k + h];
+      if (sp) {   // Q_re = a_re p_re - a_im p_im ; Q_im = a_im p_re + a_re p_im
+        atomicAdd(da + k, g_re * p_re + g_im * p_im);
+        atomicAdd(da + k + h, -g_re * p_im + g_im * p_re);
+        atomicAdd(dp + k, g_re * a_re + g_im * a_im);
+        atomicAdd(dp + k + h, -g_re * a_im + g_im * a_re);
+      } else {    // Q_re = p_re a_re + p_im a_im ; Q_im = p_re a_im - p_im a_re
+        atomicAdd(da + k, g_re * p_re - g_im * p_im);
+        atomicAdd(da + k + h, g_re * p_im + g_im * p_re);
+        atomicAdd(dp + k, g_re * a_re + g_im * a_im);
+        atomicAdd(dp + k + h, g_re * a_im - g_im * a_re);
+      }
+    }
+  } else if constexpr (MODEL == B200KGE_DISTMULT) {
+    for (int k = threadIdx.x; k < D; k += blockDim.x) {
+      atomicAdd(da + k, g[k] * p[k]);
+      atomicAdd(dp + k, g[k] * a[k]);
+    }
+  } else if constexpr (MODEL == B200KGE_SIMPLE) {
+    for (int k = threadIdx.x; k < h; k += blockDim.x) {
+      const float a_h = a[k], a_t = a[k + h], p_f = p[k], p_b = p[k + h];
+      const float g0 = 0.5f * g[k], g1 = 0.5f * g[k + h];
+      if (sp) {   // Q = 1/2 [a_t p_b | a_h p_f]
+        atomicAdd(da + k, g1 * p_f);
+        atomicAdd(da + k + h, g0 * p_b);
+        atomicAdd(dp + k, g1 * a_h);
+        atomicAdd(dp + k + h, g0 * a_t);
+      } else {    // Q = 1/2 [a_t p_f | a_h p_b]
+        atomicAdd(da + k, g1 * p_b);
+        atomicAdd(da + k + h, g0 * p_f);
+        atomicAdd(dp + k, g0 * a_t);
+        atomicAdd(dp + k + h, g1 * a_h);
+      }
+    }
+  } else {  // CP: sp_ Q = a[:h] p (vs cand[:, h:]);  _po Q = a[h:] p (vs cand[:, :h])
+    const int ao = sp ? 0 : h;
+    for (int k = threadIdx.x; k < h; k += blockDim.x) {
+      atomicAdd(da + ao + k, g[k] * p[k]);
+      atomicAdd(dp + k, g[k] * a[ao + k]);
+    }
+  }
+}
+
+}  // namespace
+
+int launch_transpose(const float* src, int64_t lds, int64_t R, int64_t C, float* dst, int64_t ldd, cudaStream_t st) {
+  if (R == 0 || C == 0) return 0;
+  dim3 grid((unsigned)((ldd + 31) / 32), (unsigned)((C + 31) / 32));
+  transpose_kernel<<<grid, 256, 0, st>>>(src, lds, R, C, dst, ldd);
+  B2K_LAUNCH_CHECK("transpose_kernel");
+  return 0;
+}
+
+int launch_grad_planes(const float* z, int64_t ldz, int64_t nq, int64_t E, const int64_t* label_idx,
+                       const float* label_dense, int64_t ldl, float offset, float inv_n, void* g_hi, void* g_lo,
+                       int64_t Ep, void* gt_hi, void* gt_lo, int64_t Np, float* g_scale, float* gt_scale,
+                       cudaStream_t st) {
+  if (nq == 0 || E == 0) return 0;
+  dim3 grid((unsigned)(Ep / 32), (unsigned)(Np / 32));
+  grad_planes_kernel<<<grid, 256, 0, st>>>(z, ldz, nq, E, label_idx, label_dense, ldl, offset, inv_n,
+                                            (__half*)g_hi, (__half*)g_lo, Ep, (__half*)gt_hi, (__half*)gt_lo, Np,
+                                            g_scale, gt_scale);
+  B2K_LAUNCH_CHECK("grad_planes_kernel");
+  return 0;
+}
+
+int launch_unfold(int model, const Rows& ent, const Rows& rel, const int64_t* triples, int64_t n, int dir,
+                  const float* dQ, int64_t ldq, float* d_ent, int64_t lde, float* d_rel, int64_t ldr, cudaStream_t st) {
+  if (n == 0) return 0;
+  const int64_t nq = dir < 0 ? 2 * n : n;
+  dim3 grid((unsigned)nq), block(128);
+  const int D = ent.dim;
+#define B2K_UNFOLD(M, SM) case M: unfold_kernel<M><<<grid, block, SM, st>>>(ent, rel, triples, n, dir, dQ, ldq, d_ent, lde, d_rel, ldr); break;
+  switch (model) {
+    B2K_UNFOLD(B200KGE_COMPLEX, 0) B2K_UNFOLD(B200KGE_DISTMULT, 0) B2K_UNFOLD(B200KGE_SIMPLE, 0)
+    B2K_UNFOLD(B200KGE_CP, 0) B2K_UNFOLD(B200KGE_RESCAL, 2 * D * sizeof(float))
+    default: set_error("the analytic backward covers the dot family only (model %d)", model); return B200KGE_ERR_UNSUPPORTED;
+  }
+#undef B2K_UNFOLD
+  B2K_LAUNCH_CHECK("unfold_kernel");
+  return 0;
+}
+
+}  // namespace b200kge

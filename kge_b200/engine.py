@@ -316,3 +316,36 @@ class HostStep:
             triples_host.data_ptr(), n, LOSS[self.loss], self.offset, self.loss_host.data_ptr(),
             self.ws.data_ptr(), self.ws.numel(), _stream(self.ent.device)))
         return float(self.loss_host[0])
+
+
+# ---- EXPERIMENTAL (b200kge_x_*): prepared for the next round, not validated on hardware yet -----------------
+def x_gemm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """C = A @ B^T (fp32 in/out) on the f16 tensor pipe from pre-split hi/lo fp16 planes."""
+    _require_cuda(a, b)
+    lib = _lib.load()
+    a, b = _f32(a), _f32(b)
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    ws = torch.empty(lib.b200kge_x_gemm_nt_workspace_bytes(M, N, K), dtype=torch.uint8, device=a.device)
+    _lib.check(lib.b200kge_x_gemm_nt(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, out.data_ptr(),
+                                     out.stride(0), ws.data_ptr(), ws.numel(), _stream(a.device)))
+    return out
+
+
+def x_train_1vsall_backward(model: str, ent, rel, triples, loss: str = "bce", offset: float = 0.0):
+    """(d_ent, d_rel): dense table gradients of train_1vsall_forward's loss (dot family, BCE)."""
+    _require_cuda(ent, rel, triples)
+    lib, k = _lib.load(), _Keep()
+    re_, rr = k.rows(ent), k.rows(rel)
+    tri = triples if (triples.dtype == torch.int64 and triples.is_contiguous()) else triples.long().contiguous()
+    n = tri.shape[0]
+    dev = ent.device
+    d_ent = torch.empty_like(_f32(ent))
+    d_rel = torch.empty_like(_f32(rel))
+    nbytes = lib.b200kge_x_train_1vsall_backward_workspace_bytes(MODELS[model], n, ent.shape[0], ent.shape[1])
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.b200kge_x_train_1vsall_backward(
+        MODELS[model], C.byref(re_), C.byref(rr), tri.data_ptr(), n, LOSS[loss], offset, d_ent.data_ptr(),
+        d_ent.stride(0), d_rel.data_ptr(), d_rel.stride(0), ws.data_ptr(), ws.numel(), _stream(dev)))
+    return d_ent, d_rel

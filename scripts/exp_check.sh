@@ -10,6 +10,11 @@ mkdir -p gpurun_out
 export B200KGE_EXPERIMENTAL=1
 timeout 120 python -m pytest tests/test_gpu_experimental.py -x -q -k evaluator > gpurun_out/exp_evaluator.log 2>&1
 echo "evaluator pytest rc=$?" >> gpurun_out/exp_summary.txt
+timeout 180 python -m pytest tests/test_gpu_experimental.py -x -q -k "x_gemm" > gpurun_out/exp_gemm.log 2>&1
+echo "x_gemm pytest rc=$?" >> gpurun_out/exp_summary.txt
+timeout 240 python -m pytest tests/test_gpu_experimental.py -q -k "x_backward" > gpurun_out/exp_backward.log 2>&1
+echo "x_backward pytest rc=$?" >> gpurun_out/exp_summary.txt
+tail -5 gpurun_out/exp_backward.log >> gpurun_out/exp_summary.txt
 for v in tc3 tc4-forward tc4-direct; do
   timeout 180 python -m pytest tests/test_gpu_experimental.py -x -q -k "$v" > "gpurun_out/exp_$v.log" 2>&1
   echo "$v pytest rc=$?" >> gpurun_out/exp_summary.txt

@@ -140,3 +140,44 @@ def test_evaluator_on_gpu_matches_reference_job(model):
             for k in ("mean_rank", "mean_reciprocal_rank", "hits_at_1", "hits_at_3", "hits_at_10"):
                 want = float(g["valid_" + k + suffix])
                 assert abs(met[k + suffix] - want) <= 1e-6 * max(1.0, abs(want)), (k + suffix, met[k + suffix], want)
+
+
+def test_x_gemm_nt_vs_fp64(eng):
+    """Pre-split fp16 GEMM (the backward's building block; also exercises presplit + pairwise_tc3 on shapes
+    the scorer never sees: long reductions, few rows, K not a multiple of 64, tiny and huge magnitudes)."""
+    g = torch.Generator().manual_seed(0)
+    for M, N, K, sa, sb in ((300, 500, 1000, 1.0, 1.0), (2048, 512, 14541, 1e-3, 1.0), (130, 40, 72, 50.0, 1e-4),
+                            (5000, 384, 2048, 1.0, 1.0)):
+        a = torch.randn((M, K), generator=g) * sa
+        b = torch.randn((N, K), generator=g) * sb
+        ref = a.double() @ b.double().t()
+        got = eng.x_gemm_nt(a.cuda(), b.cuda())
+        _assert_close(got, ref, f"gemm {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("fname", ["grads_complex_bce.npz", "grads_distmult_bce.npz", "grads_simple_bce.npz",
+                                   "grads_cp_bce.npz", "grads_rescal_bce.npz"])
+def test_x_backward_golden(eng, fname):
+    """Table gradients of one 1vsAll+BCE step against the live reference's backward."""
+    g = _load(fname)
+    model = fname[len("grads_"):-4].split("_")[0]
+    d_ent, d_rel = eng.x_train_1vsall_backward(model, g["ent"].cuda(), g["rel"].cuda(), g["triples"].cuda(), "bce",
+                                               float(g["offset"]))
+    _assert_close(d_ent, g["d_ent"], fname + " d_ent")
+    _assert_close(d_rel, g["d_rel"], fname + " d_rel")
+
+
+@pytest.mark.parametrize("model,D", [("complex", 128), ("distmult", 64), ("simple", 128), ("cp", 64), ("rescal", 24)])
+def test_x_backward_medium(eng, model, D):
+    """Ragged medium shapes with duplicate rows, against the analytic CPU assembly (oracle/kge_fold.py, itself
+    pinned to autograd and to the reference's gradients)."""
+    from oracle import kge_fold as kf
+
+    E, R, n = 3001, 7, 333
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.5)
+    tri = orc.make_triples(E, R, n)
+    tri[5] = tri[4]
+    ref_e, ref_r = kf.train_1vsall_backward(model, ent.double(), rel.double(), tri, "bce", 0.5)
+    d_ent, d_rel = eng.x_train_1vsall_backward(model, ent.cuda(), rel.cuda(), tri.cuda(), "bce", 0.5)
+    _assert_close(d_ent, ref_e, f"{model} d_ent")
+    _assert_close(d_rel, ref_r, f"{model} d_rel")
