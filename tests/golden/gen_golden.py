@@ -218,6 +218,34 @@ def gen_jobs(model, tag):
             for suffix in ("", "_filtered", "_filtered_with_test"):
                 for k in ("mean_rank", "mean_reciprocal_rank", "hits_at_1", "hits_at_3", "hits_at_10"):
                     out["valid_" + k + suffix] = np.float64(tr[k + suffix])
+    # KvsAll forward-only epochs (default query types sp_ and _po), with and without label smoothing
+    for loss, eps in (("kl", 0.0), ("kl", 0.2), ("bce", 0.2)):
+        config = Config()
+        config.folder = tempfile.mkdtemp()
+        config.set("console.quiet", True)
+        config.set("model", model)
+        config._import(model)
+        config.set("dataset.name", "synthetic")
+        config.set("dataset.num_entities", E)
+        config.set("dataset.num_relations", R)
+        config.set("dataset.pickle", False)
+        config.set("job.device", "cpu")
+        config.set("job.type", "train")
+        config.set("train.type", "KvsAll")
+        config.set("train.loss", loss)
+        config.set("train.batch_size", 16)
+        config.set("KvsAll.label_smoothing", eps)
+        config.set_all({"lookup_embedder.dim": D})
+        ds = Dataset(config, None)
+        ds._triples = dict(splits)
+        ds._meta = {"entity_ids": [f"e{i}" for i in range(E)], "relation_ids": [f"r{i}" for i in range(R)]}
+        job = Job.create(config, ds)
+        with torch.no_grad():
+            job.model.get_s_embedder()._embeddings.weight.copy_(ent)
+            job.model.get_p_embedder()._embeddings.weight.copy_(rel)
+        job.is_forward_only = True
+        job._prepare()
+        out[f"kvsall_avg_loss_{loss}_{int(eps * 10)}"] = np.float64(job.run_epoch()["avg_loss"])
     out.update(ent=_np(ent), rel=_np(rel), train=_np(splits["train"]), valid=_np(splits["valid"]),
                test=_np(splits["test"]))
     np.savez_compressed(os.path.join(HERE, f"jobs_{tag}.npz"), **out)

@@ -122,3 +122,31 @@ def test_job_traces_match_reference(model):
     for k, v in met.items():
         want = float(g["valid_" + k])
         assert abs(v - want) <= 1e-6 * max(1.0, abs(want)), (k, v, want)
+
+
+@pytest.mark.parametrize("model", ["complex", "transe"])
+def test_kvsall_epoch_matches_reference(model):
+    """TrainingJobKvsAll forward-only epoch (train_KvsAll.py:205-300): one example per distinct (s,p) and per
+    distinct (p,o) of the training split, multi-hot labels (duplicate triples add up, util.py:46-58), optional
+    label smoothing, loss summed over examples and divided by their number."""
+    g = _load(f"jobs_{model}.npz")
+    ent, rel, train = g["ent"], g["rel"], g["train"].long()
+    E = ent.shape[0]
+
+    def examples(key_cols, val_col):
+        keys, inv = torch.unique(train[:, key_cols], dim=0, return_inverse=True)
+        labels = torch.zeros((keys.shape[0], E))
+        labels.index_put_((inv, train[:, val_col]), torch.ones(len(train)), accumulate=True)
+        return keys, labels
+
+    sp_keys, sp_lab = examples([S, P], O)
+    po_keys, po_lab = examples([P, O], S)
+    sc_sp = orc.score_sp(model, ent, rel, sp_keys[:, 0], sp_keys[:, 1])
+    sc_po = orc.score_po(model, ent, rel, po_keys[:, 0], po_keys[:, 1])
+    n = sp_keys.shape[0] + po_keys.shape[0]
+    for loss, eps in (("kl", 0.0), ("kl", 0.2), ("bce", 0.2)):
+        fn = orc.kl_loss if loss == "kl" else orc.bce_loss
+        lab = (lambda y: orc.kvsall_smooth_labels(y, eps)) if eps > 0 else (lambda y: y)
+        got = float(fn(sc_sp, lab(sp_lab)) + fn(sc_po, lab(po_lab))) / n
+        want = float(g[f"kvsall_avg_loss_{loss}_{int(eps * 10)}"])
+        assert abs(got - want) <= 2e-5 * abs(want), (loss, eps, got, want)
