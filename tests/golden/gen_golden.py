@@ -283,6 +283,60 @@ def gen_index():
     print("wrote index", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
 
 
+def gen_ns_job(model, tag):
+    """One batch of the reference's TrainingJobNegativeSampling (collate -> _process_batch, forward only) with
+    the sampled negatives recorded, for all three slots and a BCE offset (train_negative_sampling.py:64-170)."""
+    import tempfile
+
+    ref_shim.import_reference()
+    from kge import Config, Dataset
+    from kge.job import Job
+
+    E, R, D = 30, 4, 16
+    g = torch.Generator().manual_seed(8)
+    tri = lambda n: torch.stack([torch.randint(0, E, (n,), generator=g), torch.randint(0, R, (n,), generator=g),
+                                 torch.randint(0, E, (n,), generator=g)], 1).int()
+    splits = {"train": tri(64), "valid": tri(8), "test": tri(8)}
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.5)
+    config = Config()
+    config.folder = tempfile.mkdtemp()
+    config.set("console.quiet", True)
+    config.set("model", model)
+    config._import(model)
+    config.set("dataset.name", "synthetic")
+    config.set("dataset.num_entities", E)
+    config.set("dataset.num_relations", R)
+    config.set("dataset.pickle", False)
+    config.set("job.device", "cpu")
+    config.set("job.type", "train")
+    config.set("train.type", "negative_sampling")
+    config.set("train.loss", "bce")
+    config.set("train.loss_arg", 0.5)
+    config.set("train.batch_size", 16)
+    config.set("negative_sampling.num_samples.s", 5)
+    config.set("negative_sampling.num_samples.p", 2)
+    config.set("negative_sampling.num_samples.o", 7)
+    config.set_all({"lookup_embedder.dim": D})
+    ds = Dataset(config, None)
+    ds._triples = dict(splits)
+    ds._meta = {"entity_ids": [f"e{i}" for i in range(E)], "relation_ids": [f"r{i}" for i in range(R)]}
+    torch.manual_seed(3)
+    job = Job.create(config, ds)
+    with torch.no_grad():
+        job.model.get_s_embedder()._embeddings.weight.copy_(ent)
+        job.model.get_p_embedder()._embeddings.weight.copy_(rel)
+    job.is_forward_only = True
+    job._prepare()
+    batch = job._get_collate_fun()(list(range(5, 21)))
+    res = job._process_batch(0, batch)
+    out = dict(ent=_np(ent), rel=_np(rel), triples=_np(batch["triples"]), avg_loss=np.float64(res.avg_loss),
+               size=np.int64(res.size), offset=np.float64(0.5))
+    for slot, nm in ((S, "s"), (P, "p"), (O, "o")):
+        out[f"neg_{nm}"] = _np(batch["negative_samples"][slot].samples())
+    np.savez_compressed(os.path.join(HERE, f"nsjob_{tag}.npz"), **out)
+    print("wrote nsjob", tag, float(out["avg_loss"]), {k: v.shape for k, v in out.items() if k.startswith("neg")})
+
+
 def gen_grads(model, D, loss, tag):
     """Entity / relation table gradients of one 1vsAll step of the LIVE reference: loss(score_sp, o)/n and
     loss(score_po, s)/n with sum reduction, backward through the reference's own autograd graph
@@ -333,6 +387,8 @@ def main():
     for model in ("complex", "transe"):
         gen_jobs(model, model)
     gen_index()
+    for model in ("complex", "rotate"):
+        gen_ns_job(model, model)
     for model in orc.MODELS:
         gen_grads(model, 8 if model == "rescal" else 16, "bce", f"{model}_bce")
     gen_grads("complex", 16, "kl", "complex_kl")

@@ -150,3 +150,26 @@ def test_kvsall_epoch_matches_reference(model):
         got = float(fn(sc_sp, lab(sp_lab)) + fn(sc_po, lab(po_lab))) / n
         want = float(g[f"kvsall_avg_loss_{loss}_{int(eps * 10)}"])
         assert abs(got - want) <= 2e-5 * abs(want), (loss, eps, got, want)
+
+
+@pytest.mark.parametrize("model", ["complex", "rotate"])
+def test_negative_sampling_batch_matches_reference_job(model):
+    """One batch of TrainingJobNegativeSampling with the sampled negatives replayed: per slot the [n, 1+K]
+    score block (positive first), BCE with offset against the first-column labels, divided by the batch size
+    (train_negative_sampling.py:113-163)."""
+    g = _load(f"nsjob_{model}.npz")
+    ent, rel, tri = g["ent"], g["rel"], g["triples"].long()
+    n, off = tri.shape[0], float(g["offset"])
+    total = 0.0
+    for slot, nm in ((S, "s"), (P, "p"), (O, "o")):
+        neg = g[f"neg_{nm}"].long()
+        for impl in ("triple", "batch"):
+            scores = orc.ns_scores_with_positive(model, ent, rel, tri, neg, slot, impl)
+            loss = float(orc.bce_loss(scores, orc.ns_labels(n, neg.shape[1]), off)) / n
+            if impl == "triple":
+                total += loss
+            else:
+                assert abs(loss - float(orc.bce_loss(orc.ns_scores_with_positive(model, ent, rel, tri, neg, slot, "triple"),
+                                                      orc.ns_labels(n, neg.shape[1]), off)) / n) <= 1e-5 * abs(loss)
+    assert int(g["size"]) == n
+    assert abs(total - float(g["avg_loss"])) <= 2e-5 * abs(float(g["avg_loss"])), (total, float(g["avg_loss"]))
