@@ -256,9 +256,9 @@ int b200kge_x_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, 
                       b200kge_stream_t stream);
 
 /* Backward of b200kge_train_1vsall_forward (loss.backward() at kge/job/train_1vsAll.py:70,81) for the
- * dot family with BCE: dense gradients of the entity table d_ent [E, lde] and of the relation table d_rel
- * [R, ldr] of  (BCE(score_sp, o) + BCE(score_po, s)) / n.  Both buffers are overwritten (the reference
- * accumulates into .grad; add them there).  Recompute-based: scores, G = sigmoid(z+off) - y, two tensor-core
+ * dot family with BCE or KL: dense gradients of the entity table d_ent [E, lde] and of the relation table d_rel
+ * [R, ldr] of  (loss(score_sp, o) + loss(score_po, s)) / n.  Both buffers are overwritten (the reference
+ * accumulates into .grad; add them there).  Recompute-based: scores, G = n dL/dz (sigmoid(z+off) - y | softmax(z) - y), two tensor-core
  * GEMMs (dT = G^T Q, dQ = G T), row-wise unfold of dQ through the relation fold (grad.cu). */
 size_t b200kge_x_train_1vsall_backward_workspace_bytes(int model, int64_t n, int64_t E, int32_t D);
 int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const b200kge_rows_t* rel,

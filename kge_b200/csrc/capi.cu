@@ -571,7 +571,7 @@ int gemm_planes(const SplitSet& A, const SplitSet& B, float* C, int64_t ldc, cud
 // the candidate columns [off, off+K) of the entity table; stores dT into those columns of d_ent and dQ
 // [nq, ldq] into the caller's buffer.  dir as in launch_unfold.
 int backward_block(int model, const Rows& E, const Rows& R, const int64_t* triples, int64_t n, int dir,
-                   const float* Q, int64_t ldq, const int64_t* lab, int col_off, int K, float offset,
+                   const float* Q, int64_t ldq, const int64_t* lab, int col_off, int K, int loss_kind, float offset,
                    float* d_ent, int64_t lde, float* dQ, Arena ws, cudaStream_t st) {
   const int64_t nq = dir < 0 ? 2 * n : n, m = E.rows;
   const int64_t ldz = round_up(m, 4), Ep = round_up(m, 64), Np = round_up(nq, 64);
@@ -593,8 +593,14 @@ int backward_block(int model, const Rows& E, const Rows& R, const int64_t* tripl
   SplitSet SG{nullptr, 0, nullptr, 0, nq, nq, (int)m, (int)Ep, nullptr, nullptr, nullptr};
   SplitSet SGT{nullptr, 0, nullptr, 0, m, m, (int)nq, (int)Np, nullptr, nullptr, nullptr};
   if (!take_planes(ws, SG) || !take_planes(ws, SGT)) { set_error("workspace too small for the gradient planes"); return B200KGE_ERR_WORKSPACE; }
-  if ((rc = launch_grad_planes(z, ldz, nq, m, lab, nullptr, 0, offset, 1.0f / (float)n, SG.hi, SG.lo, Ep, SGT.hi,
-                               SGT.lo, Np, SG.inv_scale, SGT.inv_scale, st))) return rc;
+  float* row_stat = nullptr;
+  if (loss_kind == B200KGE_LOSS_KL) {
+    row_stat = (float*)ws.take((size_t)nq * 2 * 4);
+    if (!row_stat) { set_error("workspace too small for the row statistics"); return B200KGE_ERR_WORKSPACE; }
+  }
+  if ((rc = launch_grad_planes(z, ldz, nq, m, lab, nullptr, 0, row_stat, loss_kind == B200KGE_LOSS_KL ? 0.f : offset,
+                               1.0f / (float)n, SG.hi, SG.lo, Ep, SGT.hi, SGT.lo, Np, SG.inv_scale, SGT.inv_scale,
+                               st))) return rc;
   // 3. transposed operands T^T [K, E] and Q^T [K, nq], then their planes
   float* Tt = (float*)ws.take((size_t)K * ldE * 4);
   float* Qt = (float*)ws.take((size_t)K * ldN * 4);
@@ -616,7 +622,7 @@ size_t backward_block_bytes(int64_t nq, int64_t m, int64_t K, int64_t ldq) {
   size_t b = (size_t)nq * round_up(m, 4) * 4 + 256;
   b += b200kge_workspace_bytes(0, nq, m, (int32_t)K, 0);
   b += planes_bytes(nq, nq, Ep) + planes_bytes(m, m, Np);
-  b += (size_t)K * round_up(m, 4) * 4 + (size_t)K * round_up(nq, 4) * 4 + 2 * (size_t)nq * ldq * 4 + 4 * 256;
+  b += (size_t)K * round_up(m, 4) * 4 + (size_t)K * round_up(nq, 4) * 4 + 2 * (size_t)nq * ldq * 4 + (size_t)nq * 8 + 5 * 256;
   b += planes_bytes(K, K + 32, Ep) + planes_bytes(K, K + 32, Np);
   return b;
 }
@@ -660,7 +666,7 @@ int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const 
   if (ent->idx || rel->idx) { set_error("ent/rel must be plain tables"); return B200KGE_ERR_INVALID; }
   int rc = validate_model(model, to_rows(ent), to_rows(rel)); if (rc) return rc;
   if (model > B200KGE_RESCAL) { set_error("the analytic backward covers the dot family only (model %d)", model); return B200KGE_ERR_UNSUPPORTED; }
-  if (loss_kind != B200KGE_LOSS_BCE) { set_error("the analytic backward covers BCE only so far"); return B200KGE_ERR_UNSUPPORTED; }
+  if (loss_kind != B200KGE_LOSS_BCE && loss_kind != B200KGE_LOSS_KL) { set_error("unknown loss kind %d", loss_kind); return B200KGE_ERR_INVALID; }
   if (lde < ent->dim || ldr < rel->dim) { set_error("gradient leading dimensions are smaller than the table widths"); return B200KGE_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
   Rows E = to_rows(ent), R = to_rows(rel);
@@ -676,7 +682,7 @@ int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const 
     float* dQ = (float*)ws.take((size_t)(2 * n) * ldq * 4);
     if (!dQ) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
     if ((rc = launch_prep_1vsall(model, E, R, triples, n, Q, ldq, lab, nullptr, st))) return rc;
-    if ((rc = backward_block(model, E, R, triples, n, -1, Q, ldq, lab, f0.col_off, f0.K, offset, d_ent, lde, dQ, ws, st))) return rc;
+    if ((rc = backward_block(model, E, R, triples, n, -1, Q, ldq, lab, f0.col_off, f0.K, loss_kind, offset, d_ent, lde, dQ, ws, st))) return rc;
     return launch_unfold(model, E, R, triples, n, -1, dQ, ldq, d_ent, lde, d_rel, ldr, st);
   }
   // CP: the two directions pair with different halves of the candidate columns
@@ -695,8 +701,8 @@ int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const 
   for (int dir = 0; dir < 2; ++dir) {
     const Folded& f = dir == 0 ? f0 : f1;
     if ((rc = launch_fold_queries(model, dir, dir == 0 ? S : O, Pr, n, 0, Q, ldq, st))) return rc;
-    if ((rc = backward_block(model, E, R, triples, n, dir, Q, ldq, lab + dir * n, f.col_off, f.K, offset, d_ent, lde,
-                             dQ2 + (size_t)dir * n * ldq, ws, st))) return rc;
+    if ((rc = backward_block(model, E, R, triples, n, dir, Q, ldq, lab + dir * n, f.col_off, f.K, loss_kind, offset, d_ent,
+                             lde, dQ2 + (size_t)dir * n * ldq, ws, st))) return rc;
   }
   // both halves of the dense column gradient are stored: now add the batch rows' own gradients
   for (int dir = 0; dir < 2; ++dir)

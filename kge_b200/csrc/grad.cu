@@ -49,11 +49,52 @@ __device__ __forceinline__ void split_store(__half* __restrict__ hi, __half* __r
   lo[pos] = __float2half_rn(s - __half2float(h));
 }
 
-// G = sigmoid(z + off) - y as fp16 hi/lo planes, row-major [nq, Ep] and transposed [E, Np]; pads zeroed.
+// KL needs the row's log-sum-exp and label mass first: row_stat[2i] = logsumexp_j z_ij, row_stat[2i+1] = sum_j y_ij
+// (loss.py:198-213).  One block per row.
+__global__ void __launch_bounds__(256)
+row_lse_kernel(const float* __restrict__ z, int64_t ldz, int64_t E, const int64_t* __restrict__ label_idx,
+               const float* __restrict__ label_dense, int64_t ldl, float* __restrict__ row_stat) {
+  __shared__ float red[3][8];
+  const int64_t i = blockIdx.x;
+  const float* __restrict__ zr = z + i * ldz;
+  float mx = -INFINITY, ys = 0.f;
+  for (int64_t e = threadIdx.x; e < E; e += blockDim.x) {
+    mx = fmaxf(mx, zr[e]);
+    if (label_dense) ys += label_dense[i * ldl + e];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    ys += __shfl_xor_sync(0xffffffffu, ys, o);
+  }
+  if (lane == 0) { red[0][warp] = mx; red[1][warp] = ys; }
+  __syncthreads();
+  mx = red[0][0]; ys = red[1][0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) { mx = fmaxf(mx, red[0][w]); ys += red[1][w]; }
+  float se = 0.f;
+  for (int64_t e = threadIdx.x; e < E; e += blockDim.x) se += expf(zr[e] - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+  if (lane == 0) red[2][warp] = se;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    se = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) se += red[2][w];
+    row_stat[2 * i] = mx + logf(se);
+    row_stat[2 * i + 1] = label_idx ? ((label_idx[i] >= 0 && label_idx[i] < E) ? 1.f : 0.f) : ys;
+  }
+}
+
+// G = dL/dz * n as fp16 hi/lo planes, row-major [nq, Ep] and transposed [E, Np]; pads zeroed.
+//   BCE (row_stat == nullptr): G = sigmoid(z + off) - y          KL: G = y_sum * exp(z - lse) - y
 // grid = (Ep/32, Np/32), block = 32 x 8.
 __global__ void __launch_bounds__(256)
 grad_planes_kernel(const float* __restrict__ z, int64_t ldz, int64_t nq, int64_t E,
                    const int64_t* __restrict__ label_idx, const float* __restrict__ label_dense, int64_t ldl,
+                   const float* __restrict__ row_stat,
                    float offset, float inv_n, __half* __restrict__ g_hi, __half* __restrict__ g_lo, int64_t Ep,
                    __half* __restrict__ gt_hi, __half* __restrict__ gt_lo, int64_t Np,
                    float* __restrict__ g_scale, float* __restrict__ gt_scale) {
@@ -68,7 +109,8 @@ grad_planes_kernel(const float* __restrict__ z, int64_t ldz, int64_t nq, int64_t
     if (i < nq && e < E) {
       const float x = __ldg(z + i * ldz + e) + offset;
       const float y = label_idx ? ((label_idx[i] == e) ? 1.f : 0.f) : __ldg(label_dense + i * ldl + e);
-      g = 1.0f / (1.0f + expf(-x)) - y;
+      if (row_stat) g = row_stat[2 * i + 1] * expf(x - row_stat[2 * i]) - y;
+      else g = 1.0f / (1.0f + expf(-x)) - y;
     }
     tile[ty + 8 * k][tx] = g;
     if (i < nq) {
@@ -191,12 +233,17 @@ int launch_transpose(const float* src, int64_t lds, int64_t R, int64_t C, float*
 }
 
 int launch_grad_planes(const float* z, int64_t ldz, int64_t nq, int64_t E, const int64_t* label_idx,
-                       const float* label_dense, int64_t ldl, float offset, float inv_n, void* g_hi, void* g_lo,
+                       const float* label_dense, int64_t ldl, float* row_stat /* [2*nq] scratch: KL; null: BCE */,
+                       float offset, float inv_n, void* g_hi, void* g_lo,
                        int64_t Ep, void* gt_hi, void* gt_lo, int64_t Np, float* g_scale, float* gt_scale,
                        cudaStream_t st) {
   if (nq == 0 || E == 0) return 0;
+  if (row_stat) {
+    row_lse_kernel<<<(unsigned)nq, 256, 0, st>>>(z, ldz, E, label_idx, label_dense, ldl, row_stat);
+    B2K_LAUNCH_CHECK("row_lse_kernel");
+  }
   dim3 grid((unsigned)(Ep / 32), (unsigned)(Np / 32));
-  grad_planes_kernel<<<grid, 256, 0, st>>>(z, ldz, nq, E, label_idx, label_dense, ldl, offset, inv_n,
+  grad_planes_kernel<<<grid, 256, 0, st>>>(z, ldz, nq, E, label_idx, label_dense, ldl, row_stat, offset, inv_n,
                                             (__half*)g_hi, (__half*)g_lo, Ep, (__half*)gt_hi, (__half*)gt_lo, Np,
                                             g_scale, gt_scale);
   B2K_LAUNCH_CHECK("grad_planes_kernel");

@@ -407,7 +407,7 @@ int launch_pairwise_tc4(int epi_kind, const SplitSet& Q, const SplitSet& T, cons
 // Backward pieces (grad.cu), experimental.
 int launch_transpose(const float* src, int64_t lds, int64_t R, int64_t C, float* dst, int64_t ldd, cudaStream_t st);
 int launch_grad_planes(const float* z, int64_t ldz, int64_t nq, int64_t E, const int64_t* label_idx,
-                       const float* label_dense, int64_t ldl, float offset, float inv_n, void* g_hi, void* g_lo,
+                       const float* label_dense, int64_t ldl, float* row_stat, float offset, float inv_n, void* g_hi, void* g_lo,
                        int64_t Ep, void* gt_hi, void* gt_lo, int64_t Np, float* g_scale, float* gt_scale,
                        cudaStream_t st);
 int launch_unfold(int model, const Rows& ent, const Rows& rel, const int64_t* triples, int64_t n, int dir,

@@ -156,19 +156,21 @@ def test_x_gemm_nt_vs_fp64(eng):
 
 
 @pytest.mark.parametrize("fname", ["grads_complex_bce.npz", "grads_distmult_bce.npz", "grads_simple_bce.npz",
-                                   "grads_cp_bce.npz", "grads_rescal_bce.npz"])
+                                   "grads_cp_bce.npz", "grads_rescal_bce.npz", "grads_complex_kl.npz",
+                                   "grads_rescal_kl.npz"])
 def test_x_backward_golden(eng, fname):
-    """Table gradients of one 1vsAll+BCE step against the live reference's backward."""
+    """Table gradients of one 1vsAll step (BCE with offset, KL) against the live reference's backward."""
     g = _load(fname)
-    model = fname[len("grads_"):-4].split("_")[0]
-    d_ent, d_rel = eng.x_train_1vsall_backward(model, g["ent"].cuda(), g["rel"].cuda(), g["triples"].cuda(), "bce",
+    model, loss = fname[len("grads_"):-4].split("_")
+    d_ent, d_rel = eng.x_train_1vsall_backward(model, g["ent"].cuda(), g["rel"].cuda(), g["triples"].cuda(), loss,
                                                float(g["offset"]))
     _assert_close(d_ent, g["d_ent"], fname + " d_ent")
     _assert_close(d_rel, g["d_rel"], fname + " d_rel")
 
 
+@pytest.mark.parametrize("loss", ["bce", "kl"])
 @pytest.mark.parametrize("model,D", [("complex", 128), ("distmult", 64), ("simple", 128), ("cp", 64), ("rescal", 24)])
-def test_x_backward_medium(eng, model, D):
+def test_x_backward_medium(eng, model, D, loss):
     """Ragged medium shapes with duplicate rows, against the analytic CPU assembly (oracle/kge_fold.py, itself
     pinned to autograd and to the reference's gradients)."""
     from oracle import kge_fold as kf
@@ -177,7 +179,55 @@ def test_x_backward_medium(eng, model, D):
     ent, rel = orc.make_tables(model, E, R, D, sigma=0.5)
     tri = orc.make_triples(E, R, n)
     tri[5] = tri[4]
-    ref_e, ref_r = kf.train_1vsall_backward(model, ent.double(), rel.double(), tri, "bce", 0.5)
-    d_ent, d_rel = eng.x_train_1vsall_backward(model, ent.cuda(), rel.cuda(), tri.cuda(), "bce", 0.5)
+    off = 0.5 if loss == "bce" else 0.0
+    ref_e, ref_r = kf.train_1vsall_backward(model, ent.double(), rel.double(), tri, loss, off)
+    d_ent, d_rel = eng.x_train_1vsall_backward(model, ent.cuda(), rel.cuda(), tri.cuda(), loss, off)
     _assert_close(d_ent, ref_e, f"{model} d_ent")
     _assert_close(d_rel, ref_r, f"{model} d_rel")
+
+
+@pytest.mark.parametrize("model", ["complex", "transe"])
+def test_job_traces_on_gpu(eng, model):
+    """Job-level traces of the reference (tests/golden/jobs_*.npz) through validated entry points only: 1vsAll
+    epoch loss, KvsAll epochs with multi-hot / smoothed labels.  Gated until it has run once on a B200."""
+    g = _load(f"jobs_{model}.npz")
+    ent, rel, train = g["ent"].cuda(), g["rel"].cuda(), g["train"].long().cuda()
+    E = ent.shape[0]
+    for loss in ("bce", "kl"):
+        got = float(eng.train_1vsall_forward(model, ent, rel, train, loss))
+        want = float(g[f"avg_loss_{loss}"])
+        assert abs(got - want) <= 1e-4 * abs(want), (loss, got, want)
+
+    def examples(key_cols, val_col):
+        keys, inv = torch.unique(train[:, key_cols], dim=0, return_inverse=True)
+        labels = torch.zeros((keys.shape[0], E), device="cuda")
+        labels.index_put_((inv, train[:, val_col]), torch.ones(len(train), device="cuda"), accumulate=True)
+        return keys, labels
+
+    sp_keys, sp_lab = examples([S, P], O)
+    po_keys, po_lab = examples([P, O], S)
+    n = sp_keys.shape[0] + po_keys.shape[0]
+    for loss, eps in (("kl", 0.0), ("kl", 0.2), ("bce", 0.2)):
+        lab = (lambda y: (1.0 - eps) * y + 1.0 / E) if eps > 0 else (lambda y: y)
+        l_sp = eng.score_1vsN_loss(model, "sp_", ent, rel, ent, lab(sp_lab), sp_keys[:, 0].contiguous(),
+                                   sp_keys[:, 1].contiguous(), None, loss, 0.0)
+        l_po = eng.score_1vsN_loss(model, "_po", ent, rel, ent, lab(po_lab), po_keys[:, 1].contiguous(),
+                                   po_keys[:, 0].contiguous(), None, loss, 0.0)
+        got = (float(l_sp) + float(l_po)) / n
+        want = float(g[f"kvsall_avg_loss_{loss}_{int(eps * 10)}"])
+        assert abs(got - want) <= 1e-4 * abs(want), (loss, eps, got, want)
+
+
+@pytest.mark.parametrize("model", ["complex", "rotate"])
+def test_ns_job_batch_on_gpu(eng, model):
+    g = _load(f"nsjob_{model}.npz")
+    ent, rel, tri = g["ent"].cuda(), g["rel"].cuda(), g["triples"].long().cuda()
+    n, off = tri.shape[0], float(g["offset"])
+    total = 0.0
+    for slot, nm in ((S, "s"), (P, "p"), (O, "o")):
+        neg = g[f"neg_{nm}"].long().cuda()
+        scores = eng.ns_score(model, ent, rel, tri, neg, slot, True)
+        labels = torch.zeros_like(scores)
+        labels[:, 0] = 1.0
+        total += float(eng.loss_dense(scores, labels, "bce", off)) / n
+    assert abs(total - float(g["avg_loss"])) <= 1e-4 * abs(float(g["avg_loss"])), (total, float(g["avg_loss"]))
