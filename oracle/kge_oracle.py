@@ -447,6 +447,55 @@ def entity_ranking_metrics(model, ent, rel, eval_triples, filter_splits, test_tr
     return out
 
 
+# --------------------------------------------------------------------------- f-3: penalties, normalisation
+def _abs_complex(w):
+    """lookup_embedder.py:118-121 (modulus of the complex halves, +1e-14 under the root)."""
+    h = w.shape[1] // 2
+    return torch.sqrt(w[:, :h] ** 2 + w[:, h:] ** 2 + 1e-14)
+
+
+def lookup_penalty(weight, regularize="lp", regularize_weight=0.0, p=2, weighted=False, indexes=None,
+                   space="euclidean"):
+    """LookupEmbedder.penalty (lookup_embedder.py:123-177) as a scalar tensor: Lp / N3 regularisation over the
+    whole table (unweighted) or over the batch's unique rows weighted by their counts and divided by the number
+    of indexes (weighted)."""
+    if regularize == "" or regularize_weight == 0.0:
+        return weight.new_zeros(())
+    if regularize == "n3":
+        p = 3
+    elif regularize != "lp":
+        raise ValueError(f"Invalid value regularize={regularize}")
+    if not weighted:
+        params = weight
+        if regularize == "n3" and space == "complex":
+            params = _abs_complex(params)
+        return (regularize_weight / p * params.norm(p=p) ** p).sum()
+    uniq, counts = torch.unique(indexes, return_counts=True)
+    params = weight[uniq.long()]
+    if regularize == "n3" and space == "complex":
+        params = _abs_complex(params)
+    if (p % 2 == 1) and regularize != "n3":
+        params = torch.abs(params)
+    # len(indexes): the entity call passes an [n, 2] block of subjects and objects, so the divisor is n, not 2n
+    return (regularize_weight / p * (params ** p * counts.float().view(-1, 1))).sum() / indexes.shape[0]
+
+
+def model_penalty(ent, rel, triples, ent_opts, rel_opts):
+    """KgeModel.penalty with a shared entity embedder (kge_model.py:603-649): relation penalty on triples[:,P];
+    entity penalty on the [n,2] block of subjects and objects if weighted, else the table penalty doubled."""
+    total = lookup_penalty(rel, indexes=triples[:, P], **rel_opts)
+    if ent_opts.get("weighted", False):
+        total = total + lookup_penalty(ent, indexes=triples[:, [S, O]], **ent_opts)
+    else:
+        total = total + 2.0 * lookup_penalty(ent, **ent_opts)
+    return total
+
+
+def normalize_embeddings(weight, p):
+    """LookupEmbedder._normalize_embeddings (lookup_embedder.py:64-69): rows scaled to unit Lp norm (p > 0)."""
+    return torch.nn.functional.normalize(weight, p=p, dim=-1) if p > 0 else weight
+
+
 # --------------------------------------------------------------------------- synthetic inputs
 def make_tables(model: str, E: int, R: int, D: int, sigma: float = 1.0, seed: int = 1234,
                 dtype=torch.float32):

@@ -337,6 +337,51 @@ def gen_ns_job(model, tag):
     print("wrote nsjob", tag, float(out["avg_loss"]), {k: v.shape for k, v in out.items() if k.startswith("neg")})
 
 
+PENALTY_CASES = [
+    # (tag, model, entity options, relation options)   options: regularize, regularize_weight, p, weighted
+    ("complex_l2", "complex", dict(regularize="lp", regularize_weight=0.1, p=2, weighted=False),
+     dict(regularize="lp", regularize_weight=0.2, p=2, weighted=False)),
+    ("complex_l3w", "complex", dict(regularize="lp", regularize_weight=0.1, p=3, weighted=True),
+     dict(regularize="lp", regularize_weight=0.05, p=3, weighted=True)),
+    ("complex_n3w", "complex", dict(regularize="n3", regularize_weight=0.3, p=3, weighted=True),
+     dict(regularize="n3", regularize_weight=0.2, p=3, weighted=True)),
+    ("complex_n3", "complex", dict(regularize="n3", regularize_weight=0.3, p=3, weighted=False),
+     dict(regularize="n3", regularize_weight=0.0, p=3, weighted=False)),
+    ("distmult_l1w", "distmult", dict(regularize="lp", regularize_weight=0.4, p=1, weighted=True),
+     dict(regularize="lp", regularize_weight=0.1, p=2, weighted=False)),
+]
+
+
+def gen_penalties():
+    """KgeModel.penalty(batch=...) of the live reference (kge_model.py:603-649, lookup_embedder.py:123-177) and
+    the row normalisation hook (lookup_embedder.py:64-69)."""
+    E, R, D, n = 37, 5, 16, 40
+    out = {}
+    for tag, model, eo, ro in PENALTY_CASES:
+        ent, rel = orc.make_tables(model, E, R, D, sigma=0.7)
+        tri = orc.make_triples(E, R, n, seed=4)
+        tri[1] = tri[0]
+        extra = {}
+        for key, o in (("entity_embedder", eo), ("relation_embedder", ro)):
+            extra[f"{model}.{key}.regularize"] = o["regularize"]
+            extra[f"{model}.{key}.regularize_weight"] = o["regularize_weight"]
+            extra[f"{model}.{key}.regularize_args.p"] = o["p"]
+            extra[f"{model}.{key}.regularize_args.weighted"] = o["weighted"]
+        m, _, _ = ref_shim.make_reference_model(model, E, R, D, ent, rel, extra=extra)
+        pen = m.penalty(batch={"triples": tri})
+        out[f"{tag}_total"] = np.float64(sum(float(v) for _, v in pen))
+        out[f"{tag}_ent"], out[f"{tag}_rel"], out[f"{tag}_triples"] = _np(ent), _np(rel), _np(tri)
+    ent, _ = orc.make_tables("transe", E, R, D, sigma=0.7)
+    for pn in (1.0, 2.0):
+        m, _, _ = ref_shim.make_reference_model("transe", E, R, D, ent, None, l_norm=1.0,
+                                                extra={"transe.entity_embedder.normalize.p": pn})
+        m.get_s_embedder()._normalize_embeddings()
+        out[f"normalize_p{int(pn)}"] = _np(m.get_s_embedder()._embeddings.weight)
+    out["normalize_in"] = _np(ent)
+    np.savez_compressed(os.path.join(HERE, "penalties.npz"), **out)
+    print("wrote penalties", {k: float(v) for k, v in out.items() if np.ndim(v) == 0})
+
+
 def gen_grads(model, D, loss, tag):
     """Entity / relation table gradients of one 1vsAll step of the LIVE reference: loss(score_sp, o)/n and
     loss(score_po, s)/n with sum reduction, backward through the reference's own autograd graph
@@ -387,6 +432,7 @@ def main():
     for model in ("complex", "transe"):
         gen_jobs(model, model)
     gen_index()
+    gen_penalties()
     for model in ("complex", "rotate"):
         gen_ns_job(model, model)
     for model in orc.MODELS:

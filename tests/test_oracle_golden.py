@@ -173,3 +173,23 @@ def test_negative_sampling_batch_matches_reference_job(model):
                                                       orc.ns_labels(n, neg.shape[1]), off)) / n) <= 1e-5 * abs(loss)
     assert int(g["size"]) == n
     assert abs(total - float(g["avg_loss"])) <= 2e-5 * abs(float(g["avg_loss"])), (total, float(g["avg_loss"]))
+
+
+def test_penalties_and_normalisation_match_reference():
+    """KgeModel.penalty(batch) for Lp / N3, weighted / unweighted (kge_model.py:603-649, lookup_embedder.py:123-177)
+    and the row normalisation hook (lookup_embedder.py:64-69)."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from gen_golden import PENALTY_CASES      # the option sets the fixtures were generated with
+
+    g = _load("penalties.npz")
+    for tag, model, eo, ro in PENALTY_CASES:
+        space = "complex" if model == "complex" else "euclidean"
+        got = float(orc.model_penalty(g[f"{tag}_ent"], g[f"{tag}_rel"], g[f"{tag}_triples"].long(),
+                                      dict(eo, space=space), dict(ro, space=space)))
+        want = float(g[f"{tag}_total"])
+        assert abs(got - want) <= 1e-5 * abs(want), (tag, got, want)
+    for pn in (1, 2):
+        got = orc.normalize_embeddings(g["normalize_in"], float(pn))
+        assert torch.allclose(got, g[f"normalize_p{pn}"], rtol=1e-6, atol=1e-7)
+        assert torch.allclose(got.abs().pow(pn).sum(1).pow(1.0 / pn), torch.ones(got.shape[0]), atol=1e-5)
