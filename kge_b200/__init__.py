@@ -6,9 +6,10 @@ CP / RESCAL (tcgen05 3xTF32) and TransE / RotatE (CUDA-core distance kernels), f
 loss, rank/tie counting and negative-sample gather+score.  No CPU fallback.
 """
 from . import _lib, engine, indexing  # noqa: F401
-from .model import KgeModel, LookupEmbedder, RelationalScorer, KgeLoss, BatchNegativeSample  # noqa: F401
+from .model import (KgeModel, ReciprocalRelationsModel, LookupEmbedder, RelationalScorer, KgeLoss,  # noqa: F401
+                    BatchNegativeSample)
 from .evaluate import EntityRankingEvaluator  # noqa: F401
 from .indexing import KvsAllIndex  # noqa: F401
 
-__all__ = ["engine", "indexing", "KgeModel", "LookupEmbedder", "RelationalScorer", "KgeLoss", "BatchNegativeSample",
+__all__ = ["engine", "indexing", "KgeModel", "ReciprocalRelationsModel", "LookupEmbedder", "RelationalScorer", "KgeLoss", "BatchNegativeSample",
            "EntityRankingEvaluator", "KvsAllIndex"]

@@ -207,6 +207,50 @@ class KgeModel(torch.nn.Module):
                                       rank, ties)
 
 
+class ReciprocalRelationsModel(KgeModel):
+    """reciprocal_relations_model.py:16-124: a base model with 2R relation rows; row p + R is the reciprocal of
+    relation p, and every query about subjects, (?, p, o), is answered as the object query (o, p + R, ?).  Only
+    the index arithmetic lives here — all scoring goes through the same `sp_` entry points as the base model."""
+
+    def __init__(self, model: str, num_entities: int, num_relations: int, dim: int, **kwargs):
+        super().__init__(model, num_entities, 2 * num_relations, dim, **kwargs)
+        self.num_relations = int(num_relations)
+
+    def score_spo(self, s, p, o, direction=None) -> torch.Tensor:
+        if direction == "o":
+            return super().score_spo(s, p, o, "o")
+        if direction == "s":
+            return super().score_spo(o, p + self.num_relations, s, "o")
+        raise Exception("The reciprocal relations model cannot compute undirected spo scores.")    # :79-82
+
+    def score_po(self, p, o, s=None) -> torch.Tensor:
+        return engine.score_1vsN(self.model_name, "sp_", self._ent, self._rel, self._ent, o, p + self.num_relations, s,
+                                 self.l_norm, self.precision)
+
+    def score_so(self, s, o, p=None):
+        raise Exception("The reciprocal relations model cannot score relations.")                   # :94-95
+
+    def score_sp_po(self, s, p, o, entity_subset=None) -> torch.Tensor:
+        n = s.numel()
+        m = self._ent.shape[0] if entity_subset is None else entity_subset.numel()
+        out = torch.empty((n, 2 * m), dtype=torch.float32, device=self._ent.device)
+        engine.score_1vsN(self.model_name, "sp_", self._ent, self._rel, self._ent, s, p, entity_subset, self.l_norm,
+                          self.precision, out=out[:, :m])
+        engine.score_1vsN(self.model_name, "sp_", self._ent, self._rel, self._ent, o, p + self.num_relations,
+                          entity_subset, self.l_norm, self.precision, out=out[:, m:])
+        return out
+
+    def score_po_loss(self, p, o, labels, loss="bce", offset=0.0, s=None):
+        return engine.score_1vsN_loss(self.model_name, "sp_", self._ent, self._rel, self._ent, labels, o,
+                                      p + self.num_relations, s, loss, offset, self.l_norm, self.precision)
+
+    def rank_po(self, p, o, true_scores, entity_subset=None, filter_labels=None, rtol=1e-4, atol=1e-5,
+                rank=None, ties=None):
+        return engine.score_1vsN_rank(self.model_name, "sp_", self._ent, self._rel, self._ent, true_scores, o,
+                                      p + self.num_relations, entity_subset, filter_labels, rtol, atol, self.l_norm,
+                                      self.precision, rank, ties)
+
+
 class KgeLoss:
     """loss.py:20-213 for the two in-scope losses; `__call__(scores, labels)` with labels either a
     vector of positions or a label matrix; reduction is SUM (the caller divides by batch size)."""

@@ -447,6 +447,27 @@ def entity_ranking_metrics(model, ent, rel, eval_triples, filter_splits, test_tr
     return out
 
 
+# --------------------------------------------------------------------------- f-4: reciprocal relations
+def reciprocal_score_spo(model, ent, rel2, s, p, o, direction, num_relations, l_norm=1.0):
+    """ReciprocalRelationsModel.score_spo (reciprocal_relations_model.py:72-82); rel2 has 2R rows."""
+    if direction == "o":
+        return score_spo(model, ent, rel2, s, p, o, l_norm)
+    if direction == "s":
+        return score_spo(model, ent, rel2, o, p + num_relations, s, l_norm)
+    raise Exception("The reciprocal relations model cannot compute undirected spo scores.")
+
+
+def reciprocal_score_po(model, ent, rel2, p, o, num_relations, s_subset=None, l_norm=1.0):
+    """(?, p, o) scored as the object query (o, p + R, ?)   reciprocal_relations_model.py:84-91."""
+    return score_sp(model, ent, rel2, o, p + num_relations, s_subset, l_norm=l_norm)
+
+
+def reciprocal_score_sp_po(model, ent, rel2, s, p, o, num_relations, entity_subset=None, l_norm=1.0):
+    """reciprocal_relations_model.py:97-124."""
+    return torch.cat([score_sp(model, ent, rel2, s, p, entity_subset, l_norm=l_norm),
+                      reciprocal_score_po(model, ent, rel2, p, o, num_relations, entity_subset, l_norm)], 1)
+
+
 # --------------------------------------------------------------------------- f-3: penalties, normalisation
 def _abs_complex(w):
     """lookup_embedder.py:118-121 (modulus of the complex halves, +1e-14 under the root)."""

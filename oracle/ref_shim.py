@@ -76,7 +76,7 @@ def import_reference():
 
 
 def make_reference_model(model: str, E: int, R: int, D: int, ent=None, rel=None,
-                         l_norm: float | None = None, extra: dict | None = None):
+                         l_norm: float | None = None, extra: dict | None = None, imports=()):
     """Builds a reference KgeModel on CPU over an in-memory dataset of the given shape and
     (optionally) injects seeded embedding tables."""
     import torch
@@ -90,6 +90,8 @@ def make_reference_model(model: str, E: int, R: int, D: int, ent=None, rel=None,
     config.set("console.quiet", True)
     config.set("model", model)
     config._import(model)
+    for extra_model in imports:          # e.g. the base model of reciprocal_relations_model
+        config._import(extra_model)
     config.set("dataset.name", "synthetic")
     config.set("dataset.num_entities", E)
     config.set("dataset.num_relations", R)
@@ -101,6 +103,9 @@ def make_reference_model(model: str, E: int, R: int, D: int, ent=None, rel=None,
     if extra:
         config.set_all(extra)
     dataset = Dataset(config, None)
+    # in-memory dataset: no files to read (the reciprocal-relations wrapper looks these up)
+    dataset._meta["entity_ids"] = [f"e{i}" for i in range(E)]
+    dataset._meta["relation_ids"] = [f"r{i}" for i in range(R)]
     m = KgeModel.create(config, dataset)
     m.eval()
     with torch.no_grad():

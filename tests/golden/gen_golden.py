@@ -382,6 +382,25 @@ def gen_penalties():
     print("wrote penalties", {k: float(v) for k, v in out.items() if np.ndim(v) == 0})
 
 
+def gen_reciprocal(base, tag):
+    """ReciprocalRelationsModel over `base` (reciprocal_relations_model.py): relation table with 2R rows."""
+    E, R, D, n = 53, 4, 16, 11
+    ent, rel2 = orc.make_tables(base, E, 2 * R, D, sigma=0.8)
+    tri = orc.make_triples(E, R, n, seed=6)
+    m, _, _ = ref_shim.make_reference_model(
+        "reciprocal_relations_model", E, R, D, ent, rel2,
+        extra={"reciprocal_relations_model.base_model.type": base}, imports=[base])
+    s, p, o = tri[:, S], tri[:, P], tri[:, O]
+    sub = torch.randperm(E, generator=torch.Generator().manual_seed(2))[:17]
+    with torch.no_grad():
+        out = dict(ent=_np(ent), rel2=_np(rel2), triples=_np(tri), subset=_np(sub), num_relations=np.int64(R),
+                   spo_o=_np(m.score_spo(s, p, o, "o")), spo_s=_np(m.score_spo(s, p, o, "s")),
+                   sp=_np(m.score_sp(s, p)), po=_np(m.score_po(p, o)), po_subset=_np(m.score_po(p, o, sub)),
+                   sp_po=_np(m.score_sp_po(s, p, o)), sp_po_subset=_np(m.score_sp_po(s, p, o, sub)))
+    np.savez_compressed(os.path.join(HERE, f"reciprocal_{tag}.npz"), **out)
+    print("wrote reciprocal", tag)
+
+
 def gen_grads(model, D, loss, tag):
     """Entity / relation table gradients of one 1vsAll step of the LIVE reference: loss(score_sp, o)/n and
     loss(score_po, s)/n with sum reduction, backward through the reference's own autograd graph
@@ -433,6 +452,8 @@ def main():
         gen_jobs(model, model)
     gen_index()
     gen_penalties()
+    for base in ("complex", "transe"):
+        gen_reciprocal(base, base)
     for model in ("complex", "rotate"):
         gen_ns_job(model, model)
     for model in orc.MODELS:

@@ -231,3 +231,27 @@ def test_ns_job_batch_on_gpu(eng, model):
         labels[:, 0] = 1.0
         total += float(eng.loss_dense(scores, labels, "bce", off)) / n
     assert abs(total - float(g["avg_loss"])) <= 1e-4 * abs(float(g["avg_loss"])), (total, float(g["avg_loss"]))
+
+
+@pytest.mark.parametrize("base", ["complex", "transe"])
+def test_reciprocal_model_on_gpu(base):
+    """kge_b200.ReciprocalRelationsModel (index arithmetic over validated `sp_` entry points) against the live
+    reference's ReciprocalRelationsModel.  Gated until it has run once on a B200."""
+    from kge_b200 import ReciprocalRelationsModel
+
+    g = _load(f"reciprocal_{base}.npz")
+    E, D = g["ent"].shape
+    R = int(g["num_relations"])
+    m = ReciprocalRelationsModel(base, E, R, D).cuda()
+    with torch.no_grad():
+        m.get_s_embedder().weight.copy_(g["ent"].cuda())
+        m.get_p_embedder().weight.copy_(g["rel2"].cuda())
+    tri, sub = g["triples"].long().cuda(), g["subset"].long().cuda()
+    s, p, o = tri[:, S].contiguous(), tri[:, P].contiguous(), tri[:, O].contiguous()
+    _assert_close(m.score_spo(s, p, o, "o"), g["spo_o"], "spo o")
+    _assert_close(m.score_spo(s, p, o, "s"), g["spo_s"], "spo s")
+    _assert_close(m.score_sp(s, p), g["sp"], "sp")
+    _assert_close(m.score_po(p, o), g["po"], "po")
+    _assert_close(m.score_po(p, o, sub), g["po_subset"], "po subset")
+    _assert_close(m.score_sp_po(s, p, o), g["sp_po"], "sp_po")
+    _assert_close(m.score_sp_po(s, p, o, sub), g["sp_po_subset"], "sp_po subset")

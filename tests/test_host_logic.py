@@ -101,3 +101,46 @@ def test_fp16_presplit_scheme_is_fp32_equivalent():
         got = (qh @ th.t() + qh @ tl.t() + ql @ th.t()) * qs * ts.t()
         rms = float(ref.pow(2).mean().sqrt())
         assert float((got - ref).abs().max()) <= 1e-5 * rms, sigma   # an fp32 GEMM itself sits at ~2.5e-6
+
+
+def test_reciprocal_model_index_arithmetic(monkeypatch):
+    """kge_b200.ReciprocalRelationsModel routes every subject-side query through the `sp_` entry points with
+    relation p + R (reciprocal_relations_model.py:72-124); checked on CPU with the engine calls recorded."""
+    import torch
+    import kge_b200
+    from kge_b200 import engine
+
+    calls = []
+
+    def fake_1vsN(model, combine, q_tab, rel, cand_tab, q=None, p=None, cand=None, l_norm=1.0, precision="auto", out=None):
+        calls.append(("1vsN", combine, q.tolist(), p.tolist(), None if cand is None else cand.tolist()))
+        m = cand_tab.shape[0] if cand is None else cand.numel()
+        res = torch.full((q.numel(), m), float(len(calls)))
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+    def fake_spo(model, ent_s, rel, ent_o, s=None, p=None, o=None, l_norm=1.0):
+        calls.append(("spo", s.tolist(), p.tolist(), o.tolist()))
+        return torch.zeros(s.numel())
+
+    monkeypatch.setattr(engine, "score_1vsN", fake_1vsN)
+    monkeypatch.setattr(engine, "score_spo", fake_spo)
+    m = kge_b200.ReciprocalRelationsModel("distmult", 10, 3, 8)
+    assert m.get_p_embedder().weight.shape[0] == 6 and m.num_relations == 3
+    s, p, o = torch.tensor([1, 2]), torch.tensor([0, 2]), torch.tensor([5, 7])
+    m.score_po(p, o)
+    assert calls[-1] == ("1vsN", "sp_", [5, 7], [3, 5], None)
+    m.score_spo(s, p, o, "s")
+    assert calls[-1] == ("spo", [5, 7], [3, 5], [1, 2])
+    m.score_spo(s, p, o, "o")
+    assert calls[-1] == ("spo", [1, 2], [0, 2], [5, 7])
+    out = m.score_sp_po(s, p, o, torch.tensor([4, 5, 6]))
+    assert out.shape == (2, 6) and calls[-2][1:4] == ("sp_", [1, 2], [0, 2]) and calls[-1][1:4] == ("sp_", [5, 7], [3, 5])
+    assert bool((out[:, :3] != out[:, 3:]).all())          # the two halves came from the two calls
+    import pytest
+    with pytest.raises(Exception, match="undirected"):
+        m.score_spo(s, p, o)
+    with pytest.raises(Exception, match="cannot score relations"):
+        m.score_so(s, o)

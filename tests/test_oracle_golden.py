@@ -193,3 +193,19 @@ def test_penalties_and_normalisation_match_reference():
         got = orc.normalize_embeddings(g["normalize_in"], float(pn))
         assert torch.allclose(got, g[f"normalize_p{pn}"], rtol=1e-6, atol=1e-7)
         assert torch.allclose(got.abs().pow(pn).sum(1).pow(1.0 / pn), torch.ones(got.shape[0]), atol=1e-5)
+
+
+@pytest.mark.parametrize("base", ["complex", "transe"])
+def test_reciprocal_relations_model_matches_reference(base):
+    g = _load(f"reciprocal_{base}.npz")
+    ent, rel2, tri, R, sub = g["ent"], g["rel2"], g["triples"].long(), int(g["num_relations"]), g["subset"].long()
+    s, p, o = tri[:, S], tri[:, P], tri[:, O]
+    _close(orc.reciprocal_score_spo(base, ent, rel2, s, p, o, "o", R), g["spo_o"], "spo o")
+    _close(orc.reciprocal_score_spo(base, ent, rel2, s, p, o, "s", R), g["spo_s"], "spo s")
+    _close(orc.score_sp(base, ent, rel2, s, p), g["sp"], "sp")
+    _close(orc.reciprocal_score_po(base, ent, rel2, p, o, R), g["po"], "po")
+    _close(orc.reciprocal_score_po(base, ent, rel2, p, o, R, sub), g["po_subset"], "po subset")
+    _close(orc.reciprocal_score_sp_po(base, ent, rel2, s, p, o, R), g["sp_po"], "sp_po")
+    _close(orc.reciprocal_score_sp_po(base, ent, rel2, s, p, o, R, sub), g["sp_po_subset"], "sp_po subset")
+    with pytest.raises(Exception, match="undirected"):
+        orc.reciprocal_score_spo(base, ent, rel2, s, p, o, None, R)
