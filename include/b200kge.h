@@ -266,6 +266,20 @@ int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const 
                                     float* d_ent, int64_t lde, float* d_rel, int64_t ldr,
                                     void* workspace, size_t workspace_bytes, b200kge_stream_t stream);
 
+/* LookupEmbedder.penalty (kge/model/embedder/lookup_embedder.py:123-177) on the rows view `rows` (the whole
+ * table, or the batch's unique rows through rows->idx with their `counts`, NULL = all ones):
+ *   *out = scale * sum_r counts[r] * sum_k |x_rk|^p        (complex_abs: x -> sqrt(re^2 + im^2 + 1e-14): "n3")
+ * scale = regularize_weight / p (unweighted) or regularize_weight / p / len(indexes) (weighted).
+ * workspace: (ceil(rows / 8) + 1) floats.  Deterministic (fixed-order two-stage sum). */
+int b200kge_x_lookup_penalty(const b200kge_rows_t* rows, const float* counts, float p, int complex_abs,
+                             float scale, float* out, void* workspace, size_t workspace_bytes,
+                             b200kge_stream_t stream);
+
+/* LookupEmbedder._normalize_embeddings (:64-69): rows of weight [rows, dim] (row stride ld) scaled in place to
+ * unit Lp norm (torch.nn.functional.normalize, eps 1e-12). */
+int b200kge_x_normalize_rows(float* weight, int64_t ld, int64_t rows, int32_t dim, float p,
+                             b200kge_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

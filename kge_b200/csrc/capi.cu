@@ -710,4 +710,19 @@ int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const 
   return 0;
 }
 
+
+int b200kge_x_lookup_penalty(const b200kge_rows_t* rows, const float* counts, float p, int complex_abs, float scale,
+                             float* out, void* workspace, size_t workspace_bytes, b200kge_stream_t stream) {
+  if (!rows || !out) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  if (!(p > 0.f)) { set_error("p must be positive (got %g)", (double)p); return B200KGE_ERR_INVALID; }
+  if (complex_abs && (rows->dim & 1)) { set_error("complex-space penalty needs an even embedding width"); return B200KGE_ERR_INVALID; }
+  return launch_penalty(to_rows(rows), counts, p, complex_abs, scale, (float*)workspace, workspace_bytes / 4, out,
+                        (cudaStream_t)stream);
+}
+
+int b200kge_x_normalize_rows(float* weight, int64_t ld, int64_t rows, int32_t dim, float p, b200kge_stream_t stream) {
+  if (!weight && rows > 0) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  return launch_normalize_rows(weight, ld, rows, dim, p, (cudaStream_t)stream);
+}
+
 }  // extern "C"

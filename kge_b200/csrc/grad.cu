@@ -222,7 +222,110 @@ unfold_kernel(Rows ent, Rows rel, const int64_t* __restrict__ tri, int64_t n, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lp / N3 penalty of embedding rows (lookup_embedder.py:123-177): sum over the selected rows of
+// count_r * sum_k |x_rk|^p  (N3 in complex space: x -> sqrt(re^2 + im^2 + 1e-14), p = 3), times scale.
+// One block per PEN_ROWS rows, per-block partial sums, last block (ticket) adds them in block order.
+constexpr int PEN_ROWS = 8;
+
+__device__ __forceinline__ float pow_p(float a, float p, int ip) {
+  if (ip == 1) return a;
+  if (ip == 2) return a * a;
+  if (ip == 3) return a * a * a;
+  return powf(a, p);
+}
+
+__global__ void __launch_bounds__(256)
+penalty_kernel(Rows tab, const float* __restrict__ counts, float p, int complex_abs, float scale,
+               float* __restrict__ partial, unsigned int* __restrict__ ticket, float* __restrict__ out) {
+  __shared__ float red[8];
+  __shared__ bool last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * PEN_ROWS + warp;
+  const int ip = (p == 1.f) ? 1 : (p == 2.f) ? 2 : (p == 3.f) ? 3 : 0;
+  float acc = 0.f;
+  if (r < tab.rows) {
+    const float* __restrict__ x = tab.row(r);
+    if (complex_abs) {
+      const int h = tab.dim >> 1;
+      for (int k = lane; k < h; k += 32) {
+        const float re = x[k], im = x[k + h];
+        acc += pow_p(sqrtf(re * re + im * im + 1e-14f), p, ip);
+      }
+    } else {
+      for (int k = lane; k < tab.dim; k += 32) acc += pow_p(fabsf(x[k]), p, ip);
+    }
+    if (counts) acc *= counts[r];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < PEN_ROWS; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    float t = 0.f;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += __ldcg(partial + b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tot += red[w];
+      *out = tot * scale;
+      *ticket = 0u;
+    }
+  }
+}
+
+// rows scaled to unit Lp norm in place (F.normalize, eps = 1e-12; lookup_embedder.py:64-69). One warp per row.
+__global__ void __launch_bounds__(256)
+normalize_rows_kernel(float* __restrict__ w, int64_t ld, int64_t rows, int dim, float p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + warp;
+  if (r >= rows) return;
+  float* __restrict__ x = w + r * ld;
+  const int ip = (p == 1.f) ? 1 : (p == 2.f) ? 2 : (p == 3.f) ? 3 : 0;
+  float acc = 0.f;
+  for (int k = lane; k < dim; k += 32) acc += pow_p(fabsf(x[k]), p, ip);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  const float nrm = (ip == 1) ? acc : (ip == 2) ? sqrtf(acc) : powf(acc, 1.0f / p);
+  const float inv = 1.0f / fmaxf(nrm, 1e-12f);
+  for (int k = lane; k < dim; k += 32) x[k] *= inv;
+}
+
 }  // namespace
+
+int launch_penalty(const Rows& tab, const float* counts, float p, int complex_abs, float scale, float* scratch,
+                   size_t scratch_floats, float* out, cudaStream_t st) {
+  const int64_t blocks = (tab.rows + PEN_ROWS - 1) / PEN_ROWS;
+  if (blocks == 0) { return check_cuda(cudaMemsetAsync(out, 0, 4, st), "cudaMemsetAsync(penalty)"); }
+  if ((size_t)blocks + 1 > scratch_floats || blocks >= (1ll << 31)) { set_error("workspace too small for the penalty partials"); return B200KGE_ERR_WORKSPACE; }
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + blocks);
+  cudaError_t e = cudaMemsetAsync(ticket, 0, 4, st);
+  if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(ticket)");
+  penalty_kernel<<<(unsigned)blocks, 256, 0, st>>>(tab, counts, p, complex_abs, scale, scratch, ticket, out);
+  B2K_LAUNCH_CHECK("penalty_kernel");
+  return 0;
+}
+
+int launch_normalize_rows(float* w, int64_t ld, int64_t rows, int dim, float p, cudaStream_t st) {
+  if (rows == 0 || !(p > 0.f)) return 0;
+  normalize_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w, ld, rows, dim, p);
+  B2K_LAUNCH_CHECK("normalize_rows_kernel");
+  return 0;
+}
 
 int launch_transpose(const float* src, int64_t lds, int64_t R, int64_t C, float* dst, int64_t ldd, cudaStream_t st) {
   if (R == 0 || C == 0) return 0;

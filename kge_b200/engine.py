@@ -349,3 +349,43 @@ def x_train_1vsall_backward(model: str, ent, rel, triples, loss: str = "bce", of
         MODELS[model], C.byref(re_), C.byref(rr), tri.data_ptr(), n, LOSS[loss], offset, d_ent.data_ptr(),
         d_ent.stride(0), d_rel.data_ptr(), d_rel.stride(0), ws.data_ptr(), ws.numel(), _stream(dev)))
     return d_ent, d_rel
+
+
+def x_lookup_penalty(weight: torch.Tensor, regularize: str = "lp", regularize_weight: float = 0.0, p: float = 2.0,
+                     weighted: bool = False, indexes: Optional[torch.Tensor] = None, space: str = "euclidean"):
+    """LookupEmbedder.penalty (lookup_embedder.py:123-177) as a 0-d tensor."""
+    _require_cuda(weight, indexes)
+    dev = weight.device
+    if regularize == "" or regularize_weight == 0.0:
+        return torch.zeros((), dtype=torch.float32, device=dev)
+    if regularize == "n3":
+        p = 3.0
+    elif regularize != "lp":
+        raise ValueError(f"Invalid value regularize={regularize}")
+    lib, k = _lib.load(), _Keep()
+    complex_abs = 1 if (regularize == "n3" and space == "complex") else 0
+    counts = None
+    if weighted:
+        uniq, cnt = torch.unique(indexes, return_counts=True)
+        rows = k.rows(weight, uniq)
+        counts = cnt.float().contiguous()
+        scale = regularize_weight / p / indexes.shape[0]          # len(indexes): rows of the index block
+    else:
+        rows = k.rows(weight)
+        scale = regularize_weight / p
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    ws = torch.empty(((int(rows.rows) + 7) // 8 + 2) * 4, dtype=torch.uint8, device=dev)
+    _lib.check(lib.b200kge_x_lookup_penalty(C.byref(rows), counts.data_ptr() if counts is not None else None, p,
+                                            complex_abs, scale, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
+    return out
+
+
+def x_normalize_rows_(weight: torch.Tensor, p: float) -> torch.Tensor:
+    """In-place row normalisation to unit Lp norm (lookup_embedder.py:64-69)."""
+    _require_cuda(weight)
+    w = _f32(weight)
+    if w.data_ptr() != weight.data_ptr():
+        raise ValueError("normalisation is in place: pass a row-contiguous float32 matrix")
+    _lib.check(_lib.load().b200kge_x_normalize_rows(w.data_ptr(), w.stride(0), w.shape[0], w.shape[1], p,
+                                                    _stream(w.device)))
+    return weight

@@ -255,3 +255,28 @@ def test_reciprocal_model_on_gpu(base):
     _assert_close(m.score_po(p, o, sub), g["po_subset"], "po subset")
     _assert_close(m.score_sp_po(s, p, o), g["sp_po"], "sp_po")
     _assert_close(m.score_sp_po(s, p, o, sub), g["sp_po_subset"], "sp_po subset")
+
+
+def test_x_penalties_and_normalisation_golden(eng):
+    """Row kernels for Lp / N3 penalties and normalisation against the live reference (penalties.npz)."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from gen_golden import PENALTY_CASES
+
+    g = _load("penalties.npz")
+    for tag, model, eo, ro in PENALTY_CASES:
+        space = "complex" if model == "complex" else "euclidean"
+        ent, rel, tri = g[f"{tag}_ent"].cuda(), g[f"{tag}_rel"].cuda(), g[f"{tag}_triples"].long().cuda()
+
+        def pen(w, o, idx):
+            return float(eng.x_lookup_penalty(w, o["regularize"], o["regularize_weight"], float(o["p"]), o["weighted"],
+                                              idx if o["weighted"] else None, space))
+
+        total = pen(rel, ro, tri[:, P])
+        total += pen(ent, eo, tri[:, [S, O]]) if eo["weighted"] else 2.0 * pen(ent, eo, None)
+        want = float(g[f"{tag}_total"])
+        assert abs(total - want) <= 1e-5 * abs(want), (tag, total, want)
+    for pn in (1, 2):
+        w = g["normalize_in"].cuda().clone()
+        eng.x_normalize_rows_(w, float(pn))
+        assert torch.allclose(w.cpu(), g[f"normalize_p{pn}"], rtol=1e-5, atol=1e-6)
