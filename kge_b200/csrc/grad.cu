@@ -89,7 +89,7 @@ row_lse_kernel(const float* __restrict__ z, int64_t ldz, int64_t E, const int64_
 }
 
 // G = dL/dz * n as fp16 hi/lo planes, row-major [nq, Ep] and transposed [E, Np]; pads zeroed.
-//   BCE (row_stat == nullptr): G = sigmoid(z + off) - y          KL: G = y_sum * exp(z - lse) - y
+//   BCE (row_stat == nullptr): G = sigmoid(z + off) - y          KL: G = w * exp(z - lse) - y / yc,  yc = max(sum y, 1e-12), w = sum y / yc
 // grid = (Ep/32, Np/32), block = 32 x 8.
 __global__ void __launch_bounds__(256)
 grad_planes_kernel(const float* __restrict__ z, int64_t ldz, int64_t nq, int64_t E,
@@ -109,7 +109,10 @@ grad_planes_kernel(const float* __restrict__ z, int64_t ldz, int64_t nq, int64_t
     if (i < nq && e < E) {
       const float x = __ldg(z + i * ldz + e) + offset;
       const float y = label_idx ? ((label_idx[i] == e) ? 1.f : 0.f) : __ldg(label_dense + i * ldl + e);
-      if (row_stat) g = row_stat[2 * i + 1] * expf(x - row_stat[2 * i]) - y;
+      if (row_stat) {   // labels are normalised by their row sum first (loss.py:209-213)
+        const float ys = row_stat[2 * i + 1], yc = fmaxf(ys, 1e-12f);
+        g = (ys / yc) * expf(x - row_stat[2 * i]) - y / yc;
+      }
       else g = 1.0f / (1.0f + expf(-x)) - y;
     }
     tile[ty + 8 * k][tx] = g;

@@ -140,7 +140,9 @@ def loss_grad(z: torch.Tensor, labels: torch.Tensor, loss: str, offset: float, b
     if loss == "bce":
         return (torch.sigmoid(z + offset) - y) / batch_size
     if loss == "kl":
-        return (y.sum(1, keepdim=True) * torch.softmax(z, 1) - y) / batch_size
+        # the reference normalises the labels first: KLDiv(log_softmax(z), y / max(||y||_1, 1e-12))  loss.py:209-213
+        yn = y / y.sum(1, keepdim=True).clamp_min(1e-12)
+        return (yn.sum(1, keepdim=True) * torch.softmax(z, 1) - yn) / batch_size
     raise ValueError(loss)
 
 

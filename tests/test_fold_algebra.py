@@ -89,3 +89,20 @@ def test_gradients_match_the_live_reference(fname):
         d_ent, d_rel = kf.train_1vsall_backward(model, ent, rel, tri, loss, off)
         close(d_ent, g["d_ent"], "analytic d_ent")
         close(d_rel, g["d_rel"], "analytic d_rel")
+
+
+@pytest.mark.parametrize("loss", ["bce", "kl"])
+def test_loss_grad_with_label_matrices(loss):
+    """dL/dz for multi-hot and smoothed label matrices (KvsAll) against autograd of the oracle's losses; KL
+    normalises the label rows first (loss.py:209-213), rows without labels contribute nothing."""
+    g = torch.Generator().manual_seed(5)
+    n, E = 6, 29
+    z = (torch.randn((n, E), generator=g, dtype=torch.float64) * 2).requires_grad_(True)
+    multi = (torch.rand((n, E), generator=g) < 0.15).double()
+    multi[0] = 0.0
+    multi[1, 3] = 2.0                                   # duplicate triple: label 2
+    for lab in (multi, orc.kvsall_smooth_labels(multi, 0.1)):
+        off = 0.3 if loss == "bce" else 0.0
+        l = (orc.bce_loss(z, lab, off) if loss == "bce" else orc.kl_loss(z, lab)) / n
+        (ga,) = torch.autograd.grad(l, z)
+        assert torch.allclose(kf.loss_grad(z.detach(), lab, loss, off, n), ga, rtol=1e-9, atol=1e-12)
