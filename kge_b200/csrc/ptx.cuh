@@ -75,12 +75,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-// Same load, completion bytes signalled on an mbarrier given by its shared::cluster address (may live in
-// the peer CTA of a cluster: CTA-pair kernels let both CTAs' loads complete on the leader's barrier).
+// Same load for CTA pairs: with .cta_group::2 the completion bytes may be signalled on an mbarrier in the PEER
+// CTA (given by its shared::cluster address), so both CTAs' loads complete on the leader's barrier — the form
+// CUTLASS's SM100_TMA_2SM_LOAD uses (cute/arch/copy_sm100_tma.hpp).
 __device__ __forceinline__ void tma_load_2d_cluster_bar(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
                                                         int32_t c0, int32_t c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
