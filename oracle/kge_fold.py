@@ -9,6 +9,8 @@ the analytic backward of the fused score+loss step that the gra
     dQ = g  @ cand[:, cols]       [nq, K]
     dT = g^T @ Q                  [E,  K]   (added into the entity-table gradient at `cols`)
     (da, dp) = unfold(a, p, dQ)             hand-derived vector-Jacobian products of `fold`
+(for TransE / RotatE the two GEMMs become sums over the sign / direction fields of the pairwise differences,
+`pair_backward`).
 
 tests/test_fold_algebra.py checks fold+pair against the oracle's scores for all seven models, `unfold`
 against autograd, and the assembled table gradients against autograd of the oracle's training step and
@@ -126,7 +128,48 @@ def unfold(model: str, combine: str, a: torch.Tensor, p: torch.Tensor, dQ: torch
             da = torch.bmm(dQ.unsqueeze(1), m).squeeze(1)
             dm = torch.bmm(dQ.unsqueeze(2), a.unsqueeze(1))
         return da, dm.reshape(-1, d * d)
-    raise ValueError(f"unfold is defined for the dot family only (got {model})")
+    if model == "transe":      # Q = a + p  |  Q = a - p
+        return dQ, (dQ if sp else -dQ)
+    if model == "rotate":      # Q = a * e^{i theta}  |  Q = conj(e^{i theta}) * a ;  p = theta [n, h]
+        c, sn = torch.cos(p), torch.sin(p)
+        a_re, a_im = a[:, :h], a[:, h:]
+        g_re, g_im = dQ[:, :h], dQ[:, h:]
+        if sp:    # Q_re = a_re c - a_im s ; Q_im = a_re s + a_im c
+            da = torch.cat([g_re * c + g_im * sn, -g_re * sn + g_im * c], 1)
+            dp = g_re * (-a_re * sn - a_im * c) + g_im * (a_re * c - a_im * sn)
+        else:     # Q_re = c a_re + s a_im ; Q_im = c a_im - s a_re
+            da = torch.cat([g_re * c - g_im * sn, g_re * sn + g_im * c], 1)
+            dp = g_re * (-sn * a_re + c * a_im) + g_im * (-sn * a_im - c * a_re)
+        return da, dp
+    raise ValueError(model)
+
+
+def pair_backward(model: str, Q: torch.Tensor, T: torch.Tensor, g: torch.Tensor, l_norm: float = 1.0):
+    """(dQ, dT) of sum_ij g_ij * pair(Q_i, T_j): two GEMMs for the dot family; for the distance family the
+    sign / direction fields of the pairwise differences (what a CUDA-core gradient kernel accumulates tile by
+    tile, never materialising [n, E, D])."""
+    if model in ("complex", "distmult", "simple", "cp", "rescal"):
+        return g @ T, g.t() @ Q
+    if model == "transe":      # z = -||q - t||_p
+        d = Q.unsqueeze(1) - T.unsqueeze(0)                       # [n, E, K]
+        if l_norm == 1.0:
+            w = -torch.sign(d)
+        else:
+            nrm = d.abs().pow(l_norm).sum(2, keepdim=True).pow(1.0 / l_norm)
+            w = -torch.sign(d) * d.abs().pow(l_norm - 1) / nrm.clamp_min(1e-30).pow(l_norm - 1)
+        gw = g.unsqueeze(2) * w
+        return gw.sum(1), -gw.sum(0)
+    if model == "rotate":      # z = -sum_k |q_k - t_k| (complex modulus), L1 over k
+        if l_norm != 1.0:
+            raise NotImplementedError("rotate backward is restated for l_norm = 1 only")
+        h = Q.shape[1] // 2
+        dre = Q[:, :h].unsqueeze(1) - T[:, :h].unsqueeze(0)
+        dim = Q[:, h:].unsqueeze(1) - T[:, h:].unsqueeze(0)
+        mod = torch.sqrt(dre * dre + dim * dim).clamp_min(1e-30)
+        wre, wim = -dre / mod, -dim / mod
+        gre, gim = g.unsqueeze(2) * wre, g.unsqueeze(2) * wim
+        return torch.cat([gre.sum(1), gim.sum(1)], 1), -torch.cat([gre.sum(0), gim.sum(0)], 1)
+    raise ValueError(model)
 
 
 def loss_grad(z: torch.Tensor, labels: torch.Tensor, loss: str, offset: float, batch_size: int) -> torch.Tensor:
@@ -146,9 +189,10 @@ def loss_grad(z: torch.Tensor, labels: torch.Tensor, loss: str, offset: float, b
     raise ValueError(loss)
 
 
-def train_1vsall_backward(model, ent, rel, triples, loss="bce", offset=0.0):
-    """(dEnt [E,D], dRel [R,Dr]) of [loss(score_sp, o) + loss(score_po, s)] / n (train_1vsAll.py:48-82), dot
-    family, assembled as the gradient kernels will: G pass, two GEMMs, row-wise unfold, scatter-add."""
+def train_1vsall_backward(model, ent, rel, triples, loss="bce", offset=0.0, l_norm=1.0):
+    """(dEnt [E,D], dRel [R,Dr]) of [loss(score_sp, o) + loss(score_po, s)] / n (train_1vsAll.py:48-82),
+    assembled as the gradient kernels will: G pass, pair backward (two GEMMs for the dot family), row-wise
+    unfold, scatter-add."""
     s, p, o = triples[:, S].long(), triples[:, P].long(), triples[:, O].long()
     n, D = triples.shape[0], ent.shape[1]
     d_ent, d_rel = torch.zeros_like(ent), torch.zeros_like(rel)
@@ -157,8 +201,8 @@ def train_1vsall_backward(model, ent, rel, triples, loss="bce", offset=0.0):
         a, pr = ent[q_idx], rel[p]
         Q = fold(model, combine, a, pr)
         T = ent[:, off:off + K]
-        g = loss_grad(Q @ T.t(), lab, loss, offset, n)
-        dQ, dT = g @ T, g.t() @ Q
+        g = loss_grad(pair_scores(model, Q, T, l_norm), lab, loss, offset, n)
+        dQ, dT = pair_backward(model, Q, T, g, l_norm)
         d_ent[:, off:off + K] += dT
         da, dp = unfold(model, combine, a, pr, dQ)
         d_ent.index_add_(0, q_idx, da)
