@@ -140,6 +140,51 @@ class ShardedKgeModel:
         self._all_reduce(counts)
         return counts[0], counts[1], counts[2], counts[3]
 
+    # -- duck-typed model interface of kge_b200.evaluate.EntityRankingEvaluator ------------------------
+    # (filtered entity ranking over a sharded table: every rank runs the same evaluator on the same batches;
+    # use chunk_size=-1 — the shards are the chunks)
+    def score_sp(self, s, p, o=None):
+        """[n, |o|] scores of (s,p) against the entities `o` (global ids), identical on every rank: the
+        true-score path of the evaluation loop (eval_entity_ranking.py:192-203)."""
+        if o is None:
+            return self.score_sp_po(s, p, s)[:, : self.E]
+        rows = self.gather_entity_rows(torch.cat([s.long(), o.long()]))
+        n = s.numel()
+        return self.backend.score_1vsN(self.model, "sp_", rows[:n], self.rel[p.long()], rows[n:], self.l_norm, self.precision)
+
+    def score_po(self, p, o, s=None):
+        if s is None:
+            return self.score_sp_po(o, p, o)[:, self.E:]
+        rows = self.gather_entity_rows(torch.cat([o.long(), s.long()]))
+        n = o.numel()
+        return self.backend.score_1vsN(self.model, "_po", rows[:n], self.rel[p.long()], rows[n:], self.l_norm, self.precision)
+
+    def _rank_dir(self, combine, q, p, true_scores, entity_subset, filter_labels, rtol, atol, rank, ties):
+        if entity_subset is not None:
+            raise ValueError("the sharded model ranks against its whole shard: use chunk_size=-1")
+        q_emb = self.gather_entity_rows(q)
+        n = q.numel()
+        counts = torch.zeros((2, n), dtype=torch.int64, device=self.ent.device)
+        if self.hi > self.lo:
+            f = None if filter_labels is None else filter_labels[:, self.lo:self.hi].contiguous()
+            r, t = self.backend.rank_1vsN(self.model, combine, q_emb, self.rel[p.long()], self.ent, true_scores, f, rtol,
+                                          atol, self.l_norm, self.precision)
+            counts[0], counts[1] = r, t
+        self._all_reduce(counts)
+        if rank is None:
+            rank = torch.zeros(n, dtype=torch.int64, device=self.ent.device)
+        if ties is None:
+            ties = torch.zeros(n, dtype=torch.int64, device=self.ent.device)
+        rank += counts[0]
+        ties += counts[1]
+        return rank, ties
+
+    def rank_sp(self, s, p, true_scores, entity_subset=None, filter_labels=None, rtol=1e-4, atol=1e-5, rank=None, ties=None):
+        return self._rank_dir("sp_", s, p, true_scores, entity_subset, filter_labels, rtol, atol, rank, ties)
+
+    def rank_po(self, p, o, true_scores, entity_subset=None, filter_labels=None, rtol=1e-4, atol=1e-5, rank=None, ties=None):
+        return self._rank_dir("_po", o, p, true_scores, entity_subset, filter_labels, rtol, atol, rank, ties)
+
     # -- 1vsAll BCE ------------------------------------------------------------------------------------
     def loss_1vsall_bce(self, s, p, o, offset: float = 0.0):
         """(BCE(score_sp, o) + BCE(score_po, s)) / n with sum reductions (train_1vsAll.py:48-82): BCE is

@@ -125,3 +125,45 @@ def test_shard_bounds_cover_everything():
         assert spans[0][0] == 0 and spans[-1][1] == E
         for a, b in zip(spans, spans[1:]):
             assert a[1] == b[0]
+
+
+def _eval_worker(rank, world, port, model, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+        from kge_b200.evaluate import EntityRankingEvaluator
+        from kge_b200.sharded import ShardedKgeModel
+
+        torch.set_num_threads(2)
+        z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"jobs_{model}.npz"))
+        g = {k: torch.from_numpy(z[k]) if z[k].ndim else z[k].item() for k in z.files}
+        E = g["ent"].shape[0]
+        lo, hi = ShardedKgeModel.shard_bounds(E, world, rank)
+        m = ShardedKgeModel(model, g["ent"][lo:hi].clone(), g["rel"], E, rank, world, backend=OracleBackend())
+        ev = EntityRankingEvaluator(m, E, [g["train"], g["valid"]], g["test"], batch_size=16, hits_at_k_s=(1, 3, 10))
+        met = ev.evaluate(g["valid"])
+        if rank == 0:
+            out.put((met, {k: float(v) for k, v in g.items() if k.startswith("valid_")}))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("model", ["complex", "transe"])
+def test_sharded_evaluation_matches_reference_job(model):
+    """The evaluation loop over an entity-sharded table (2 ranks, gloo): integer rank counts are all-reduced per
+    (ranking, direction); metrics equal the reference EntityRankingJob's trace."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_eval_worker, args=(r, world, port, model, out)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(180)
+        assert pr.exitcode == 0, f"worker failed with exit code {pr.exitcode}"
+    met, want = out.get()
+    for k, v in want.items():
+        assert met[k[len("valid_"):]] == pytest.approx(v, rel=1e-6, abs=1e-9), (k, met[k[len("valid_"):]], v)
