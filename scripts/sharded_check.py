@@ -58,6 +58,30 @@ def main():
         print(json.dumps({"check": "sharded == single-GPU (ranks, logits, BCE, top-k)", "world": world, "ok": True}),
               flush=True)
 
+    # ---- 1b. filtered entity ranking over the sharded table == the reference job's trace --------------
+    # (golden fixtures travel with the repo; first run of this section is part of the next round's checks)
+    try:
+        import numpy as np
+        from kge_b200.evaluate import EntityRankingEvaluator
+
+        for model in ("complex", "transe"):
+            z = np.load(os.path.join(ROOT, "tests", "golden", f"jobs_{model}.npz"))
+            g = {k: torch.from_numpy(z[k]) if z[k].ndim else z[k].item() for k in z.files}
+            E = g["ent"].shape[0]
+            lo, hi = ShardedKgeModel.shard_bounds(E, world, rank)
+            m = ShardedKgeModel(model, g["ent"][lo:hi].to(dev), g["rel"].to(dev), E)
+            ev = EntityRankingEvaluator(m, E, [g["train"], g["valid"]], g["test"], batch_size=16, hits_at_k_s=(1, 3, 10),
+                                        device=dev)
+            met = ev.evaluate(g["valid"])
+            bad = {k: (met[k[6:]], float(v)) for k, v in g.items()
+                   if k.startswith("valid_") and abs(met[k[6:]] - float(v)) > 1e-6 * max(1.0, abs(float(v)))}
+            if rank == 0:
+                print(json.dumps({"check": f"sharded evaluation == reference job ({model})", "world": world,
+                                  "ok": not bad, "mismatch": bad}), flush=True)
+    except Exception as ex:  # keep the timing section running even if this new section fails
+        if rank == 0:
+            print(json.dumps({"check": "sharded evaluation", "world": world, "ok": False, "error": repr(ex)}), flush=True)
+
     # ---- 2. timing at Wikidata5M-shaped shards ---------------------------------------------------
     model, D, n = "transe", args.dim, args.n
     E = args.rows_per_gpu * world
