@@ -208,3 +208,73 @@ def train_1vsall_backward(model, ent, rel, triples, loss="bce", offset=0.0, l_no
         d_ent.index_add_(0, q_idx, da)
         d_rel.index_add_(0, p, dp)
     return d_ent, d_rel
+
+
+def spo_backward(model, ent, rel, s, p, o, g, d_ent, d_rel, l_norm=1.0):
+    """Accumulate into (d_ent, d_rel) the gradient of sum_i g_i * score(s_i, p_i, o_i) through the folded form
+    score = pair(fold_sp(s, p), o[cols]): the row-wise backward that covers positives and every negative-sample
+    slot (a negative sample is one more triple with one slot replaced)."""
+    s, p, o = s.long(), p.long(), o.long()
+    off, K = cand_cols(model, "sp_", ent.shape[1])
+    a, pr = ent[s], rel[p]
+    Q = fold(model, "sp_", a, pr)
+    T = ent[o][:, off:off + K]
+    if model in ("complex", "distmult", "simple", "cp", "rescal"):
+        dQ, dT = g.unsqueeze(1) * T, g.unsqueeze(1) * Q
+    elif model == "transe":
+        d = Q - T
+        if l_norm == 1.0:
+            w = -torch.sign(d)
+        else:
+            nrm = d.abs().pow(l_norm).sum(1, keepdim=True).pow(1.0 / l_norm)
+            w = -torch.sign(d) * d.abs().pow(l_norm - 1) / nrm.clamp_min(1e-30).pow(l_norm - 1)
+        dQ = g.unsqueeze(1) * w
+        dT = -dQ
+    elif model == "rotate":
+        h = Q.shape[1] // 2
+        dre, dim = Q[:, :h] - T[:, :h], Q[:, h:] - T[:, h:]
+        mod = torch.sqrt(dre * dre + dim * dim).clamp_min(1e-30)
+        dQ = g.unsqueeze(1) * torch.cat([-dre / mod, -dim / mod], 1)
+        dT = -dQ
+    else:
+        raise ValueError(model)
+    da, dp = unfold(model, "sp_", a, pr, dQ)
+    d_ent.index_add_(0, s, da)
+    d_rel.index_add_(0, p, dp)
+    full = torch.zeros((o.numel(), ent.shape[1]), dtype=ent.dtype)
+    full[:, off:off + K] = dT
+    d_ent.index_add_(0, o, full)
+
+
+def ns_backward(model, ent, rel, triples, negatives, offset=0.0, l_norm=1.0):
+    """(dEnt, dRel) of one negative-sampling batch with BCE (train_negative_sampling.py:113-164): per slot the
+    [n, 1+K] block (positive first, label 1; negatives label 0), loss summed and divided by the batch size.
+    negatives = {slot: [n, K] ids}."""
+    n = triples.shape[0]
+    d_ent, d_rel = torch.zeros_like(ent), torch.zeros_like(rel)
+    for slot, neg in negatives.items():
+        k = neg.shape[1]
+        t = triples.long().repeat_interleave(1 + k, 0).view(n, 1 + k, 3).clone()
+        t[:, 1:, slot] = neg.long()
+        t = t.view(-1, 3)
+        z = pair_rowwise(model, ent, rel, t[:, S], t[:, P], t[:, O], l_norm)
+        y = torch.zeros((n, 1 + k), dtype=ent.dtype)
+        y[:, 0] = 1.0
+        g = ((torch.sigmoid(z + offset) - y.view(-1)) / n)
+        spo_backward(model, ent, rel, t[:, S], t[:, P], t[:, O], g, d_ent, d_rel, l_norm)
+    return d_ent, d_rel
+
+
+def pair_rowwise(model, ent, rel, s, p, o, l_norm=1.0):
+    """score(s_i, p_i, o_i) through the folded form (row-wise pair)."""
+    off, K = cand_cols(model, "sp_", ent.shape[1])
+    Q = fold(model, "sp_", ent[s.long()], rel[p.long()])
+    T = ent[o.long()][:, off:off + K]
+    if model in ("complex", "distmult", "simple", "cp", "rescal"):
+        return (Q * T).sum(1)
+    if model == "transe":
+        d = (Q - T).abs()
+        return -(d.sum(1) if l_norm == 1.0 else d.pow(l_norm).sum(1).pow(1.0 / l_norm))
+    h = Q.shape[1] // 2
+    mod = torch.sqrt((Q[:, :h] - T[:, :h]) ** 2 + (Q[:, h:] - T[:, h:]) ** 2)
+    return -(mod.sum(1) if l_norm == 1.0 else mod.pow(l_norm).sum(1).pow(1.0 / l_norm))

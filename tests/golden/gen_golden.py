@@ -329,8 +329,14 @@ def gen_ns_job(model, tag):
     job._prepare()
     batch = job._get_collate_fun()(list(range(5, 21)))
     res = job._process_batch(0, batch)
+    # the same batch once more with the backward pass (train_negative_sampling.py:160-164): table gradients
+    job.is_forward_only = False
+    job.model.zero_grad()
+    job._process_batch(0, batch)
     out = dict(ent=_np(ent), rel=_np(rel), triples=_np(batch["triples"]), avg_loss=np.float64(res.avg_loss),
-               size=np.int64(res.size), offset=np.float64(0.5))
+               size=np.int64(res.size), offset=np.float64(0.5),
+               d_ent=_np(job.model.get_s_embedder()._embeddings.weight.grad),
+               d_rel=_np(job.model.get_p_embedder()._embeddings.weight.grad))
     for slot, nm in ((S, "s"), (P, "p"), (O, "o")):
         out[f"neg_{nm}"] = _np(batch["negative_samples"][slot].samples())
     np.savez_compressed(os.path.join(HERE, f"nsjob_{tag}.npz"), **out)
