@@ -266,6 +266,16 @@ int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const 
                                     float* d_ent, int64_t lde, float* d_rel, int64_t ldr,
                                     void* workspace, size_t workspace_bytes, b200kge_stream_t stream);
 
+/* Backward of one slot of a negative-sampling batch with BCE (kge/job/train_negative_sampling.py:113-164): the
+ * [n, 1+K] block of the slot (column 0 = the positive triple, label 1; columns 1.. = the sampled ids neg [n,K],
+ * label 0), loss summed and divided by batch_size.  ADDS into d_ent [E, lde] and d_rel [R, ldr] (zero them before
+ * the first slot).  slot 0 (S) or 2 (O); TransE with l_norm 1 or 2, RotatE with l_norm 1, and the dot family.
+ * workspace: n * round_up(K_folded, 32) floats. */
+int b200kge_x_ns_backward(int model, float l_norm, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+                          const int64_t* triples, int slot, const int64_t* neg, int64_t n, int64_t K,
+                          float offset, int64_t batch_size, float* d_ent, int64_t lde, float* d_rel,
+                          int64_t ldr, void* workspace, size_t workspace_bytes, b200kge_stream_t stream);
+
 /* LookupEmbedder.penalty (kge/model/embedder/lookup_embedder.py:123-177) on the rows view `rows` (the whole
  * table, or the batch's unique rows through rows->idx with their `counts`, NULL = all ones):
  *   *out = scale * sum_r counts[r] * sum_k |x_rk|^p        (complex_abs: x -> sqrt(re^2 + im^2 + 1e-14): "n3")

@@ -75,6 +75,9 @@ SIGNATURES = {
     "b200kge_x_train_1vsall_backward": (C.c_int, [C.c_int, _RP, _RP, C.c_void_p, C.c_int64, C.c_int, C.c_float,
                                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                                   C.c_size_t, C.c_void_p]),
+    "b200kge_x_ns_backward": (C.c_int, [C.c_int, C.c_float, _RP, _RP, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
+                                        C.c_int64, C.c_float, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                        C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200kge_x_lookup_penalty": (C.c_int, [_RP, C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                            C.c_size_t, C.c_void_p]),
     "b200kge_x_normalize_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),

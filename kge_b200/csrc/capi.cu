@@ -725,4 +725,25 @@ int b200kge_x_normalize_rows(float* weight, int64_t ld, int64_t rows, int32_t di
   return launch_normalize_rows(weight, ld, rows, dim, p, (cudaStream_t)stream);
 }
 
+
+int b200kge_x_ns_backward(int model, float l_norm, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+                          const int64_t* triples, int slot, const int64_t* neg, int64_t n, int64_t K, float offset,
+                          int64_t batch_size, float* d_ent, int64_t lde, float* d_rel, int64_t ldr, void* workspace,
+                          size_t workspace_bytes, b200kge_stream_t stream) {
+  if (!ent || !rel || !triples || (!neg && n * K > 0) || !d_ent || !d_rel) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  if (ent->idx || rel->idx) { set_error("ent/rel must be plain tables"); return B200KGE_ERR_INVALID; }
+  int rc = validate_model(model, to_rows(ent), to_rows(rel)); if (rc) return rc;
+  if ((rc = validate_norm(model, l_norm))) return rc;
+  if (batch_size <= 0) { set_error("batch_size must be positive"); return B200KGE_ERR_INVALID; }
+  if (lde < ent->dim || ldr < rel->dim) { set_error("gradient leading dimensions are smaller than the table widths"); return B200KGE_ERR_INVALID; }
+  Rows E = to_rows(ent), R = to_rows(rel);
+  Folded f = folded_problem(model, B200KGE_SP_, E.dim, l_norm);
+  const int64_t ldq = round_up(f.K, 32);
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  float* dQ = (float*)ws.take((size_t)n * ldq * 4);
+  if (!dQ && n > 0) { set_error("workspace too small (need n * round_up(K,32) floats)"); return B200KGE_ERR_WORKSPACE; }
+  return launch_ns_backward(model, l_norm, E, R, triples, slot, neg, n, K, offset, 1.0f / (float)batch_size, d_ent, lde,
+                            d_rel, ldr, dQ, ldq, (cudaStream_t)stream);
+}
+
 }  // extern "C"

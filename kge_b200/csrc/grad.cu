@@ -308,7 +308,190 @@ normalize_rows_kernel(float* __restrict__ w, int64_t ld, int64_t rows, int dim, 
   for (int k = lane; k < dim; k += 32) x[k] *= inv;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward of one negative-sampling slot with BCE (train_negative_sampling.py:113-164), S and O slots: block
+// (i, y) folds the positive triple's (other entity, relation) into q once — as ns_kernel does — and walks 64
+// of the row's 1 + K columns (column 0 = the positive, label 1; columns 1..K = sampled ids, label 0): per
+// column it recomputes z = pair(q, t), g = (sigmoid(z + off) - y) / batch, adds g * dpair/dt into the sampled
+// row of d_ent (atomics: the scatter is inherent) and accumulates g * dpair/dq per lane; the block's dq is
+// added into dQ[i, :], which unfold_kernel then pushes through the relation fold.
+constexpr int NSB_WARPS = 4, NSB_PER_BLOCK = 64, NSB_MAXK = 1024;   // lane-local dq: K / 32 <= 32 registers
+
+template <int MODEL>
+__global__ void __launch_bounds__(NSB_WARPS * 32)
+ns_backward_kernel(Rows ent, Rows rel, const int64_t* __restrict__ tri, int sp, const int64_t* __restrict__ neg,
+                   int64_t Kneg, Folded f, float l_norm, float offset, float inv_batch, float* __restrict__ d_ent,
+                   int64_t lde, float* __restrict__ dQ, int64_t ldq) {
+  extern __shared__ __align__(16) float sh[];  // q[K] | dq[K] (+ entity row for RESCAL)
+  const int64_t i = blockIdx.x;
+  const int64_t si = tri[3 * i], pi = tri[3 * i + 1], oi = tri[3 * i + 2];
+  const int D = ent.dim, h = D >> 1, K = f.K;
+  const float* __restrict__ a = ent.base + (sp ? si : oi) * ent.ld;
+  const float* __restrict__ p = rel.base + pi * rel.ld;
+  float* q = sh;
+  float* sdq = sh + K;
+  if constexpr (MODEL == B200KGE_RESCAL) {
+    float* sa = sh + 2 * K;
+    for (int k = threadIdx.x; k < D; k += blockDim.x) sa[k] = a[k];
+    __syncthreads();
+    fold_rescal_block(sp != 0, sa, p, D, [&](int k, float v) { q[k] = v; });
+  } else {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) q[k] = fold_element<MODEL>(sp != 0, a, p, k, h);
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) sdq[k] = 0.f;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t c0 = (int64_t)blockIdx.y * NSB_PER_BLOCK;
+  const int hk = K >> 1;
+  float dq[NSB_MAXK / 32];
+#pragma unroll
+  for (int j = 0; j < NSB_MAXK / 32; ++j) dq[j] = 0.f;
+  for (int64_t c = c0 + warp; c < c0 + NSB_PER_BLOCK && c <= Kneg; c += NSB_WARPS) {
+    // column 0 is the positive triple (its open slot holds the true entity), columns 1..K the samples
+    const int64_t e = (c == 0) ? (sp ? oi : si) : neg[i * Kneg + (c - 1)];
+    const float y = (c == 0) ? 1.f : 0.f;
+    const float* __restrict__ t = ent.base + e * ent.ld + f.col_off;
+    float* __restrict__ dt = d_ent + e * lde + f.col_off;
+    float acc = 0.f;
+    if (f.pair_op == PAIR_DOT) {
+      for (int k = lane; k < K; k += 32) acc = fmaf(q[k], t[k], acc);
+    } else if (f.pair_op == PAIR_L1) {
+      for (int k = lane; k < K; k += 32) acc += fabsf(q[k] - t[k]);
+    } else if (f.pair_op == PAIR_L2) {
+      for (int k = lane; k < K; k += 32) { const float d = q[k] - t[k]; acc = fmaf(d, d, acc); }
+    } else {   // PAIR_CMOD_L1
+      for (int k = lane; k < hk; k += 32) {
+        const float d_re = q[k] - t[k], d_im = q[k + hk] - t[k + hk];
+        acc += sqrtf(fmaf(d_im, d_im, d_re * d_re));
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    float z = acc, nrm = 1.f;
+    if (f.pair_op == PAIR_L1 || f.pair_op == PAIR_CMOD_L1) z = -acc;
+    else if (f.pair_op == PAIR_L2) { nrm = sqrtf(acc); z = -nrm; }
+    const float g = (1.0f / (1.0f + expf(-(z + offset))) - y) * inv_batch;
+    if (f.pair_op == PAIR_DOT) {
+      for (int k = lane, j = 0; k < K; k += 32, ++j) {
+        dq[j] = fmaf(g, t[k], dq[j]);
+        atomicAdd(dt + k, g * q[k]);
+      }
+    } else if (f.pair_op == PAIR_L1) {          // z = -sum |q - t|
+      for (int k = lane, j = 0; k < K; k += 32, ++j) {
+        const float d = q[k] - t[k];
+        const float w = (d > 0.f) ? -g : (d < 0.f ? g : 0.f);
+        dq[j] += w;
+        atomicAdd(dt + k, -w);
+      }
+    } else if (f.pair_op == PAIR_L2) {          // z = -||q - t||_2
+      const float inv = (nrm > 0.f) ? g / nrm : 0.f;
+      for (int k = lane, j = 0; k < K; k += 32, ++j) {
+        const float w = -(q[k] - t[k]) * inv;
+        dq[j] += w;
+        atomicAdd(dt + k, -w);
+      }
+    } else {                                     // z = -sum_k |q_k - t_k| (complex modulus)
+      for (int k = lane, j = 0; k < hk; k += 32, j += 2) {
+        const float d_re = q[k] - t[k], d_im = q[k + hk] - t[k + hk];
+        const float m = sqrtf(fmaf(d_im, d_im, d_re * d_re));
+        const float inv = (m > 0.f) ? g / m : 0.f;
+        const float w_re = -d_re * inv, w_im = -d_im * inv;
+        dq[j] += w_re;
+        dq[j + 1] += w_im;
+        atomicAdd(dt + k, -w_re);
+        atomicAdd(dt + k + hk, -w_im);
+      }
+    }
+  }
+  // block-level dq: lanes own disjoint columns, warps add up through shared memory
+  if (f.pair_op == PAIR_CMOD_L1) {
+    for (int k = lane, j = 0; k < hk; k += 32, j += 2) { atomicAdd(sdq + k, dq[j]); atomicAdd(sdq + k + hk, dq[j + 1]); }
+  } else {
+    for (int k = lane, j = 0; k < K; k += 32, ++j) atomicAdd(sdq + k, dq[j]);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) atomicAdd(dQ + i * ldq + k, sdq[k]);
+}
+
+// unfold for the distance family (TransE: Q = a +- p; RotatE: rotation) — appended to the dot-family unfold
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+unfold_distance_kernel(Rows ent, Rows rel, const int64_t* __restrict__ tri, int64_t n, int dir,
+                       const float* __restrict__ dQ, int64_t ldq, float* __restrict__ d_ent, int64_t lde,
+                       float* __restrict__ d_rel, int64_t ldr) {
+  const int64_t b = blockIdx.x;
+  const bool sp = dir < 0 ? (b < n) : (dir == 0);
+  const int64_t i = (dir < 0 && b >= n) ? b - n : b;
+  const int64_t si = tri[3 * i], pi = tri[3 * i + 1], oi = tri[3 * i + 2];
+  const int64_t ai = sp ? si : oi;
+  const float* __restrict__ a = ent.base + ai * ent.ld;
+  const float* __restrict__ p = rel.base + pi * rel.ld;
+  const float* __restrict__ g = dQ + b * ldq;
+  float* __restrict__ da = d_ent + ai * lde;
+  float* __restrict__ dp = d_rel + pi * ldr;
+  const int D = ent.dim, h = D >> 1;
+  if constexpr (MODEL == B200KGE_TRANSE) {      // Q = a + p | Q = a - p
+    for (int k = threadIdx.x; k < D; k += blockDim.x) {
+      atomicAdd(da + k, g[k]);
+      atomicAdd(dp + k, sp ? g[k] : -g[k]);
+    }
+  } else {                                        // RotatE, p = phases [h]
+    for (int k = threadIdx.x; k < h; k += blockDim.x) {
+      float sn, c;
+      sincosf(p[k], &sn, &c);
+      const float a_re = a[k], a_im = a[k + h], g_re = g[k], g_im = g[k + h];
+      if (sp) {   // Q_re = a_re c - a_im s ; Q_im = a_re s + a_im c
+        atomicAdd(da + k, g_re * c + g_im * sn);
+        atomicAdd(da + k + h, -g_re * sn + g_im * c);
+        atomicAdd(dp + k, g_re * (-a_re * sn - a_im * c) + g_im * (a_re * c - a_im * sn));
+      } else {    // Q_re = c a_re + s a_im ; Q_im = c a_im - s a_re
+        atomicAdd(da + k, g_re * c - g_im * sn);
+        atomicAdd(da + k + h, g_re * sn + g_im * c);
+        atomicAdd(dp + k, g_re * (-sn * a_re + c * a_im) + g_im * (-sn * a_im - c * a_re));
+      }
+    }
+  }
+}
+
 }  // namespace
+
+int launch_ns_backward(int model, float l_norm, const Rows& ent, const Rows& rel, const int64_t* triples, int slot,
+                       const int64_t* neg, int64_t n, int64_t K, float offset, float inv_batch, float* d_ent,
+                       int64_t lde, float* d_rel, int64_t ldr, float* dQ, int64_t ldq, cudaStream_t st) {
+  if (n == 0) return 0;
+  if (slot != 0 && slot != 2) { set_error("the fused negative-sampling backward covers the S and O slots"); return B200KGE_ERR_UNSUPPORTED; }
+  const int sp = (slot == 2) ? 1 : 0;      // O slot: fold (s,p), candidates are objects
+  Folded f = folded_problem(model, sp ? B200KGE_SP_ : B200KGE__PO, ent.dim, l_norm);
+  if (f.pair_op == PAIR_LP || f.pair_op == PAIR_CMOD_LP) { set_error("the negative-sampling backward covers l_norm 1 and 2 (TransE) / 1 (RotatE)"); return B200KGE_ERR_UNSUPPORTED; }
+  if (f.K > NSB_MAXK) { set_error("embedding width %d exceeds the backward kernel's limit of %d", f.K, NSB_MAXK); return B200KGE_ERR_UNSUPPORTED; }
+  if (ldq < f.K) { set_error("dQ is narrower than the folded width"); return B200KGE_ERR_INVALID; }
+  cudaError_t e = cudaMemsetAsync(dQ, 0, (size_t)n * ldq * 4, st);
+  if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(dQ)");
+  size_t smem = (size_t)2 * f.K * sizeof(float) + (model == B200KGE_RESCAL ? (size_t)ent.dim * sizeof(float) : 0);
+  const int64_t by = (K + 1 + NSB_PER_BLOCK - 1) / NSB_PER_BLOCK;
+  if (by > 65535) { set_error("too many negatives per row (%lld)", (long long)K); return B200KGE_ERR_UNSUPPORTED; }
+  dim3 grid((unsigned)n, (unsigned)by), block(NSB_WARPS * 32);
+#define B2K_NSB(M) case M: ns_backward_kernel<M><<<grid, block, smem, st>>>(ent, rel, triples, sp, neg, K, f, l_norm, offset, inv_batch, d_ent, lde, dQ, ldq); break;
+  switch (model) {
+    B2K_NSB(B200KGE_COMPLEX) B2K_NSB(B200KGE_DISTMULT) B2K_NSB(B200KGE_SIMPLE) B2K_NSB(B200KGE_CP)
+    B2K_NSB(B200KGE_RESCAL) B2K_NSB(B200KGE_TRANSE) B2K_NSB(B200KGE_ROTATE)
+    default: set_error("unknown model %d", model); return B200KGE_ERR_INVALID;
+  }
+#undef B2K_NSB
+  B2K_LAUNCH_CHECK("ns_backward_kernel");
+  const int dir = sp ? 0 : 1;
+  if (model == B200KGE_TRANSE || model == B200KGE_ROTATE) {
+    dim3 g2((unsigned)n), b2(128);
+    if (model == B200KGE_TRANSE)
+      unfold_distance_kernel<B200KGE_TRANSE><<<g2, b2, 0, st>>>(ent, rel, triples, n, dir, dQ, ldq, d_ent, lde, d_rel, ldr);
+    else
+      unfold_distance_kernel<B200KGE_ROTATE><<<g2, b2, 0, st>>>(ent, rel, triples, n, dir, dQ, ldq, d_ent, lde, d_rel, ldr);
+    B2K_LAUNCH_CHECK("unfold_distance_kernel");
+    return 0;
+  }
+  return launch_unfold(model, ent, rel, triples, n, dir, dQ, ldq, d_ent, lde, d_rel, ldr, st);
+}
 
 int launch_penalty(const Rows& tab, const float* counts, float p, int complex_abs, float scale, float* scratch,
                    size_t scratch_floats, float* out, cudaStream_t st) {

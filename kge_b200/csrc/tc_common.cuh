@@ -410,6 +410,9 @@ int launch_grad_planes(const float* z, int64_t ldz, int64_t nq, int64_t E, const
                        const float* label_dense, int64_t ldl, float* row_stat, float offset, float inv_n, void* g_hi, void* g_lo,
                        int64_t Ep, void* gt_hi, void* gt_lo, int64_t Np, float* g_scale, float* gt_scale,
                        cudaStream_t st);
+int launch_ns_backward(int model, float l_norm, const Rows& ent, const Rows& rel, const int64_t* triples, int slot,
+                       const int64_t* neg, int64_t n, int64_t K, float offset, float inv_batch, float* d_ent,
+                       int64_t lde, float* d_rel, int64_t ldr, float* dQ, int64_t ldq, cudaStream_t st);
 int launch_penalty(const Rows& tab, const float* counts, float p, int complex_abs, float scale, float* scratch,
                    size_t scratch_floats, float* out, cudaStream_t st);
 int launch_normalize_rows(float* w, int64_t ld, int64_t rows, int dim, float p, cudaStream_t st);

@@ -389,3 +389,24 @@ def x_normalize_rows_(weight: torch.Tensor, p: float) -> torch.Tensor:
     _lib.check(_lib.load().b200kge_x_normalize_rows(w.data_ptr(), w.stride(0), w.shape[0], w.shape[1], p,
                                                     _stream(w.device)))
     return weight
+
+
+def x_ns_backward(model: str, ent, rel, triples, negatives: dict, offset: float = 0.0, l_norm: float = 1.0,
+                  batch_size: Optional[int] = None):
+    """(d_ent, d_rel) of one negative-sampling batch with BCE; negatives = {slot: [n, K] ids}, slots 0 (S), 2 (O)."""
+    _require_cuda(ent, rel, triples)
+    lib, k = _lib.load(), _Keep()
+    re_, rr = k.rows(ent), k.rows(rel)
+    tri = triples if (triples.dtype == torch.int64 and triples.is_contiguous()) else triples.long().contiguous()
+    n = tri.shape[0]
+    dev = ent.device
+    d_ent = torch.zeros_like(_f32(ent))
+    d_rel = torch.zeros_like(_f32(rel))
+    ws = torch.empty(n * (ent.shape[1] + 32) * 4 + 1024, dtype=torch.uint8, device=dev)
+    for slot, neg in negatives.items():
+        ng = neg if (neg.dtype == torch.int64 and neg.is_contiguous()) else neg.long().contiguous()
+        _lib.check(lib.b200kge_x_ns_backward(
+            MODELS[model], l_norm, C.byref(re_), C.byref(rr), tri.data_ptr(), int(slot), ng.data_ptr(), n, ng.shape[1],
+            offset, batch_size or n, d_ent.data_ptr(), d_ent.stride(0), d_rel.data_ptr(), d_rel.stride(0),
+            ws.data_ptr(), ws.numel(), _stream(dev)))
+    return d_ent, d_rel

@@ -13,7 +13,7 @@ echo "evaluator + job-trace pytest rc=$?" >> gpurun_out/exp_summary.txt
 tail -4 gpurun_out/exp_evaluator.log >> gpurun_out/exp_summary.txt
 timeout 180 python -m pytest tests/test_gpu_experimental.py -x -q -k "x_gemm" > gpurun_out/exp_gemm.log 2>&1
 echo "x_gemm pytest rc=$?" >> gpurun_out/exp_summary.txt
-timeout 240 python -m pytest tests/test_gpu_experimental.py -q -k "x_backward" > gpurun_out/exp_backward.log 2>&1
+timeout 240 python -m pytest tests/test_gpu_experimental.py -q -k "x_backward or x_ns_backward" > gpurun_out/exp_backward.log 2>&1
 echo "x_backward pytest rc=$?" >> gpurun_out/exp_summary.txt
 tail -5 gpurun_out/exp_backward.log >> gpurun_out/exp_summary.txt
 for v in tc3 tc4-forward tc4-direct; do

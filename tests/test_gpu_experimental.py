@@ -280,3 +280,22 @@ def test_x_penalties_and_normalisation_golden(eng):
         w = g["normalize_in"].cuda().clone()
         eng.x_normalize_rows_(w, float(pn))
         assert torch.allclose(w.cpu(), g[f"normalize_p{pn}"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("model,D,ln", [("complex", 64, 1.0), ("distmult", 32, 1.0), ("simple", 64, 1.0), ("cp", 64, 1.0),
+                                        ("rescal", 16, 1.0), ("transe", 64, 1.0), ("transe", 64, 2.0), ("rotate", 64, 1.0)])
+def test_x_ns_backward(eng, model, D, ln):
+    """Fused negative-sampling backward (S and O slots, positive column included) against the CPU algebra
+    (oracle/kge_fold.ns_backward, itself pinned to the reference job's gradients)."""
+    from oracle import kge_fold as kf
+
+    E, R, n, K = 501, 5, 37, 150
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.5)
+    tri = orc.make_triples(E, R, n)
+    g = torch.Generator().manual_seed(3)
+    negs = {S: torch.randint(0, E, (n, K), generator=g), O: torch.randint(0, E, (n, K + 7), generator=g)}
+    ref_e, ref_r = kf.ns_backward(model, ent.double(), rel.double(), tri, negs, 0.25, ln)
+    d_ent, d_rel = eng.x_ns_backward(model, ent.cuda(), rel.cuda(), tri.cuda(), {k: v.cuda() for k, v in negs.items()},
+                                     0.25, ln)
+    _assert_close(d_ent, ref_e, f"{model} d_ent")
+    _assert_close(d_rel, ref_r, f"{model} d_rel")
