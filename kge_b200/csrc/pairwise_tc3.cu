@@ -115,7 +115,7 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int s = 2 * (int)(c & 1) + h;
-              ptx::mbar_wait(&free_[s], par);
+              ptx::mbar_wait_bounded(&free_[s], par);
               uint8_t* sp = smem + s * SLOT_BYTES;
               ptx::mbar_arrive_expect_tx(&full[s], tx);
               ptx::tma_load_2d(sp, h ? &tmQl : &tmQh, &full[s], kc * TKH, qt * TM);
@@ -135,7 +135,7 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
         work_range(w, qt, et0, et1, ec);
         for (int et = et0; et < et1; ++et, ++it) {
           const int b = it & 1;
-          ptx::mbar_wait(&tempty[b], ((it >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+          ptx::mbar_wait_bounded(&tempty[b], ((it >> 1) & 1) ^ 1);   // epilogue drained this accumulator
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(b * TN);
           for (int kc = 0; kc < nk; ++kc, ++c) {
@@ -143,13 +143,13 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
             const uint32_t par = (c >> 1) & 1;
             const uint32_t a_hi = ptx::smem_u32(smem + sh * SLOT_BYTES), b_hi = a_hi + A_BYTES;
             const uint32_t a_lo = ptx::smem_u32(smem + sl * SLOT_BYTES), b_lo = a_lo + A_BYTES;
-            ptx::mbar_wait(&full[sh], par);
+            ptx::mbar_wait_bounded(&full[sh], par);
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TKH / 16; ++k)
               ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
                              (kc > 0 || k > 0) ? 1u : 0u);
-            ptx::mbar_wait(&full[sl], par);
+            ptx::mbar_wait_bounded(&full[sl], par);
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TKH / 16; ++k) {
@@ -181,7 +181,7 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
       const float qs = row_ok ? __ldg(prm.q_scale + row) : 0.f;
       for (int et = et0; et < et1; ++et, ++it) {
         const int b = it & 1;
-        ptx::mbar_wait(&tfull[b], (it >> 1) & 1);
+        ptx::mbar_wait_bounded(&tfull[b], (it >> 1) & 1);
         ptx::tc_fence_after();
         const int64_t tile_end = (int64_t)(et + 1) * prm.tn;
         tc::epilogue_tile<EPI, 4, true>(P, st, aux,

@@ -125,7 +125,7 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int s = s0 + h;
-              ptx::mbar_wait_cluster(&empty[s], ph ^ 1);
+              ptx::mbar_wait_cluster_bounded(&empty[s], ph ^ 1);
               uint8_t* sp = smem + s * SLOT_BYTES;
               if (DIRECT) {
                 // completion of BOTH CTAs' boxes is counted on the leader's barrier
@@ -154,7 +154,7 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
         work_range(w, qt, et0, et1, ec);
         for (int et = et0; et < et1; ++et, ++it) {
           const int b = it & 1;
-          ptx::mbar_wait_cluster(&tempty[b], ((it >> 1) & 1) ^ 1);
+          ptx::mbar_wait_cluster_bounded(&tempty[b], ((it >> 1) & 1) ^ 1);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(b * TN);
           for (int kc = 0; kc < nk; ++kc, ++c) {
@@ -162,13 +162,13 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
             const uint32_t ph = phase_of(c);
             const uint32_t a_hi = ptx::smem_u32(smem + sh * SLOT_BYTES), b_hi = a_hi + A_BYTES;
             const uint32_t a_lo = ptx::smem_u32(smem + sl * SLOT_BYTES), b_lo = a_lo + A_BYTES;
-            ptx::mbar_wait_cluster(&ready[sh], ph);
+            ptx::mbar_wait_cluster_bounded(&ready[sh], ph);
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TKH / 16; ++k)
               ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
                                   (kc > 0 || k > 0) ? 1u : 0u);
-            ptx::mbar_wait_cluster(&ready[sl], ph);
+            ptx::mbar_wait_cluster_bounded(&ready[sl], ph);
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TKH / 16; ++k) {
@@ -195,7 +195,7 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
             const uint32_t ph = phase_of(c);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              ptx::mbar_wait(&full[s0 + h], ph);
+              ptx::mbar_wait_bounded(&full[s0 + h], ph);
               ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&landed[s0 + h]), 0));
             }
           }
@@ -221,7 +221,7 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
       const float qs = row_ok ? __ldg(prm.q_scale + row) : 0.f;
       for (int et = et0; et < et1; ++et, ++it) {
         const int b = it & 1;
-        ptx::mbar_wait_cluster(&tfull[b], (it >> 1) & 1);
+        ptx::mbar_wait_cluster_bounded(&tfull[b], (it >> 1) & 1);
         ptx::tc_fence_after();
         tc::epilogue_tile<EPI, 4, true>(P, st, aux,
                                         tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TN + half * 128),
