@@ -266,6 +266,20 @@ int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const 
                                     float* d_ent, int64_t lde, float* d_rel, int64_t ldr,
                                     void* workspace, size_t workspace_bytes, b200kge_stream_t stream);
 
+/* KvsAll loss with CSR multi-hot labels (kge/job/train_KvsAll.py:242-300 without the densified label matrix):
+ * row i's labels are the columns csr_col[csr_off[i] .. csr_off[i+1]) (sorted; a repeated column counts as often
+ * as it appears, like duplicate triples in the reference), optionally smoothed: y = (1 - eps) * count + 1/m.
+ * *loss_out = sum_i loss(score row i, y_i) (BCE with offset | KL), row_loss_out (optional) the per-row terms.
+ * Composition of the fused scorer (label-free pass) with row kernels over the nnz listed columns; cand must be a
+ * plain table; eps > 0 needs a dot-family model.  Sizes: b200kge_x_score_1vsN_loss_csr_workspace_bytes. */
+size_t b200kge_x_score_1vsN_loss_csr_workspace_bytes(int model, int64_t n, int64_t m, int32_t D, int64_t nnz);
+int b200kge_x_score_1vsN_loss_csr(int model, int combine, float l_norm, int precision,
+                                  const b200kge_rows_t* q, const b200kge_rows_t* p,
+                                  const b200kge_rows_t* cand, int64_t n, const int64_t* csr_off,
+                                  const int64_t* csr_col, int64_t nnz, float label_smoothing, int loss_kind,
+                                  float offset, float* loss_out, float* row_loss_out, void* workspace,
+                                  size_t workspace_bytes, b200kge_stream_t stream);
+
 /* Backward of one slot of a negative-sampling batch with BCE (kge/job/train_negative_sampling.py:113-164): the
  * [n, 1+K] block of the slot (column 0 = the positive triple, label 1; columns 1.. = the sampled ids neg [n,K],
  * label 0), loss summed and divided by batch_size.  ADDS into d_ent [E, lde] and d_rel [R, ldr] (zero them before

@@ -746,4 +746,86 @@ int b200kge_x_ns_backward(int model, float l_norm, const b200kge_rows_t* ent, co
                             d_rel, ldr, dQ, ldq, (cudaStream_t)stream);
 }
 
+
+size_t b200kge_x_score_1vsN_loss_csr_workspace_bytes(int model, int64_t n, int64_t m, int32_t D, int64_t nnz) {
+  const int64_t ldq = round_up(D, 32), tot = nnz + n;
+  size_t b = b200kge_workspace_bytes(model, n, m, D, 0);
+  b += (size_t)n * 8 + 3 * ((size_t)tot * 8 + 256) + (size_t)tot * 4 + 4 * ((size_t)n * 4 + 256) + 2048;
+  b += (size_t)n * ldq * 4 + ((size_t)((m + 1023) / 1024) + 1) * ldq * 4 + 512;
+  return b;
+}
+
+int b200kge_x_score_1vsN_loss_csr(int model, int combine, float l_norm, int precision, const b200kge_rows_t* q,
+                                  const b200kge_rows_t* p, const b200kge_rows_t* cand, int64_t n,
+                                  const int64_t* csr_off, const int64_t* csr_col, int64_t nnz, float label_smoothing,
+                                  int loss_kind, float offset, float* loss_out, float* row_loss_out, void* workspace,
+                                  size_t workspace_bytes, b200kge_stream_t stream) {
+  int rc = check_1vsN_args(model, combine, q, p, cand, n); if (rc) return rc;
+  if ((rc = validate_norm(model, l_norm))) return rc;
+  if (!csr_off || (!csr_col && nnz > 0) || !loss_out || nnz < 0) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  if (cand->idx) { set_error("CSR labels address the columns of a plain candidate table (cand.idx must be NULL)"); return B200KGE_ERR_INVALID; }
+  if (loss_kind != B200KGE_LOSS_BCE && loss_kind != B200KGE_LOSS_KL) { set_error("unknown loss kind %d", loss_kind); return B200KGE_ERR_INVALID; }
+  if (!(label_smoothing >= 0.f && label_smoothing < 1.f)) { set_error("label_smoothing must be in [0, 1)"); return B200KGE_ERR_INVALID; }
+  const bool dot = model <= B200KGE_RESCAL;
+  if (label_smoothing > 0.f && !dot) { set_error("label smoothing with CSR labels is available for the dot family"); return B200KGE_ERR_UNSUPPORTED; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0 || cand->rows == 0) { B2K_CUDA(cudaMemsetAsync(loss_out, 0, 4, st)); return 0; }
+  Rows Q = to_rows(q), Pr = to_rows(p), C = to_rows(cand);
+  const int64_t m = C.rows, tot = nnz + (loss_kind == B200KGE_LOSS_KL ? n : 0);
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  int64_t* lab = (int64_t*)ws.take((size_t)n * 8);
+  int64_t* qsel = (int64_t*)ws.take((size_t)tot * 8 + 8);
+  int64_t* psel = (int64_t*)ws.take((size_t)tot * 8 + 8);
+  int64_t* esel = (int64_t*)ws.take((size_t)tot * 8 + 8);
+  float* zpos = (float*)ws.take((size_t)tot * 4 + 8);
+  float* fused = (float*)ws.take((size_t)n * 4);
+  float* rows = row_loss_out ? row_loss_out : (float*)ws.take((size_t)n * 4);
+  float* total = (float*)ws.take(256);
+  void* scratch = ws.take(1024);
+  if (!lab || !qsel || !psel || !esel || !zpos || !fused || !rows || !total || !scratch) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+  // 1. label-free fused pass: BCE with no label (index -1) -> sum_j softplus;  KL with the one-hot label at
+  //    column 0 -> lse_i - z_i0
+  B2K_CUDA(cudaMemsetAsync(lab, loss_kind == B200KGE_LOSS_BCE ? 0xFF : 0, (size_t)n * 8, st));
+  {
+    EpiParams P = empty_epi();
+    P.label_idx = lab;
+    P.offset = (loss_kind == B200KGE_LOSS_BCE) ? offset : 0.f;
+    Block B{model, combine, &Q, nullptr, &Pr, &C, n};
+    int nch = 0;
+    float* part = nullptr;
+    Arena w2 = ws;
+    const int epi = (loss_kind == B200KGE_LOSS_BCE) ? EPI_BCE : EPI_KL;
+    if ((rc = run_block(B, l_norm, precision, epi, P, w2, st, &nch, &part))) return rc;
+    if ((rc = launch_loss_finalize(loss_kind, part, nch, n, total, fused, 1.0f, 0, scratch, 0, st))) return rc;
+  }
+  // 2. scores of the listed columns (and of column 0 for KL) through the row-wise triple kernel
+  if ((rc = launch_csr_expand(csr_off, csr_col, n, nnz, loss_kind == B200KGE_LOSS_KL ? 1 : 0, Q.idx, Pr.idx, qsel, psel,
+                              esel, st))) return rc;
+  if (tot > 0) {
+    Rows Qs = Q; Qs.idx = qsel; Qs.rows = tot;
+    Rows Ps = Pr; Ps.idx = psel; Ps.rows = tot;
+    Rows Es = C; Es.idx = esel; Es.rows = tot;
+    if (combine == B200KGE_SP_) rc = launch_spo(model, l_norm, Qs, Ps, Es, tot, zpos, 1, st);
+    else                        rc = launch_spo(model, l_norm, Es, Ps, Qs, tot, zpos, 1, st);
+    if (rc) return rc;
+  }
+  // 3. label smoothing: sum_j z_ij = Q_i . colsum(T)   (dot family)
+  float* zsum = nullptr;
+  if (label_smoothing > 0.f) {
+    Folded f = folded_problem(model, combine, Q.dim, l_norm);
+    const int64_t ldq = round_up(f.K, 32);
+    float* Qf = (float*)ws.take((size_t)n * ldq * 4);
+    float* cs = (float*)ws.take(((size_t)((m + 1023) / 1024) + 1) * ldq * 4);
+    zsum = (float*)ws.take((size_t)n * 4);
+    if (!Qf || !cs || !zsum) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+    if ((rc = launch_fold_queries(model, combine, Q, Pr, n, 0, Qf, ldq, st))) return rc;
+    if ((rc = launch_row_score_sums(Qf, ldq, n, C.base + f.col_off, C.ld, m, f.K, cs, zsum, st))) return rc;
+  }
+  // 4. per-row combination and the scalar
+  const float a = 1.0f - label_smoothing, b = label_smoothing > 0.f ? 1.0f / (float)m : 0.f;
+  if ((rc = launch_csr_rows(loss_kind, csr_off, csr_col, zpos, n, nnz, fused, zsum, a, b, (float)m,
+                            loss_kind == B200KGE_LOSS_BCE ? offset : 0.f, rows, st))) return rc;
+  return launch_rows_sum(rows, n, 1.0f, loss_out, st);
+}
+
 }  // extern "C"

@@ -410,6 +410,15 @@ int launch_grad_planes(const float* z, int64_t ldz, int64_t nq, int64_t E, const
                        const float* label_dense, int64_t ldl, float* row_stat, float offset, float inv_n, void* g_hi, void* g_lo,
                        int64_t Ep, void* gt_hi, void* gt_lo, int64_t Np, float* g_scale, float* gt_scale,
                        cudaStream_t st);
+// CSR-label losses (csr_loss.cu), experimental.
+int launch_csr_expand(const int64_t* off, const int64_t* col, int64_t n, int64_t nnz, int extra, const int64_t* q_idx,
+                      const int64_t* p_idx, int64_t* qsel, int64_t* psel, int64_t* esel, cudaStream_t st);
+int launch_csr_rows(int loss_kind, const int64_t* off, const int64_t* col, const float* zpos, int64_t n, int64_t nnz,
+                    const float* fused, const float* zsum, float a, float b, float E, float offset, float* row_loss,
+                    cudaStream_t st);
+int launch_rows_sum(const float* rows, int64_t n, float scale, float* out, cudaStream_t st);
+int launch_row_score_sums(const float* Q, int64_t ldq, int64_t n, const float* T, int64_t ldt, int64_t E, int K,
+                          float* scratch, float* zsum, cudaStream_t st);
 int launch_ns_backward(int model, float l_norm, const Rows& ent, const Rows& rel, const int64_t* triples, int slot,
                        const int64_t* neg, int64_t n, int64_t K, float offset, float inv_batch, float* d_ent,
                        int64_t lde, float* d_rel, int64_t ldr, float* dQ, int64_t ldq, cudaStream_t st);

@@ -410,3 +410,25 @@ def x_ns_backward(model: str, ent, rel, triples, negatives: dict, offset: float 
             offset, batch_size or n, d_ent.data_ptr(), d_ent.stride(0), d_rel.data_ptr(), d_rel.stride(0),
             ws.data_ptr(), ws.numel(), _stream(dev)))
     return d_ent, d_rel
+
+
+def x_score_1vsN_loss_csr(model: str, combine: str, q_tab, rel, cand_tab, csr_offsets, csr_cols, q=None, p=None,
+                          loss: str = "kl", offset: float = 0.0, label_smoothing: float = 0.0, l_norm: float = 1.0,
+                          precision: str = "auto", return_rows: bool = False):
+    """KvsAll loss (sum over rows) with CSR multi-hot labels — see b200kge_x_score_1vsN_loss_csr."""
+    _require_cuda(q_tab, rel, cand_tab, csr_offsets, csr_cols)
+    lib, k = _lib.load(), _Keep()
+    rq, rp, rc = k.rows(q_tab, q), k.rows(rel, p), k.rows(cand_tab)
+    n, m = int(rq.rows), int(rc.rows)
+    dev = q_tab.device
+    offs, cols = _i64(csr_offsets), _i64(csr_cols)
+    nnz = int(cols.numel())
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    rows = torch.empty(n, dtype=torch.float32, device=dev) if return_rows else None
+    nbytes = lib.b200kge_x_score_1vsN_loss_csr_workspace_bytes(MODELS[model], n, m, rq.dim, nnz)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.b200kge_x_score_1vsN_loss_csr(
+        MODELS[model], SP_ if combine == "sp_" else _PO, l_norm, PREC[precision], C.byref(rq), C.byref(rp), C.byref(rc),
+        n, offs.data_ptr(), cols.data_ptr() if nnz else None, nnz, label_smoothing, LOSS[loss], offset, out.data_ptr(),
+        rows.data_ptr() if rows is not None else None, ws.data_ptr(), ws.numel(), _stream(dev)))
+    return (out, rows) if return_rows else out

@@ -8,7 +8,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 : > gpurun_out/exp_summary.txt
 export B200KGE_EXPERIMENTAL=1
-timeout 180 python -m pytest tests/test_gpu_experimental.py -q -k "evaluator or job or reciprocal or penalties" > gpurun_out/exp_evaluator.log 2>&1
+timeout 180 python -m pytest tests/test_gpu_experimental.py -q -k "evaluator or job or reciprocal or penalties or csr" > gpurun_out/exp_evaluator.log 2>&1
 echo "evaluator + job-trace pytest rc=$?" >> gpurun_out/exp_summary.txt
 tail -4 gpurun_out/exp_evaluator.log >> gpurun_out/exp_summary.txt
 timeout 180 python -m pytest tests/test_gpu_experimental.py -x -q -k "x_gemm" > gpurun_out/exp_gemm.log 2>&1

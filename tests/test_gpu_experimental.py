@@ -299,3 +299,37 @@ def test_x_ns_backward(eng, model, D, ln):
                                      0.25, ln)
     _assert_close(d_ent, ref_e, f"{model} d_ent")
     _assert_close(d_rel, ref_r, f"{model} d_rel")
+
+
+@pytest.mark.parametrize("model,D", [("complex", 128), ("distmult", 32), ("rescal", 24), ("cp", 64), ("transe", 64), ("rotate", 64)])
+@pytest.mark.parametrize("loss", ["bce", "kl"])
+def test_x_loss_with_csr_labels(eng, model, D, loss):
+    """KvsAll losses with CSR multi-hot labels (duplicates, empty rows, label smoothing) against the oracle on the
+    densified label matrix; both directions."""
+    E, R, n = 3001, 5, 200
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.3)
+    tri = orc.make_triples(E, R, n)
+    g = torch.Generator().manual_seed(3)
+    counts = (torch.rand((n, E), generator=g) < 0.004).float()
+    counts[torch.arange(n), tri[:, O]] += 1.0
+    counts[5, int(tri[5, O])] += 1.0          # a duplicate triple: label 2
+    counts[7] = 0.0                            # a row without labels
+    rows, cols = torch.nonzero(counts, as_tuple=True)
+    rep = counts[rows, cols].long()
+    cols_rep = torch.repeat_interleave(cols, rep)
+    rows_rep = torch.repeat_interleave(rows, rep)
+    offs = torch.zeros(n + 1, dtype=torch.int64)
+    offs[1:] = torch.cumsum(torch.bincount(rows_rep, minlength=n), 0)
+    ce, cr = ent.cuda(), rel.cuda()
+    off = 1.0 if loss == "bce" else 0.0
+    fn = (lambda x, y: orc.bce_loss(x, y, off)) if loss == "bce" else orc.kl_loss
+    dot = model in ("complex", "distmult", "rescal", "cp")
+    for combine, qi, sc in (("sp_", tri[:, S], orc.score_sp(model, ent, rel, tri[:, S], tri[:, P])),
+                            ("_po", tri[:, O], orc.score_po(model, ent, rel, tri[:, P], tri[:, O]))):
+        for eps in ((0.0, 0.1) if dot else (0.0,)):
+            lab = orc.kvsall_smooth_labels(counts, eps) if eps > 0 else counts
+            ref = float(fn(sc, lab))
+            got, rws = eng.x_score_1vsN_loss_csr(model, combine, ce, cr, ce, offs.cuda(), cols_rep.cuda(), qi.cuda(),
+                                                 tri[:, P].cuda(), loss, off, eps, return_rows=True)
+            assert abs(float(got) - ref) <= 1e-4 * abs(ref), (model, loss, combine, eps, float(got), ref)
+            assert abs(float(rws.sum()) - ref) <= 1e-4 * abs(ref)

@@ -144,3 +144,42 @@ def test_reciprocal_model_index_arithmetic(monkeypatch):
         m.score_spo(s, p, o)
     with pytest.raises(Exception, match="cannot score relations"):
         m.score_so(s, o)
+
+
+def test_csr_loss_decomposition_matches_dense_losses():
+    """The algebra of kge_b200/csrc/csr_loss.cu: with labels y = a*count + b the KvsAll losses split into a
+    label-free per-row term (what the fused scorer produces) and sums over the listed columns only.  Emulated in
+    torch and compared with the oracle's losses on the densified label matrix (duplicates, empty rows, smoothing)."""
+    import math
+    import torch
+    from oracle import kge_oracle as orc
+
+    g = torch.Generator().manual_seed(2)
+    n, E = 9, 41
+    z = torch.randn((n, E), generator=g, dtype=torch.float64) * 2
+    counts = (torch.rand((n, E), generator=g) < 0.1).double()
+    counts[2, 5] = 3.0
+    counts[4] = 0.0
+    for eps in (0.0, 0.2):
+        a, b = 1.0 - eps, (1.0 / E if eps > 0 else 0.0)
+        y = a * counts + b
+        off = 0.7
+        # BCE
+        A = torch.nn.functional.softplus(z + off).sum(1)
+        B = (counts * (z + off)).sum(1)
+        Cs = (z + off).sum(1)
+        got = float((A - a * B - b * Cs).sum())
+        assert abs(got - float(orc.bce_loss(z, y, off))) <= 1e-9 * abs(got)
+        # KL
+        lse = torch.logsumexp(z, 1)
+        Bz, Zs, nnz = (counts * z).sum(1), z.sum(1), counts.sum(1)
+        Y = a * nnz + b * E
+        total = 0.0
+        for i in range(n):
+            if float(Y[i]) <= 0:
+                continue
+            listed = counts[i][counts[i] > 0]
+            ylogy = float(((a * listed + b) * torch.log(a * listed + b)).sum())
+            rest = (E - listed.numel()) * b * math.log(b) if b > 0 else 0.0
+            total += (ylogy + rest) / float(Y[i]) - math.log(float(Y[i])) - (a * float(Bz[i]) + b * float(Zs[i])) / float(Y[i]) + float(lse[i])
+        assert abs(total - float(orc.kl_loss(z, y))) <= 1e-9 * abs(total)
