@@ -89,3 +89,36 @@ def test_edge_cases():
     assert len(ix) == len(d)
     for k, v in list(d.items())[:200]:
         assert ix[k].tolist() == sorted(v)
+
+
+def test_index_properties_randomised():
+    """Property test of the native index against a plain dictionary over random small graphs (many duplicate keys
+    and duplicate triples), all three key layouts, lookups of present and absent keys."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.tuples(st.integers(0, 5), st.integers(0, 2), st.integers(0, 5)), min_size=0, max_size=40),
+           st.sampled_from(["sp", "po", "so"]),
+           st.lists(st.tuples(st.integers(0, 7), st.integers(0, 7)), min_size=0, max_size=10))
+    def check(triples, key, queries):
+        cols, val = KEYS[key]
+        tri = torch.tensor(triples, dtype=torch.int64).view(-1, 3)
+        ix = indexing.index_KvsAll(tri, key)
+        d = {}
+        for t in triples:
+            d.setdefault((t[cols[0]], t[cols[1]]), []).append(t[val])
+        assert len(ix) == len(d)
+        assert [tuple(k) for k in ix._keys.tolist()] == sorted(d)
+        assert ix._values.tolist() == [v for k in sorted(d) for v in sorted(d[k])]
+        assert ix._values_offset.tolist()[-1] == len(triples)
+        q = torch.tensor(queries, dtype=torch.int64).view(-1, 2)
+        offs, vals = ix.get_all_csr(q)
+        for i, k in enumerate(queries):
+            assert vals[int(offs[i]): int(offs[i + 1])].tolist() == sorted(d.get(tuple(k), []))
+        if len(ix):
+            ex = torch.arange(len(ix) - 1, -1, -1)
+            qs, o2, c2 = ix.collate_csr(ex)
+            assert [tuple(k) for k in qs.tolist()] == sorted(d)[::-1]
+            assert int(o2[-1]) == len(triples)
+
+    check()
