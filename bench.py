@@ -162,8 +162,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
 
-    from kge_b200 import engine
-    from oracle import kge_oracle as orc
+    from kge_b200 import engine, synthetic          # the device arm never touches oracle/
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -179,11 +178,11 @@ def run_ours(args):
     if not engine.device_ok():
         raise RuntimeError("bench.py needs an sm_100 (B200) device; kge_b200 has no fallback path")
 
-    ent_c, rel_c = orc.make_tables(MODEL, E, R, D, sigma=1.0)
+    ent_c, rel_c = synthetic.make_tables(MODEL, E, R, D, sigma=1.0)
     ent, rel = ent_c.to(dev), rel_c.to(dev)
     K, W = args.steps, max(args.warmup, 3)
     # every rank scores its own batches (weak scaling: per-GPU work fixed, no data-path collective)
-    batches_host = [orc.make_triples(E, R, N_BATCH, seed=1000 * rank + i).contiguous().pin_memory()
+    batches_host = [synthetic.make_triples(E, R, N_BATCH, seed=1000 * rank + i).contiguous().pin_memory()
                     for i in range(4)]
     batches_dev = [b.to(dev) for b in batches_host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -14,7 +14,8 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 from kge_b200 import engine  # noqa: E402
-from oracle import kge_oracle as orc  # noqa: E402
+from kge_b200 import synthetic  # noqa: E402
+from oracle import kge_oracle as orc  # noqa: E402  (the parity cases use it as the checker)
 
 dev = torch.device("cuda", 0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -40,8 +41,8 @@ def timeit(fn, iters=10, warm=3):
 
 
 def case_1vsall(model, E, R, D, n, prec, epi, l_norm=1.0):
-    ent, rel = orc.make_tables(model, E, R, D)
-    tri = orc.make_triples(E, R, n).to(dev)
+    ent, rel = synthetic.make_tables(model, E, R, D)
+    tri = synthetic.make_triples(E, R, n).to(dev)
     ent, rel = ent.to(dev), rel.to(dev)
     s, p, o = tri[:, 0].contiguous(), tri[:, 1].contiguous(), tri[:, 2].contiguous()
     if epi == "store":
@@ -64,8 +65,8 @@ def case_1vsall(model, E, R, D, n, prec, epi, l_norm=1.0):
 
 def case_kvsall(model, E, R, D, n, loss):
     """Fused score_sp + loss with DENSE multi-hot labels (KvsAll, train_KvsAll.py:242-289)."""
-    ent, rel = orc.make_tables(model, E, R, D, sigma=0.3)
-    tri = orc.make_triples(E, R, n).to(dev)
+    ent, rel = synthetic.make_tables(model, E, R, D, sigma=0.3)
+    tri = synthetic.make_triples(E, R, n).to(dev)
     ent, rel = ent.to(dev), rel.to(dev)
     lab = (torch.rand((n, E), device=dev) < 2e-4).float()
     s, p = tri[:, 0].contiguous(), tri[:, 1].contiguous()
@@ -77,8 +78,8 @@ def case_kvsall(model, E, R, D, n, loss):
 
 
 def case_ns(model, E, R, D, n, K):
-    ent, rel = orc.make_tables(model, E, R, D)
-    tri = orc.make_triples(E, R, n).to(dev)
+    ent, rel = synthetic.make_tables(model, E, R, D)
+    tri = synthetic.make_triples(E, R, n).to(dev)
     ent, rel = ent.to(dev), rel.to(dev)
     neg = torch.randint(0, E, (n, K), device=dev)
     fn = lambda: engine.ns_score(model, ent, rel, tri, neg, 2, True)
@@ -101,8 +102,8 @@ def case_ns(model, E, R, D, n, K):
 def case_parity():
     """max|d|/rms of the TC path vs the fp32 SIMT path and vs the fp64 oracle (n=256 sample)."""
     model, E, R, D, n = "complex", 14541, 237, 512, 256
-    ent, rel = orc.make_tables(model, E, R, D)
-    tri = orc.make_triples(E, R, n)
+    ent, rel = synthetic.make_tables(model, E, R, D)
+    tri = synthetic.make_triples(E, R, n)
     ref = orc.score_sp(model, ent.double(), rel.double(), tri[:, 0], tri[:, 1])
     rms = float(ref.pow(2).mean().sqrt())
     e, r, t = ent.to(dev), rel.to(dev), tri.to(dev)

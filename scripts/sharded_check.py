@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from kge_b200.sharded import ShardedKgeModel  # noqa: E402
-from oracle import kge_oracle as orc  # noqa: E402
+from kge_b200 import synthetic as orc  # noqa: E402  (seeded synthetic inputs only)
 
 
 def main():

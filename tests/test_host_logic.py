@@ -183,3 +183,18 @@ def test_csr_loss_decomposition_matches_dense_losses():
             rest = (E - listed.numel()) * b * math.log(b) if b > 0 else 0.0
             total += (ylogy + rest) / float(Y[i]) - math.log(float(Y[i])) - (a * float(Bz[i]) + b * float(Zs[i])) / float(Y[i]) + float(lse[i])
         assert abs(total - float(orc.kl_loss(z, y))) <= 1e-9 * abs(total)
+
+
+def test_synthetic_inputs_match_the_checkers_copy():
+    """kge_b200.synthetic (used by bench.py's device arm and the scripts, which must not import oracle/) and the
+    oracle's own generators produce identical tensors."""
+    import torch
+    from kge_b200 import synthetic
+    from oracle import kge_oracle as orc
+
+    for model in orc.MODELS:
+        D = 8 if model == "rescal" else 16
+        a, b = synthetic.make_tables(model, 23, 4, D, sigma=0.3, seed=7), orc.make_tables(model, 23, 4, D, sigma=0.3, seed=7)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        assert synthetic.relation_dim(model, D) == orc.relation_dim(model, D)
+    assert torch.equal(synthetic.make_triples(23, 4, 9, seed=3), orc.make_triples(23, 4, 9, seed=3))
