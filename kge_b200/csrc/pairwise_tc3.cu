@@ -31,17 +31,27 @@ namespace {
 
 constexpr int TM = 128;             // queries per tile  (UMMA M)
 constexpr int TN = 256;             // max entities per tile (UMMA N)
-constexpr int TKH = 64;             // halfs per K chunk (128 B swizzle atom)
-constexpr int NSLOT = 4;
-constexpr int A_BYTES = TM * TKH * 2;   // 16 KB
-constexpr int B_BYTES = TN * TKH * 2;   // 32 KB
-constexpr int SLOT_BYTES = A_BYTES + B_BYTES;
 using tc::EPI_WARPS;
 using tc::STG_LD;
 constexpr int NTHREADS3 = 12 * 32;
 constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + NSLOT * SLOT_BYTES + STG_BYTES + 256 /*barriers*/;
+constexpr int PIPE_BYTES = 192 * 1024;
 constexpr int TMEM_COLS = 512;
+
+// TKH = halfs per K chunk: 64 (128-byte rows, 128-byte swizzle, 4 slots of 48 KB — the default) or 32 (64-byte
+// rows, 64-byte swizzle, 8 slots of 24 KB: same bytes in flight in twice as many, half as large transactions;
+// B200KGE_TC3_TK=32).  Which granularity feeds the MMAs better is a measurement for the next round.
+template <int TKH> struct Cfg3 {
+  static constexpr int A_BYTES = TM * TKH * 2;
+  static constexpr int B_BYTES = TN * TKH * 2;
+  static constexpr int SLOT_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NSLOT = PIPE_BYTES / SLOT_BYTES;      // 4 | 8
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + PIPE_BYTES + STG_BYTES + 256 /*barriers*/;
+};
+template <int TKH>
+__device__ __forceinline__ uint64_t make_desc3(uint32_t addr) {
+  return (TKH == 64) ? ptx::umma_desc_sw128(addr) : ptx::umma_desc_sw64(addr);
+}
 
 struct Tc3Params {
   int64_t nq, m;
@@ -53,11 +63,14 @@ struct Tc3Params {
   EpiParams epi;
 };
 
-template <int EPI>
+template <int EPI, int TKH>
 __global__ void __launch_bounds__(NTHREADS3, 1)
 pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                     const __grid_constant__ CUtensorMap tmTh, const __grid_constant__ CUtensorMap tmTl,
                     const Tc3Params prm) {
+  using C = Cfg3<TKH>;
+  constexpr int NSLOT = C::NSLOT, A_BYTES = C::A_BYTES, SLOT_BYTES = C::SLOT_BYTES;
+  constexpr int NPAIR = NSLOT / 2;      // K chunks in flight: chunk c owns slots 2*(c % NPAIR), +1 on use c / NPAIR
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* stg = reinterpret_cast<float*>(smem + NSLOT * SLOT_BYTES);
@@ -105,16 +118,16 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
     // ================================ TMA producer =========================================
     if (lane == 0) {
       const uint32_t tx = (uint32_t)(A_BYTES + prm.tn * TKH * 2);
-      uint32_t c = 0;      // K-chunk counter; chunk c owns slots 2*(c&1) and 2*(c&1)+1, use number c>>1
+      uint32_t c = 0;      // K-chunk counter
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         int qt, et0, et1, ec;
         work_range(w, qt, et0, et1, ec);
         for (int et = et0; et < et1; ++et) {
           for (int kc = 0; kc < nk; ++kc, ++c) {
-            const uint32_t par = ((c >> 1) & 1) ^ 1;
+            const uint32_t par = ((c / NPAIR) & 1) ^ 1;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const int s = 2 * (int)(c & 1) + h;
+              const int s = 2 * (int)(c % NPAIR) + h;
               ptx::mbar_wait_bounded(&free_[s], par);
               uint8_t* sp = smem + s * SLOT_BYTES;
               ptx::mbar_arrive_expect_tx(&full[s], tx);
@@ -139,22 +152,22 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(b * TN);
           for (int kc = 0; kc < nk; ++kc, ++c) {
-            const int sh = 2 * (int)(c & 1), sl = sh + 1;
-            const uint32_t par = (c >> 1) & 1;
+            const int sh = 2 * (int)(c % NPAIR), sl = sh + 1;
+            const uint32_t par = (c / NPAIR) & 1;
             const uint32_t a_hi = ptx::smem_u32(smem + sh * SLOT_BYTES), b_hi = a_hi + A_BYTES;
             const uint32_t a_lo = ptx::smem_u32(smem + sl * SLOT_BYTES), b_lo = a_lo + A_BYTES;
             ptx::mbar_wait_bounded(&full[sh], par);
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TKH / 16; ++k)
-              ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
+              ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc,
                              (kc > 0 || k > 0) ? 1u : 0u);
             ptx::mbar_wait_bounded(&full[sl], par);
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TKH / 16; ++k) {
-              ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_lo + k * 32), idesc, 1u);
-              ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(a_lo + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+              ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_lo + k * 32), idesc, 1u);
+              ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_lo + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc, 1u);
             }
             ptx::umma_commit(&free_[sh]);
             ptx::umma_commit(&free_[sl]);
@@ -232,17 +245,26 @@ void plan3(int64_t nq, int64_t m, int& q_tiles, int& e_tiles, int& echunks, int&
   echunks = per;
 }
 
-template <int EPI>
-int launch_k3(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& th, const CUtensorMap& tl,
-              const Tc3Params& prm, int grid, cudaStream_t st) {
-  auto kern = pairwise_tc3_kernel<EPI>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+template <int EPI, int TKH>
+int launch_k3t(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& th, const CUtensorMap& tl,
+               const Tc3Params& prm, int grid, cudaStream_t st) {
+  auto kern = pairwise_tc3_kernel<EPI, TKH>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3<TKH>::SMEM_BYTES);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pairwise_tc3_kernel)");
   profile_begin(st);
-  kern<<<grid, NTHREADS3, SMEM_BYTES, st>>>(qh, ql, th, tl, prm);
+  kern<<<grid, NTHREADS3, Cfg3<TKH>::SMEM_BYTES, st>>>(qh, ql, th, tl, prm);
   profile_end(st);
   B2K_LAUNCH_CHECK("pairwise_tc3_kernel");
   return 0;
+}
+template <int EPI>
+int launch_k3(int tkh, const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& th, const CUtensorMap& tl,
+              const Tc3Params& prm, int grid, cudaStream_t st) {
+  return tkh == 32 ? launch_k3t<EPI, 32>(qh, ql, th, tl, prm, grid, st) : launch_k3t<EPI, 64>(qh, ql, th, tl, prm, grid, st);
+}
+int tk3_choice() {
+  const char* e = getenv("B200KGE_TC3_TK");
+  return (e && atoi(e) == 32) ? 32 : 64;
 }
 
 }  // namespace
@@ -256,26 +278,27 @@ int tc3_nchunks(int64_t nq, int64_t m) {
 int launch_pairwise_tc3(int epi_kind, const SplitSet& Q, const SplitSet& T, const EpiParams& P, cudaStream_t st) {
   const int64_t nq = Q.rows, m = T.rows;
   if (nq == 0 || m == 0) return 0;
-  if (Q.Kp != T.Kp || Q.Kp % TKH != 0) { set_error("operand planes disagree on the padded reduction length"); return B200KGE_ERR_INVALID; }
+  if (Q.Kp != T.Kp || Q.Kp % 64 != 0) { set_error("operand planes disagree on the padded reduction length"); return B200KGE_ERR_INVALID; }
+  const int tkh = tk3_choice();
   Tc3Params prm;
-  prm.nq = nq; prm.m = m; prm.nk = Q.Kp / TKH;
+  prm.nq = nq; prm.m = m; prm.nk = Q.Kp / tkh;
   plan3(nq, m, prm.q_tiles, prm.e_tiles, prm.echunks, prm.tn);
   prm.q_scale = Q.inv_scale; prm.t_scale = T.inv_scale;
   CUtensorMap mQh, mQl, mTh, mTl;
   int rc;
-  if ((rc = tc::make_map_f16(&mQh, Q.hi, nq, Q.Kp, Q.Kp, TM))) return rc;
-  if ((rc = tc::make_map_f16(&mQl, Q.lo, nq, Q.Kp, Q.Kp, TM))) return rc;
-  if ((rc = tc::make_map_f16(&mTh, T.hi, m, T.Kp, T.Kp, prm.tn))) return rc;
-  if ((rc = tc::make_map_f16(&mTl, T.lo, m, T.Kp, T.Kp, prm.tn))) return rc;
+  if ((rc = tc::make_map_f16(&mQh, Q.hi, nq, Q.Kp, Q.Kp, TM, tkh))) return rc;
+  if ((rc = tc::make_map_f16(&mQl, Q.lo, nq, Q.Kp, Q.Kp, TM, tkh))) return rc;
+  if ((rc = tc::make_map_f16(&mTh, T.hi, m, T.Kp, T.Kp, prm.tn, tkh))) return rc;
+  if ((rc = tc::make_map_f16(&mTl, T.lo, m, T.Kp, T.Kp, prm.tn, tkh))) return rc;
   prm.epi = P;
   prm.epi.nchunks = 2 * prm.echunks;   // two epilogue warps (column halves) per row
   const int total = prm.q_tiles * prm.echunks;
   const int grid = total < num_sms() ? total : num_sms();
   switch (epi_kind) {
-    case EPI_STORE: return launch_k3<EPI_STORE>(mQh, mQl, mTh, mTl, prm, grid, st);
-    case EPI_BCE:   return launch_k3<EPI_BCE>(mQh, mQl, mTh, mTl, prm, grid, st);
-    case EPI_KL:    return launch_k3<EPI_KL>(mQh, mQl, mTh, mTl, prm, grid, st);
-    case EPI_RANK:  return launch_k3<EPI_RANK>(mQh, mQl, mTh, mTl, prm, grid, st);
+    case EPI_STORE: return launch_k3<EPI_STORE>(tkh, mQh, mQl, mTh, mTl, prm, grid, st);
+    case EPI_BCE:   return launch_k3<EPI_BCE>(tkh, mQh, mQl, mTh, mTl, prm, grid, st);
+    case EPI_KL:    return launch_k3<EPI_KL>(tkh, mQh, mQl, mTh, mTl, prm, grid, st);
+    case EPI_RANK:  return launch_k3<EPI_RANK>(tkh, mQh, mQl, mTh, mTl, prm, grid, st);
   }
   set_error("bad epilogue kind %d", epi_kind);
   return B200KGE_ERR_INVALID;

@@ -348,17 +348,19 @@ inline int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
   return 0;
 }
 
-// 2-D fp16 tensor map over [rows, cols] halfs with row stride ld halfs; box = 64 x box_rows (128-byte
-// rows, 128-byte swizzle).
-inline int make_map_f16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2-D fp16 tensor map over [rows, cols] halfs with row stride ld halfs; box = box_cols x box_rows with
+// box_cols = 64 (128-byte rows, 128-byte swizzle) or 32 (64-byte rows, 64-byte swizzle).
+inline int make_map_f16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                        int box_cols = 64) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return B200KGE_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(f16) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows,

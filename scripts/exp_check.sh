@@ -16,17 +16,18 @@ echo "x_gemm pytest rc=$?" >> gpurun_out/exp_summary.txt
 timeout 240 python -m pytest tests/test_gpu_experimental.py -q -k "x_backward or x_ns_backward" > gpurun_out/exp_backward.log 2>&1
 echo "x_backward pytest rc=$?" >> gpurun_out/exp_summary.txt
 tail -5 gpurun_out/exp_backward.log >> gpurun_out/exp_summary.txt
-for v in tc3 tc4-forward tc4-direct; do
-  timeout 180 python -m pytest tests/test_gpu_experimental.py -x -q -k "$v" > "gpurun_out/exp_$v.log" 2>&1
+for v in "tc3 and not tk32" tc3-tk32 tc4-forward tc4-direct; do
+  f="gpurun_out/exp_$(echo "$v" | tr ' ' '_').log"
+  timeout 180 python -m pytest tests/test_gpu_experimental.py -x -q -k "$v" > "$f" 2>&1
   echo "$v pytest rc=$?" >> gpurun_out/exp_summary.txt
-  tail -3 "gpurun_out/exp_$v.log" >> gpurun_out/exp_summary.txt
+  tail -3 "$f" >> gpurun_out/exp_summary.txt
 done
-for cfg in "1 0" "3 0" "4 0" "4 1"; do
+for cfg in "1 0 64" "3 0 64" "3 0 32" "4 0 64" "4 1 64"; do
   set -- $cfg
-  B200KGE_TC_VERSION=$1 B200KGE_TC4_DIRECT=$2 timeout 180 python bench.py --steps 100 --warmup 5 \
-    > "gpurun_out/bench_v$1_d$2.json" 2> "gpurun_out/bench_v$1_d$2.err"
-  echo "bench v$1 direct=$2 rc=$?" >> gpurun_out/exp_summary.txt
-  python - "gpurun_out/bench_v$1_d$2.json" >> gpurun_out/exp_summary.txt <<'PY'
+  B200KGE_TC_VERSION=$1 B200KGE_TC4_DIRECT=$2 B200KGE_TC3_TK=$3 timeout 180 python bench.py --steps 100 --warmup 5 \
+    > "gpurun_out/bench_v$1_d$2_k$3.json" 2> "gpurun_out/bench_v$1_d$2_k$3.err"
+  echo "bench v$1 direct=$2 tk=$3 rc=$?" >> gpurun_out/exp_summary.txt
+  python - "gpurun_out/bench_v$1_d$2_k$3.json" >> gpurun_out/exp_summary.txt <<'PY'
 import json, sys
 try:
     j = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])

@@ -1,5 +1,5 @@
 #!/bin/bash
-# ncu capture of the dominant kernel and the launch list for one tensor-core path:
+# ncu capture of the dominant kernel and the launch list for one tensor-core path (B200KGE_TC3_TK from the environment):
 #   gpurun --timeout 900 -- 'bash scripts/exp_profile.sh 3'        # B200KGE_TC_VERSION (1 default, 3, 4)
 #   gpurun --timeout 900 -- 'bash scripts/exp_profile.sh 4 1'      # tc4 with direct TMA signalling
 # Reports stay in /tmp on the box (they exceed gpurun_out's size limit); the raw-page CSV and the launch list

@@ -30,17 +30,19 @@ def eng():
     return engine
 
 
-VARIANTS = [("3", "0"), ("4", "0"), ("4", "1")]   # (B200KGE_TC_VERSION, B200KGE_TC4_DIRECT)
+VARIANTS = [("3", "0", "64"), ("3", "0", "32"), ("4", "0", "64"), ("4", "1", "64")]
+# (B200KGE_TC_VERSION, B200KGE_TC4_DIRECT, B200KGE_TC3_TK)
 
 
-@pytest.fixture(params=VARIANTS, ids=["tc3", "tc4-forward", "tc4-direct"])
+@pytest.fixture(params=VARIANTS, ids=["tc3", "tc3-tk32", "tc4-forward", "tc4-direct"])
 def variant(request, monkeypatch):
     """Selects the experimental kernel for the duration of a test (the default path is restored afterwards)."""
-    ver, direct = request.param
+    ver, direct, tk = request.param
 
     def select():
         monkeypatch.setenv("B200KGE_TC_VERSION", ver)
         monkeypatch.setenv("B200KGE_TC4_DIRECT", direct)
+        monkeypatch.setenv("B200KGE_TC3_TK", tk)
     return select
 
 
