@@ -432,3 +432,7 @@ def x_score_1vsN_loss_csr(model: str, combine: str, q_tab, rel, cand_tab, csr_of
         n, offs.data_ptr(), cols.data_ptr() if nnz else None, nnz, label_smoothing, LOSS[loss], offset, out.data_ptr(),
         rows.data_ptr() if rows is not None else None, ws.data_ptr(), ws.numel(), _stream(dev)))
     return (out, rows) if return_rows else out
+
+
+# validated names of entry points that started life as experimental
+score_1vsN_loss_csr = x_score_1vsN_loss_csr

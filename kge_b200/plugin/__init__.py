@@ -99,11 +99,52 @@ def _scorer(name, base):
     return type(f"B200{base.__name__}", (_B200ScorerMixin, base), {"_b200_name": name})
 
 
+class _TableScoreFn(torch.autograd.Function):
+    """Index-level scoring that reads the embedding tables in place.  Forward: sm_100a kernels (gather fused,
+    no `embed_all()` copy).  Backward: `model._b200_score_backward` (gradient kernels where validated, else
+    recomputation through the reference's dense expression)."""
+
+    @staticmethod
+    def forward(ctx, ent_w, rel_w, model, kind, a, p, b):
+        ctx.model, ctx.kind = model, kind
+        ctx.save_for_backward(ent_w, rel_w, a, p, b if b is not None else torch.empty(0, device=ent_w.device))
+        ctx.has_b = b is not None
+        return model._b200_score_forward(ent_w.detach(), rel_w.detach(), kind, a, p, b)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ent_w, rel_w, a, p, b = ctx.saved_tensors
+        d_ent, d_rel = ctx.model._b200_score_backward(ent_w, rel_w, ctx.kind, a, p, b if ctx.has_b else None,
+                                                      grad_out)
+        return d_ent, d_rel, None, None, None, None, None
+
+
+class _Loss1vsAllFn(torch.autograd.Function):
+    """Fused 1vsAll step: (loss(score_sp, o) + loss(score_po, s)) / n as ONE launch sequence."""
+
+    @staticmethod
+    def forward(ctx, ent_w, rel_w, model, triples, loss, offset):
+        ctx.model, ctx.loss, ctx.offset = model, loss, offset
+        ctx.save_for_backward(ent_w, rel_w, triples)
+        ln, prec = model._b200_args()
+        return engine.train_1vsall_forward(model._b200_name, ent_w.detach(), rel_w.detach(), triples, loss, offset,
+                                           ln, prec)
+
+    @staticmethod
+    def backward(ctx, g):
+        ent_w, rel_w, triples = ctx.saved_tensors
+        d_ent, d_rel = ctx.model._b200_loss_1vsall_backward(ent_w, rel_w, triples, ctx.loss, ctx.offset)
+        return d_ent * g, d_rel * g, None, None, None, None
+
+
 class _B200ModelMixin:
     """Index-level overrides (kge_model.py:663-789): read the tables in place when possible."""
 
     _b200_name = None
     _b200_scorer_cls = None
+    #: "native": gradient kernels of libb200kge where they exist (dot family, bce/kl); "reference": recompute
+    #: through the reference's dense torch expression (autograd)
+    b200_backward = "reference"
 
     def __init__(self, config, dataset, configuration_key=None, init_for_load_only=False):
         super().__init__(config=config, dataset=dataset, configuration_key=configuration_key,
@@ -112,58 +153,142 @@ class _B200ModelMixin:
         self._scorer = self._b200_scorer_cls(config, dataset, self.configuration_key)
 
     # -- helpers
-    def _b200_direct(self):
-        """True if the tables can be read in place: plain LookupEmbedders, dropout inactive, and no
-        autograd graph requested (training backward goes through the scorer-level Function)."""
+    def b200_fusable(self):
+        """True if the tables can be read in place: plain LookupEmbedders, one entity table, dropout inactive."""
         es, ep, eo = self.get_s_embedder(), self.get_p_embedder(), self.get_o_embedder()
         for e in (es, ep, eo):
             if type(e) is not LookupEmbedder:
                 return False
             if e.dropout.p > 0 and e.training:
                 return False
-        if es is not eo:
-            return False
-        w = es._embeddings.weight
-        if torch.is_grad_enabled() and (w.requires_grad or ep._embeddings.weight.requires_grad):
-            return False
-        return True
+        return es is eo
+
+    _b200_direct = b200_fusable
+
+    def b200_csr_labels_ok(self, label_smoothing):
+        return label_smoothing == 0.0 or self._b200_name in ("complex", "distmult", "simple", "cp", "rescal")
+
+    def _b200_weights(self):
+        return self.get_s_embedder()._embeddings.weight, self.get_p_embedder()._embeddings.weight
 
     def _b200_tables(self):
-        return (self.get_s_embedder()._embeddings.weight.detach(),
-                self.get_p_embedder()._embeddings.weight.detach())
+        e, r = self._b200_weights()
+        return e.detach(), r.detach()
 
     def _b200_args(self):
         sc = self._scorer
         return sc._b200_l_norm(), sc._b200_precision()
 
+    def _b200_needs_grad(self):
+        e, r = self._b200_weights()
+        return torch.is_grad_enabled() and (e.requires_grad or r.requires_grad)
+
+    def _b200_score_forward(self, ent, rel, kind, a, p, b):
+        ln, prec = self._b200_args()
+        name = self._b200_name
+        if kind == "spo":
+            return engine.score_spo(name, ent, rel, ent, a, p, b, ln).view(-1)
+        if kind == "sp_":
+            return engine.score_1vsN(name, "sp_", ent, rel, ent, a, p, b, ln, prec)
+        if kind == "_po":
+            return engine.score_1vsN(name, "_po", ent, rel, ent, a, p, b, ln, prec)
+        if kind == "sp_po":   # a = [s | o] stacked
+            n = p.numel()
+            return engine.score_sp_po(name, ent, rel, a[:n], p, a[n:], b, ln, prec)
+        raise ValueError(kind)
+
+    def _b200_ref_scores(self, ent, rel, kind, a, p, b):
+        """The reference's dense expression on gathered rows (for the recompute backward)."""
+        ref = super(_B200ScorerMixin, self._scorer).score_emb
+        if kind == "spo":
+            return ref(ent[a], rel[p], ent[b], "spo").view(-1)
+        cand = ent if b is None else ent[b]
+        if kind == "sp_":
+            return ref(ent[a], rel[p], cand, "sp_")
+        if kind == "_po":
+            return ref(cand, rel[p], ent[a], "_po")
+        n = p.numel()
+        return torch.cat((ref(ent[a[:n]], rel[p], cand, "sp_"), ref(cand, rel[p], ent[a[n:]], "_po")), dim=1)
+
+    def _b200_score_backward(self, ent_w, rel_w, kind, a, p, b, grad_out):
+        e, r = ent_w.detach().requires_grad_(True), rel_w.detach().requires_grad_(True)
+        with torch.enable_grad():
+            out = self._b200_ref_scores(e, r, kind, a, p, b)
+            return torch.autograd.grad(out, (e, r), grad_out.reshape(out.shape), allow_unused=False)
+
+    def _b200_loss_1vsall_backward(self, ent_w, rel_w, triples, loss, offset):
+        name = self._b200_name
+        if self.b200_backward == "native" and name in ("complex", "distmult", "simple", "cp", "rescal"):
+            return engine.x_train_1vsall_backward(name, ent_w.detach(), rel_w.detach(), triples, loss, offset)
+        e, r = ent_w.detach().requires_grad_(True), rel_w.detach().requires_grad_(True)
+        n = triples.shape[0]
+        s, p, o = triples[:, 0], triples[:, 1], triples[:, 2]
+        with torch.enable_grad():
+            total = 0.0
+            for kind, a, lab in (("sp_", s, o), ("_po", o, s)):
+                x = self._b200_ref_scores(e, r, kind, a, p, None)
+                if loss == "bce":
+                    y = torch.zeros_like(x)
+                    y[torch.arange(n, device=x.device), lab] = 1.0
+                    total = total + torch.nn.functional.binary_cross_entropy_with_logits(x + offset, y, reduction="sum")
+                else:
+                    total = total + torch.nn.functional.cross_entropy(x, lab, reduction="sum")
+            return torch.autograd.grad(total / n, (e, r))
+
+    def _b200_call(self, kind, a, p, b):
+        ent_w, rel_w = self._b200_weights()
+        if self._b200_needs_grad():
+            return _TableScoreFn.apply(ent_w, rel_w, self, kind, a, p, b)
+        return self._b200_score_forward(ent_w.detach(), rel_w.detach(), kind, a, p, b)
+
     def score_spo(self, s, p, o, direction=None):
-        if not self._b200_direct():
+        if not self.b200_fusable():
             return super().score_spo(s, p, o, direction)
-        ent, rel = self._b200_tables()
-        return engine.score_spo(self._b200_name, ent, rel, ent, s, p, o, self._b200_args()[0]).view(-1)
+        return self._b200_call("spo", s, p, o)
 
     def score_sp(self, s, p, o=None):
-        if not self._b200_direct():
+        if not self.b200_fusable():
             return super().score_sp(s, p, o)
-        ent, rel = self._b200_tables()
-        ln, prec = self._b200_args()
-        return engine.score_1vsN(self._b200_name, "sp_", ent, rel, ent, s, p, o, ln, prec)
+        return self._b200_call("sp_", s, p, o)
 
     def score_po(self, p, o, s=None):
-        if not self._b200_direct():
+        if not self.b200_fusable():
             return super().score_po(p, o, s)
-        ent, rel = self._b200_tables()
-        ln, prec = self._b200_args()
-        return engine.score_1vsN(self._b200_name, "_po", ent, rel, ent, o, p, s, ln, prec)
+        return self._b200_call("_po", o, p, s)
 
     def score_sp_po(self, s, p, o, entity_subset=None):
-        if not self._b200_direct():
+        if not self.b200_fusable():
             return super().score_sp_po(s, p, o, entity_subset)
+        return self._b200_call("sp_po", torch.cat((s.reshape(-1), o.reshape(-1))), p, entity_subset)
+
+    # -- fused forms for the job plugins (kge_b200/plugin/jobs.py): scores never reach HBM
+    def loss_1vsall(self, triples, loss="bce", offset=0.0, need_grad=None):
+        """(loss(score_sp, o) + loss(score_po, s)) / n for a [n,3] batch (train_1vsAll.py:48-82)."""
+        ent_w, rel_w = self._b200_weights()
+        if need_grad is None:
+            need_grad = self._b200_needs_grad()
+        if need_grad and self._b200_needs_grad():
+            return _Loss1vsAllFn.apply(ent_w, rel_w, self, triples, loss, offset)
+        ln, prec = self._b200_args()
+        return engine.train_1vsall_forward(self._b200_name, ent_w.detach(), rel_w.detach(), triples, loss, offset,
+                                           ln, prec)
+
+    def loss_kvsall(self, combine, a, p, csr_offsets, csr_cols, loss="kl", offset=0.0, label_smoothing=0.0):
+        """Sum over rows of the KvsAll loss with CSR multi-hot labels (train_KvsAll.py:242-294); forward only."""
         ent, rel = self._b200_tables()
         ln, prec = self._b200_args()
-        return engine.score_sp_po(self._b200_name, ent, rel, s, p, o, entity_subset, ln, prec)
+        return engine.score_1vsN_loss_csr(self._b200_name, combine, ent, rel, ent, csr_offsets, csr_cols, a, p,
+                                          loss, offset, label_smoothing, ln, prec)
 
-    # -- fused forms for job plugins (scores never reach HBM); forward only
+    def score_negatives(self, triples, negatives, slot):
+        """[n, 1+K]: the positive triple's score in column 0, its K corrupted versions after it
+        (train_negative_sampling.py:139-148 + sampler.py:263-344); forward only."""
+        ent, rel = self._b200_tables()
+        return engine.ns_score(self._b200_name, ent, rel, triples, negatives, slot, True, self._b200_args()[0])
+
+    def loss_dense(self, scores, labels, loss="bce", offset=0.0):
+        return engine.loss_dense(scores, labels, loss, offset)
+
     def score_sp_loss(self, s, p, labels, loss="bce", offset=0.0):
         ent, rel = self._b200_tables()
         ln, prec = self._b200_args()
@@ -202,7 +327,10 @@ B200Rescal = _model("B200Rescal", "rescal", Rescal, RescalScorer)
 B200TransE = _model("B200TransE", "transe", TransE, TransEScorer)
 B200RotatE = _model("B200RotatE", "rotate", RotatE, RotatEScorer)
 
-__all__ = ["B200ComplEx", "B200DistMult", "B200SimplE", "B200CP", "B200Rescal", "B200TransE", "B200RotatE"]
+from .jobs import B200TrainingJob1vsAll, B200TrainingJobKvsAll, B200TrainingJobNegativeSampling  # noqa: E402
+
+__all__ = ["B200ComplEx", "B200DistMult", "B200SimplE", "B200CP", "B200Rescal", "B200TransE", "B200RotatE",
+           "B200TrainingJob1vsAll", "B200TrainingJobKvsAll", "B200TrainingJobNegativeSampling"]
 
 
 def install_native_indexes(dataset, splits=("train", "valid", "test")):

@@ -1,0 +1,190 @@
+"""Job plugins: thin subclasses of the reference's own training jobs whose `_process_subbatch` calls the FUSED
+entry points of libb200kge (score + loss in one launch sequence, scores never reach HBM).
+
+Selected through the reference's job factory (kge/job/train.py:127-137: `init_from(config.get("<type>.class_name"),
+config.modules(), ...)`), i.e. in a LibKGE config:
+
+    modules: [kge.job, kge.model, kge.model.embedder, kge_b200.plugin]
+    model: b200_complex
+    1vsAll.class_name: B200TrainingJob1vsAll
+    KvsAll.class_name: B200TrainingJobKvsAll
+    negative_sampling.class_name: B200TrainingJobNegativeSampling
+
+Everything else of the job (data loading, collate, sub-batching, trace entries, penalties, optimizer, hooks,
+checkpoints) is the reference's code, unchanged.  Whenever a fused form is not available for the configured
+combination (a non-b200 model, a loss other than bce / kl, dropout active, ...) the method falls through to
+the reference implementation, which then still reaches the kernels through `model.score_*`.
+"""
+from __future__ import annotations
+
+import time
+
+import torch
+
+from kge.job.train_1vsAll import TrainingJob1vsAll
+from kge.job.train_KvsAll import TrainingJobKvsAll
+from kge.job.train_negative_sampling import TrainingJobNegativeSampling
+from kge.job import Job
+from kge.util.loss import BCEWithLogitsKgeLoss, KLDivWithSoftmaxKgeLoss
+
+S, P, O = 0, 1, 2
+SLOT_STR = ["s", "p", "o"]
+
+
+def _fused_loss_kind(loss):
+    """("bce"|"kl", offset) if the job's KgeLoss has a fused form, else None (loss.py:139-213)."""
+    if type(loss) is BCEWithLogitsKgeLoss and loss._bce_type is None:
+        return "bce", float(loss._offset)
+    if type(loss) is KLDivWithSoftmaxKgeLoss:
+        return "kl", 0.0
+    return None
+
+
+def _fused_model(model):
+    """The b200 model if its fused entry points can read the tables in place, else None."""
+    if getattr(model, "_b200_name", None) is None or not hasattr(model, "b200_fusable"):
+        return None
+    return model if model.b200_fusable() else None
+
+
+class B200TrainingJob1vsAll(TrainingJob1vsAll):
+    """`TrainingJob1vsAll` (train_1vsAll.py:10-82) with the sub-batch step as ONE fused call:
+    (loss(score_sp, o) + loss(score_po, s)) / batch_size, both directions stacked into one problem."""
+
+    def __init__(self, config, dataset, parent_job=None, model=None, forward_only=False):
+        super().__init__(config, dataset, parent_job, model=model, forward_only=forward_only)
+        if self.__class__ == B200TrainingJob1vsAll:
+            for f in Job.job_created_hooks:
+                f(self)
+
+    def _process_subbatch(self, batch_index, batch, subbatch_slice, result):
+        model, kind = _fused_model(self.model), _fused_loss_kind(self.loss)
+        if model is None or kind is None:
+            return super()._process_subbatch(batch_index, batch, subbatch_slice, result)
+        batch_size = result.size
+
+        result.prepare_time -= time.time()
+        triples = batch["triples"][subbatch_slice].to(self.device, non_blocking=True)
+        result.prepare_time += time.time()
+
+        result.forward_time -= time.time()
+        # sum over both directions and all rows of the sub-batch, divided by the sub-batch size by the kernel's
+        # finaliser; the reference divides by the size of the whole batch (train_1vsAll.py:65,76)
+        loss_value = model.loss_1vsall(triples, kind[0], kind[1], need_grad=not self.is_forward_only)
+        if len(triples) != batch_size:
+            loss_value = loss_value * (len(triples) / batch_size)
+        result.avg_loss += loss_value.item()
+        result.forward_time += time.time()
+
+        result.backward_time -= time.time()
+        if not self.is_forward_only:
+            loss_value.backward()
+        result.backward_time += time.time()
+
+
+class B200TrainingJobKvsAll(TrainingJobKvsAll):
+    """`TrainingJobKvsAll` (train_KvsAll.py:205-294): per query type one fused score+loss call that consumes the
+    batch's label coordinates as CSR (no dense [n, E] label matrix: job/util.py:32-60 + `.to_dense()`,
+    train_KvsAll.py:242-266 are not executed)."""
+
+    def __init__(self, config, dataset, parent_job=None, model=None, forward_only=False):
+        super().__init__(config, dataset, parent_job, model=model, forward_only=forward_only)
+        if self.__class__ == B200TrainingJobKvsAll:
+            for f in Job.job_created_hooks:
+                f(self)
+
+    def _process_subbatch(self, batch_index, batch, subbatch_slice, result):
+        model, kind = _fused_model(self.model), _fused_loss_kind(self.loss)
+        qtypes = [q for q in self.query_types]
+        if (model is None or kind is None or not self.is_forward_only or "s_o" in qtypes
+                or not model.b200_csr_labels_ok(self.label_smoothing)):
+            return super()._process_subbatch(batch_index, batch, subbatch_slice, result)
+        batch_size = result.size
+
+        result.prepare_time -= time.time()
+        queries = batch["queries"][subbatch_slice].to(self.device)
+        qt = batch["query_type_indexes"][subbatch_slice].to(self.device)
+        coords = batch["label_coords"]                       # [nnz, 2] int, rows ascending (collate order)
+        start, stop = subbatch_slice.start or 0, subbatch_slice.stop
+        rows = coords[:, 0].long()
+        if start != 0 or stop < batch_size:
+            keep = (rows >= start) & (rows < stop)
+            rows, cols = rows[keep] - start, coords[keep, 1].long()
+        else:
+            cols = coords[:, 1].long()
+        n_sub = len(queries)
+        result.prepare_time += time.time()
+
+        for query_type_index, query_type in enumerate(self.query_types):
+            result.prepare_time -= time.time()
+            examples = (qt == query_type_index).nonzero(as_tuple=False).view(-1)
+            if len(examples) == 0:
+                result.prepare_time += time.time()
+                continue
+            # CSR of the selected rows: counts per selected row, columns in row order
+            sel = torch.zeros(n_sub, dtype=torch.bool, device=self.device)
+            sel[examples] = True
+            keep = sel[rows]
+            counts = torch.bincount(rows[keep], minlength=n_sub)[examples]
+            offsets = torch.zeros(len(examples) + 1, dtype=torch.int64, device=self.device)
+            torch.cumsum(counts, 0, out=offsets[1:])
+            ccols = cols[keep]
+            result.prepare_time += time.time()
+
+            result.forward_time -= time.time()
+            # sp_ queries are (s, p) pairs, _po queries are (p, o) pairs (indexing.py:197-235)
+            if query_type == "sp_":
+                combine, ent_idx, rel_idx = "sp_", queries[examples, 0], queries[examples, 1]
+            else:
+                combine, ent_idx, rel_idx = "_po", queries[examples, 1], queries[examples, 0]
+            loss_value = model.loss_kvsall(combine, ent_idx, rel_idx, offsets, ccols, kind[0], kind[1],
+                                           self.label_smoothing) / batch_size
+            result.avg_loss += loss_value.item()
+            result.forward_time += time.time()
+
+
+class B200TrainingJobNegativeSampling(TrainingJobNegativeSampling):
+    """`TrainingJobNegativeSampling` (train_negative_sampling.py:103-164): per slot ONE kernel gathers the sampled
+    rows and scores them, with the positive triple in column 0 — neither `[n*K, D]` gathers (`triple`
+    implementation, sampler.py:294-305) nor scoring against all unique targets (`batch`, :306-339)."""
+
+    def __init__(self, config, dataset, parent_job=None, model=None, forward_only=False):
+        super().__init__(config, dataset, parent_job, model=model, forward_only=forward_only)
+        if self.__class__ == B200TrainingJobNegativeSampling:
+            for f in Job.job_created_hooks:
+                f(self)
+
+    def _process_subbatch(self, batch_index, batch, subbatch_slice, result):
+        model = _fused_model(self.model)
+        if model is None or not self.is_forward_only:
+            return super()._process_subbatch(batch_index, batch, subbatch_slice, result)
+        batch_size = result.size
+        result.prepare_time -= time.time()
+        triples = batch["triples"][subbatch_slice]
+        negs = batch["negative_samples"]
+        subbatch_size = len(triples)
+        labels = batch["labels"]
+        result.prepare_time += time.time()
+        kind = _fused_loss_kind(self.loss)
+
+        for slot in [S, P, O]:
+            num_samples = self._sampler.num_samples[slot]
+            if num_samples <= 0:
+                continue
+            result.prepare_time -= time.time()
+            negatives = negs[slot].samples(subbatch_slice if (subbatch_size != batch_size) else None)
+            result.prepare_time += time.time()
+
+            result.forward_time -= time.time()
+            scores = model.score_negatives(triples, negatives.to(self.device), slot)      # [n, 1+K], positive first
+            if kind is not None and kind[0] == "bce":
+                # labels are 1 in column 0 and 0 elsewhere (train_negative_sampling.py:128-137): index labels
+                lab = torch.zeros(subbatch_size, dtype=torch.int64, device=self.device)
+                loss_value = model.loss_dense(scores, lab, "bce", kind[1]) / batch_size
+            else:
+                if labels[slot] is None or labels[slot].shape != (subbatch_size, 1 + num_samples):
+                    labels[slot] = torch.zeros((subbatch_size, 1 + num_samples), device=self.device)
+                    labels[slot][:, 0] = 1
+                loss_value = self.loss(scores, labels[slot], num_negatives=num_samples) / batch_size
+            result.avg_loss += loss_value.item()
+            result.forward_time += time.time()
