@@ -66,12 +66,15 @@ typedef enum {
 
 /* Which kernel family computes dot-product scorers. */
 typedef enum {
-  B200KGE_PREC_AUTO = 0,   /* tcgen05 mixed mode (TF32_BF16X2) when the shape allows it, else fp32 SIMT */
+  B200KGE_PREC_AUTO = 0,   /* F16X3 for dot-product scorers with 32 <= K <= 1024 and n >= 16, else fp32 SIMT */
   B200KGE_PREC_FP32 = 1,   /* CUDA-core fp32 FFMA (bit-for-bit fp32 products)                    */
   B200KGE_PREC_3XTF32 = 2, /* tcgen05 tensor cores, hi/lo split, fp32-equivalent (~3e-6 of rms)  */
   B200KGE_PREC_TF32 = 3,   /* tcgen05 single pass (~4e-3 of rms; does NOT meet the 1e-4 bar)     */
-  B200KGE_PREC_TF32_BF16X2 = 4 /* tf32 hi*hi + two bf16 cross terms: 8 MMAs per 32-wide K chunk instead
+  B200KGE_PREC_TF32_BF16X2 = 4, /* tf32 hi*hi + two bf16 cross terms: 8 MMAs per 32-wide K chunk instead
                               of 12, operand error ~2^-20 (below the accumulator's)               */
+  B200KGE_PREC_F16X3 = 5   /* operands split ONCE per call into row-scaled fp16 hi/lo planes (22 significant
+                              bits), hi*hi + hi*lo + lo*hi on the f16 tensor pipe: 6 MMA slots per 32
+                              reduction elements, no shared-memory round trip in the main loop    */
 } b200kge_precision;
 
 typedef enum {
@@ -271,9 +274,9 @@ int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const 
  * as it appears, like duplicate triples in the reference), optionally smoothed: y = (1 - eps) * count + 1/m.
  * *loss_out = sum_i loss(score row i, y_i) (BCE with offset | KL), row_loss_out (optional) the per-row terms.
  * Composition of the fused scorer (label-free pass) with row kernels over the nnz listed columns; cand must be a
- * plain table; eps > 0 needs a dot-family model.  Sizes: b200kge_x_score_1vsN_loss_csr_workspace_bytes. */
-size_t b200kge_x_score_1vsN_loss_csr_workspace_bytes(int model, int64_t n, int64_t m, int32_t D, int64_t nnz);
-int b200kge_x_score_1vsN_loss_csr(int model, int combine, float l_norm, int precision,
+ * plain table; eps > 0 needs a dot-family model.  Sizes: b200kge_score_1vsN_loss_csr_workspace_bytes. */
+size_t b200kge_score_1vsN_loss_csr_workspace_bytes(int model, int64_t n, int64_t m, int32_t D, int64_t nnz);
+int b200kge_score_1vsN_loss_csr(int model, int combine, float l_norm, int precision,
                                   const b200kge_rows_t* q, const b200kge_rows_t* p,
                                   const b200kge_rows_t* cand, int64_t n, const int64_t* csr_off,
                                   const int64_t* csr_col, int64_t nnz, float label_smoothing, int loss_kind,
@@ -292,16 +295,17 @@ int b200kge_x_ns_backward(int model, float l_norm, const b200kge_rows_t* ent, co
 
 /* LookupEmbedder.penalty (kge/model/embedder/lookup_embedder.py:123-177) on the rows view `rows` (the whole
  * table, or the batch's unique rows through rows->idx with their `counts`, NULL = all ones):
- *   *out = scale * sum_r counts[r] * sum_k |x_rk|^p        (complex_abs: x -> sqrt(re^2 + im^2 + 1e-14): "n3")
+ *   *out = scale * sum_r counts[r] * sum_k |x_rk|^p        (complex_abs: x -> sqrt(re^2 + im^2 + 1e-14): "n3",
+ *   which the reference accepts in complex space only, lookup_embedder.py:29-34)
  * scale = regularize_weight / p (unweighted) or regularize_weight / p / len(indexes) (weighted).
  * workspace: (ceil(rows / 8) + 1) floats.  Deterministic (fixed-order two-stage sum). */
-int b200kge_x_lookup_penalty(const b200kge_rows_t* rows, const float* counts, float p, int complex_abs,
+int b200kge_lookup_penalty(const b200kge_rows_t* rows, const float* counts, float p, int complex_abs,
                              float scale, float* out, void* workspace, size_t workspace_bytes,
                              b200kge_stream_t stream);
 
 /* LookupEmbedder._normalize_embeddings (:64-69): rows of weight [rows, dim] (row stride ld) scaled in place to
  * unit Lp norm (torch.nn.functional.normalize, eps 1e-12). */
-int b200kge_x_normalize_rows(float* weight, int64_t ld, int64_t rows, int32_t dim, float p,
+int b200kge_normalize_rows(float* weight, int64_t ld, int64_t rows, int32_t dim, float p,
                              b200kge_stream_t stream);
 
 #ifdef __cplusplus

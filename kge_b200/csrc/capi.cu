@@ -106,17 +106,32 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
   const int K = f0.K;
   const int64_t ldq = round_up(K, 32);
 
-  bool use_tc = false;
+  // Path selection depends on the model, K, the table and the PER-DIRECTION row count n only — never on whether
+  // the two directions are stacked — so score_sp / score_po / score_sp_po / the fused forms of one batch all run
+  // the same arithmetic (EntityRankingJob compares them, eval_entity_ranking.py:192-203,242-274).
+  //   AUTO    -> F16X3 (pre-split fp16 planes, pairwise_tc3.cu) for dot-product scorers with 32 <= K <= 1024 and
+  //              n >= 16; fp32 SIMT otherwise (beyond K = 1024 the tensor core's fp32 accumulator error, which
+  //              grows with the reduction length — 2.8e-4 of rms at K = 14541 — leaves too little margin)
+  //   F16X3   -> pairwise_tc3.cu (pairwise_tc4.cu, the CTA-pair version, with B200KGE_TC_VERSION=4)
+  //   TF32_BF16X2 / 3XTF32 / TF32 -> pairwise_tc.cu (in-kernel split of raw fp32 tiles; needs TMA-able tables)
+  int tc_kind = 0;       // 0 SIMT, 1 in-kernel split (pairwise_tc.cu), 3 pre-split planes
   if (f0.pair_op == PAIR_DOT && precision != B200KGE_PREC_FP32 && !cols_differ) {
-    const bool ok = tc_supported(f0.pair_op, K, *B.cand, f0.col_off);
-    if (precision == B200KGE_PREC_AUTO) use_tc = ok && nq >= 16;
-    else {
-      if (!ok) { set_error("tensor-core path needs K>=32, 16-byte aligned tables with ld%%4==0"); return B200KGE_ERR_UNSUPPORTED; }
-      use_tc = true;
+    if (precision == B200KGE_PREC_AUTO) {
+      if (K >= 32 && K <= 1024 && n >= 16 && m < (1ll << 31)) tc_kind = 3;
+    } else if (precision == B200KGE_PREC_F16X3) {
+      if (K < 16 || m >= (1ll << 31)) { set_error("the pre-split tensor-core path needs K >= 16"); return B200KGE_ERR_UNSUPPORTED; }
+      tc_kind = 3;
+    } else {
+      if (!tc_supported(f0.pair_op, K, *B.cand, f0.col_off)) { set_error("tensor-core path needs K>=32, 16-byte aligned tables with ld%%4==0"); return B200KGE_ERR_UNSUPPORTED; }
+      tc_kind = 1;
     }
-  } else if (precision == B200KGE_PREC_3XTF32 || precision == B200KGE_PREC_TF32 || precision == B200KGE_PREC_TF32_BF16X2) {
+  } else if (precision != B200KGE_PREC_AUTO && precision != B200KGE_PREC_FP32) {
     if (f0.pair_op != PAIR_DOT) { set_error("tensor-core precision modes apply to dot-product scorers only"); return B200KGE_ERR_UNSUPPORTED; }
   }
+  { const char* env_v = getenv("B200KGE_TC_VERSION");      // experiments: 1 forces the in-kernel split
+    if (env_v && atoi(env_v) == 1 && tc_kind == 3 && tc_supported(f0.pair_op, K, *B.cand, f0.col_off)) {
+      tc_kind = 1; precision = B200KGE_PREC_TF32_BF16X2;
+    } }
 
   if (cols_differ) {
     // run the two halves as separate blocks (CP reads different candidate columns per direction)
@@ -131,10 +146,7 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
     return run_block(h1, l_norm, precision, epi_kind, P1, ws, st, nchunks_out);
   }
 
-  if (use_tc) {
-    // AUTO = mixed mode (tf32 hi*hi + bf16 cross terms): measured both more accurate (2.4e-5 vs 3.0e-5 of
-    // rms: fewer accumulation steps) and faster (8 MMAs per K-chunk instead of 12) than 3xTF32 on B200
-    const int passes = (precision == B200KGE_PREC_TF32) ? 1 : (precision == B200KGE_PREC_3XTF32 ? 3 : 2);
+  if (tc_kind) {
     int rc = 0;
     const float* Q = B.Qpre;
     if (!Q) {
@@ -145,11 +157,11 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
       if (B.q1) { rc = launch_fold_queries(B.model, 1 - B.combine, *B.q1, *B.p, n, n, Qw, ldq, st); if (rc) return rc; }
       Q = Qw;
     }
-    const char* env_v = getenv("B200KGE_TC_VERSION");
-    const int tc_version = env_v ? atoi(env_v) : 1;
-    if ((tc_version == 3 || tc_version == 4) && passes == 2) {
-      // EXPERIMENTAL pre-split fp16 path (presplit.cu + pairwise_tc3.cu | pairwise_tc4.cu): one launch derives the hi/lo
-      // planes of the folded queries and of the (gathered) candidate rows, one launch scores them.
+    if (tc_kind == 3) {
+      // pre-split fp16 path (presplit.cu + pairwise_tc3.cu | pairwise_tc4.cu): one launch derives the hi/lo planes of
+      // the folded queries and of the (gathered) candidate rows, one launch scores them.
+      const char* env_v = getenv("B200KGE_TC_VERSION");
+      const bool pair = env_v && atoi(env_v) == 4;
       const int Kp = (int)round_up(K, 64);
       SplitSet SQ{Q, ldq, nullptr, 0, nq, nq, K, Kp, nullptr, nullptr, nullptr};
       SplitSet ST{B.cand->base, B.cand->ld, B.cand->idx, f0.col_off, m, m + 32, K, Kp, nullptr, nullptr, nullptr};
@@ -161,7 +173,7 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
         set_error("workspace too small for the pre-split operand planes");
         return B200KGE_ERR_WORKSPACE;
       }
-      const int nch3 = tc_version == 4 ? tc4_nchunks(nq, m) : tc3_nchunks(nq, m);
+      const int nch3 = pair ? tc4_nchunks(nq, m) : tc3_nchunks(nq, m);
       if (epi_kind == EPI_BCE || epi_kind == EPI_KL) {
         const int F = (epi_kind == EPI_BCE) ? 2 : 5;
         P.part = (float*)ws.take((size_t)nq * nch3 * F * 4);
@@ -171,9 +183,10 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
       P.nchunks = nch3;
       if (nchunks_out) *nchunks_out = nch3;
       if ((rc = launch_presplit(ST, SQ, st))) return rc;
-      if (tc_version == 4) return launch_pairwise_tc4(epi_kind, SQ, ST, P, st);
+      if (pair) return launch_pairwise_tc4(epi_kind, SQ, ST, P, st);
       return launch_pairwise_tc3(epi_kind, SQ, ST, P, st);
     }
+    const int passes = (precision == B200KGE_PREC_TF32) ? 1 : (precision == B200KGE_PREC_3XTF32 ? 3 : 2);
     const float* T = B.cand->base + f0.col_off;
     int64_t ldt = B.cand->ld;
     if (B.cand->idx) {
@@ -183,11 +196,7 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
       if (rc) return rc;
       T = G; ldt = ldq;
     }
-    // The 1-CTA kernel is the default: on B200 it measured faster than the CTA-pair (cta_group::2)
-    // kernel at every batch size once the epilogue stopped being the bottleneck
-    // (profiles/r1_notes.md).  B200KGE_TC_VERSION=2 selects the pair kernel (kept for experiments).
-    const bool pair = tc_version == 2;
-    const int nch = pair ? tc2_nchunks(nq, m) : tc_nchunks(nq, m);
+    const int nch = tc_nchunks(nq, m);
     if (epi_kind == EPI_BCE || epi_kind == EPI_KL) {
       const int F = (epi_kind == EPI_BCE) ? 2 : 5;
       P.part = (float*)ws.take((size_t)nq * nch * F * 4);
@@ -196,7 +205,6 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
     }
     P.nchunks = nch;
     if (nchunks_out) *nchunks_out = nch;
-    if (pair) return launch_pairwise_tc2(epi_kind, passes, Q, ldq, nq, T, ldt, m, K, P, st);
     return launch_pairwise_tc(epi_kind, passes, Q, ldq, nq, T, ldt, m, K, P, st);
   }
 
@@ -298,11 +306,10 @@ size_t b200kge_workspace_bytes(int model, int64_t n, int64_t m, int32_t D, int c
   if (nch < 320) nch = 320;                              // tensor-core kernels: <= 2 * #SMs chunks per row
   b += (size_t)nq * nch * 5 * 4 + 256;                   // loss partials
   b += (size_t)n * 3 * 8 + (size_t)n * 5 * 8 + 4096;     // host entry: triples, s/p/o, labels, scalar, finaliser scratch
-  { const char* env_v = getenv("B200KGE_TC_VERSION");
-    if (env_v && (atoi(env_v) == 3 || atoi(env_v) == 4)) {   // experimental pre-split fp16 planes + row scales
-      const int64_t Kp = round_up(D, 64);
-      b += 2 * ((size_t)nq * Kp * 2 + 256) + 2 * ((size_t)m * Kp * 2 + 256) + (size_t)(nq + m + 32) * 4 + 512;
-    } }
+  { // pre-split fp16 planes + row scales (the default tensor-core path)
+    const int64_t Kp = round_up(D, 64);
+    b += 2 * ((size_t)nq * Kp * 2 + 256) + 2 * ((size_t)m * Kp * 2 + 256) + (size_t)(nq + m + 32) * 4 + 512;
+  }
   return b + 4096;
 }
 
@@ -711,7 +718,7 @@ int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const 
 }
 
 
-int b200kge_x_lookup_penalty(const b200kge_rows_t* rows, const float* counts, float p, int complex_abs, float scale,
+int b200kge_lookup_penalty(const b200kge_rows_t* rows, const float* counts, float p, int complex_abs, float scale,
                              float* out, void* workspace, size_t workspace_bytes, b200kge_stream_t stream) {
   if (!rows || !out) { set_error("null operand"); return B200KGE_ERR_INVALID; }
   if (!(p > 0.f)) { set_error("p must be positive (got %g)", (double)p); return B200KGE_ERR_INVALID; }
@@ -720,7 +727,7 @@ int b200kge_x_lookup_penalty(const b200kge_rows_t* rows, const float* counts, fl
                         (cudaStream_t)stream);
 }
 
-int b200kge_x_normalize_rows(float* weight, int64_t ld, int64_t rows, int32_t dim, float p, b200kge_stream_t stream) {
+int b200kge_normalize_rows(float* weight, int64_t ld, int64_t rows, int32_t dim, float p, b200kge_stream_t stream) {
   if (!weight && rows > 0) { set_error("null operand"); return B200KGE_ERR_INVALID; }
   return launch_normalize_rows(weight, ld, rows, dim, p, (cudaStream_t)stream);
 }
@@ -747,7 +754,7 @@ int b200kge_x_ns_backward(int model, float l_norm, const b200kge_rows_t* ent, co
 }
 
 
-size_t b200kge_x_score_1vsN_loss_csr_workspace_bytes(int model, int64_t n, int64_t m, int32_t D, int64_t nnz) {
+size_t b200kge_score_1vsN_loss_csr_workspace_bytes(int model, int64_t n, int64_t m, int32_t D, int64_t nnz) {
   const int64_t ldq = round_up(D, 32), tot = nnz + n;
   size_t b = b200kge_workspace_bytes(model, n, m, D, 0);
   b += (size_t)n * 8 + 3 * ((size_t)tot * 8 + 256) + (size_t)tot * 4 + 4 * ((size_t)n * 4 + 256) + 2048;
@@ -755,7 +762,7 @@ size_t b200kge_x_score_1vsN_loss_csr_workspace_bytes(int model, int64_t n, int64
   return b;
 }
 
-int b200kge_x_score_1vsN_loss_csr(int model, int combine, float l_norm, int precision, const b200kge_rows_t* q,
+int b200kge_score_1vsN_loss_csr(int model, int combine, float l_norm, int precision, const b200kge_rows_t* q,
                                   const b200kge_rows_t* p, const b200kge_rows_t* cand, int64_t n,
                                   const int64_t* csr_off, const int64_t* csr_col, int64_t nnz, float label_smoothing,
                                   int loss_kind, float offset, float* loss_out, float* row_loss_out, void* workspace,

@@ -257,15 +257,14 @@ int launch_k3t(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& 
   B2K_LAUNCH_CHECK("pairwise_tc3_kernel");
   return 0;
 }
+// K chunk = 64 halfs (128-byte rows, 128-byte swizzle, 4 slots of 48 KB).  The 32-half variant (8 slots of 24 KB)
+// measured slower on B200 (74.4 vs 69.3 us at the FB15k-237 shape, profiles/r2_summary.md) and was removed.
 template <int EPI>
-int launch_k3(int tkh, const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& th, const CUtensorMap& tl,
+int launch_k3(int, const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& th, const CUtensorMap& tl,
               const Tc3Params& prm, int grid, cudaStream_t st) {
-  return tkh == 32 ? launch_k3t<EPI, 32>(qh, ql, th, tl, prm, grid, st) : launch_k3t<EPI, 64>(qh, ql, th, tl, prm, grid, st);
+  return launch_k3t<EPI, 64>(qh, ql, th, tl, prm, grid, st);
 }
-int tk3_choice() {
-  const char* e = getenv("B200KGE_TC3_TK");
-  return (e && atoi(e) == 32) ? 32 : 64;
-}
+int tk3_choice() { return 64; }
 
 }  // namespace
 

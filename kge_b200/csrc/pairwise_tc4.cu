@@ -269,10 +269,12 @@ int launch_k4(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& t
   return 0;
 }
 
+// DIRECT signalling only: the forwarding variant (local barrier + forwarder lane) measured 85.9 us against 68.4 us
+// at the FB15k-237 shape (profiles/r2_summary.md) and is no longer instantiated.
 template <int EPI>
-int launch_e4(bool direct, const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& th, const CUtensorMap& tl,
+int launch_e4(bool, const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& th, const CUtensorMap& tl,
               const Tc4Params& prm, int grid, cudaStream_t st) {
-  return direct ? launch_k4<EPI, true>(qh, ql, th, tl, prm, grid, st) : launch_k4<EPI, false>(qh, ql, th, tl, prm, grid, st);
+  return launch_k4<EPI, true>(qh, ql, th, tl, prm, grid, st);
 }
 
 }  // namespace

@@ -1,4 +1,4 @@
-// tc_common.cuh — pieces shared by the 1-CTA (pairwise_tc.cu) and 2-CTA (pairwise_tc2.cu) tcgen05 kernels.
+// tc_common.cuh — pieces shared by the tcgen05 kernels (pairwise_tc.cu, pairwise_tc3.cu, pairwise_tc4.cu).
 #pragma once
 #include <cuda.h>
 #include <cstdlib>
@@ -382,12 +382,6 @@ inline int num_sms() {
 }
 
 }  // namespace tc
-
-// 2-CTA kernel (pairwise_tc2.cu)
-int tc2_nchunks(int64_t nq, int64_t m);
-int launch_pairwise_tc2(int epi_kind, int passes, const float* Q, int64_t ldq,
-                        int64_t nq, const float* T, int64_t ldt, int64_t m, int K,
-                        const EpiParams& P, cudaStream_t st);
 
 // Pre-split fp16 kernels (presplit.cu + pairwise_tc3.cu / pairwise_tc4.cu), experimental: B200KGE_TC_VERSION=3|4.
 // One row set of the operand split: rows of `src` (optionally gathered through idx, starting at column

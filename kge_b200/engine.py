@@ -351,7 +351,7 @@ def x_train_1vsall_backward(model: str, ent, rel, triples, loss: str = "bce", of
     return d_ent, d_rel
 
 
-def x_lookup_penalty(weight: torch.Tensor, regularize: str = "lp", regularize_weight: float = 0.0, p: float = 2.0,
+def lookup_penalty(weight: torch.Tensor, regularize: str = "lp", regularize_weight: float = 0.0, p: float = 2.0,
                      weighted: bool = False, indexes: Optional[torch.Tensor] = None, space: str = "euclidean"):
     """LookupEmbedder.penalty (lookup_embedder.py:123-177) as a 0-d tensor."""
     _require_cuda(weight, indexes)
@@ -363,7 +363,11 @@ def x_lookup_penalty(weight: torch.Tensor, regularize: str = "lp", regularize_we
     elif regularize != "lp":
         raise ValueError(f"Invalid value regularize={regularize}")
     lib, k = _lib.load(), _Keep()
-    complex_abs = 1 if (regularize == "n3" and space == "complex") else 0
+    if regularize == "n3" and space != "complex":
+        # the reference accepts n3 only in complex space (lookup_embedder.py:29-34), so its signed-cube branch for
+        # weighted n3 elsewhere (:158) is unreachable
+        raise ValueError("Illegal value n3 for key regularize; allowed values are ['', 'lp'] (space is not complex)")
+    complex_abs = 1 if regularize == "n3" else 0
     counts = None
     if weighted:
         uniq, cnt = torch.unique(indexes, return_counts=True)
@@ -375,18 +379,18 @@ def x_lookup_penalty(weight: torch.Tensor, regularize: str = "lp", regularize_we
         scale = regularize_weight / p
     out = torch.empty((), dtype=torch.float32, device=dev)
     ws = torch.empty(((int(rows.rows) + 7) // 8 + 2) * 4, dtype=torch.uint8, device=dev)
-    _lib.check(lib.b200kge_x_lookup_penalty(C.byref(rows), counts.data_ptr() if counts is not None else None, p,
+    _lib.check(lib.b200kge_lookup_penalty(C.byref(rows), counts.data_ptr() if counts is not None else None, p,
                                             complex_abs, scale, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
     return out
 
 
-def x_normalize_rows_(weight: torch.Tensor, p: float) -> torch.Tensor:
+def normalize_rows_(weight: torch.Tensor, p: float) -> torch.Tensor:
     """In-place row normalisation to unit Lp norm (lookup_embedder.py:64-69)."""
     _require_cuda(weight)
     w = _f32(weight)
     if w.data_ptr() != weight.data_ptr():
         raise ValueError("normalisation is in place: pass a row-contiguous float32 matrix")
-    _lib.check(_lib.load().b200kge_x_normalize_rows(w.data_ptr(), w.stride(0), w.shape[0], w.shape[1], p,
+    _lib.check(_lib.load().b200kge_normalize_rows(w.data_ptr(), w.stride(0), w.shape[0], w.shape[1], p,
                                                     _stream(w.device)))
     return weight
 
@@ -412,10 +416,10 @@ def x_ns_backward(model: str, ent, rel, triples, negatives: dict, offset: float 
     return d_ent, d_rel
 
 
-def x_score_1vsN_loss_csr(model: str, combine: str, q_tab, rel, cand_tab, csr_offsets, csr_cols, q=None, p=None,
+def score_1vsN_loss_csr(model: str, combine: str, q_tab, rel, cand_tab, csr_offsets, csr_cols, q=None, p=None,
                           loss: str = "kl", offset: float = 0.0, label_smoothing: float = 0.0, l_norm: float = 1.0,
                           precision: str = "auto", return_rows: bool = False):
-    """KvsAll loss (sum over rows) with CSR multi-hot labels — see b200kge_x_score_1vsN_loss_csr."""
+    """KvsAll loss (sum over rows) with CSR multi-hot labels — see b200kge_score_1vsN_loss_csr."""
     _require_cuda(q_tab, rel, cand_tab, csr_offsets, csr_cols)
     lib, k = _lib.load(), _Keep()
     rq, rp, rc = k.rows(q_tab, q), k.rows(rel, p), k.rows(cand_tab)
@@ -425,14 +429,10 @@ def x_score_1vsN_loss_csr(model: str, combine: str, q_tab, rel, cand_tab, csr_of
     nnz = int(cols.numel())
     out = torch.empty((), dtype=torch.float32, device=dev)
     rows = torch.empty(n, dtype=torch.float32, device=dev) if return_rows else None
-    nbytes = lib.b200kge_x_score_1vsN_loss_csr_workspace_bytes(MODELS[model], n, m, rq.dim, nnz)
+    nbytes = lib.b200kge_score_1vsN_loss_csr_workspace_bytes(MODELS[model], n, m, rq.dim, nnz)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    _lib.check(lib.b200kge_x_score_1vsN_loss_csr(
+    _lib.check(lib.b200kge_score_1vsN_loss_csr(
         MODELS[model], SP_ if combine == "sp_" else _PO, l_norm, PREC[precision], C.byref(rq), C.byref(rp), C.byref(rc),
         n, offs.data_ptr(), cols.data_ptr() if nnz else None, nnz, label_smoothing, LOSS[loss], offset, out.data_ptr(),
         rows.data_ptr() if rows is not None else None, ws.data_ptr(), ws.numel(), _stream(dev)))
     return (out, rows) if return_rows else out
-
-
-# validated names of entry points that started life as experimental
-score_1vsN_loss_csr = x_score_1vsN_loss_csr

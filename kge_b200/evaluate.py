@@ -33,12 +33,14 @@ class EntityRankingEvaluator:
     def __init__(self, model, num_entities: int, filter_splits: Sequence[torch.Tensor],
                  test_triples: Optional[torch.Tensor] = None, batch_size: int = 100, chunk_size: int = -1,
                  tie_handling: str = "rounded_mean_rank", rtol: float = 1e-4, atol: float = 1e-5,
-                 hits_at_k_s: Iterable[int] = (1, 3, 10, 50, 100, 200, 300, 400, 500, 1000), device=None):
+                 hits_at_k_s: Iterable[int] = (1, 3, 10, 50, 100, 200, 300, 400, 500, 1000), device=None,
+                 warn_only: bool = False):
         if tie_handling not in ("rounded_mean_rank", "best_rank", "worst_rank"):
             raise NotImplementedError(tie_handling)       # eval_entity_ranking.py:616-618
         self.model, self.E = model, int(num_entities)
         self.batch_size, self.chunk_size = int(batch_size), int(chunk_size)
         self.tie_handling, self.rtol, self.atol = tie_handling, rtol, atol
+        self.warn_only = warn_only                                            # entity_ranking.tie_handling.warn_only
         self.hits_at_k_s = [k for k in hits_at_k_s if k <= self.E] or [1]     # :45-52 (k capped by #entities)
         self.device = device
         known = torch.cat([t.view(-1, 3).long().cpu() for t in filter_splits], 0) if len(filter_splits) else \
@@ -106,6 +108,19 @@ class EntityRankingEvaluator:
         out = {}
         for r in rankings:
             s_rank, s_ties, o_rank, o_ties = counts[r]
+            # the true answer counts as a tie of itself, so ties >= 1 in every ranking; 0 means the fused rank
+            # kernel's value at the true column left the tolerance band around the precomputed true score — the
+            # condition the reference checks at eval_entity_ranking.py:240-274 ("Error in tie-handling")
+            bad = int((s_ties < 1).sum()) + int((o_ties < 1).sum())
+            if bad:
+                msg = (f"Error in tie-handling: {bad} true answers of ranking '{r or '_raw'}' fall outside the "
+                       f"tolerance band (rtol={self.rtol}, atol={self.atol}) around their true scores")
+                if not self.warn_only:
+                    raise ValueError(msg)
+                import warnings
+                warnings.warn(msg)
+                s_ties.clamp_(min=1)
+                o_ties.clamp_(min=1)
             out["s" + r] = self._final(s_rank, s_ties)
             out["o" + r] = self._final(o_rank, o_ties)
         return out

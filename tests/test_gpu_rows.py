@@ -1,0 +1,180 @@
+"""Parity tests of the callers and rows either side of the scorer that were validated on a B200 in round 2
+(SURVEY 8f): the evaluation loop on the fused rank kernels, the reference jobs' traces re-derived on the validated
+entry points, one negative-sampling training batch, the reciprocal-relations model, Lp/N3 penalties + row
+normalisation, and the KvsAll losses with CSR multi-hot labels."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kge_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+S, P, O = 0, 1, 2
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from kge_b200 import engine
+
+    assert torch.cuda.is_available() and engine.device_ok()
+    return engine
+
+
+@pytest.mark.parametrize("model", ["complex", "transe"])
+def test_evaluator_on_gpu_matches_reference_job(model):
+    """kge_b200.evaluate.EntityRankingEvaluator driving the fused rank kernels reproduces the reference
+    EntityRankingJob's trace (host logic is covered on CPU by tests/test_evaluate_cpu.py; this adds the device
+    side: chunked subsets, dense filter planes, accumulation into rank/ties).  To be promoted into
+    tests/test_gpu_model.py once it has run green on a B200."""
+    from kge_b200 import KgeModel
+    from kge_b200.evaluate import EntityRankingEvaluator
+
+    g = _load(f"jobs_{model}.npz")
+    E, D = g["ent"].shape
+    m = KgeModel(model, E, g["rel"].shape[0], D).cuda()
+    with torch.no_grad():
+        m.get_s_embedder().weight.copy_(g["ent"].cuda())
+        m.get_p_embedder().weight.copy_(g["rel"].cuda())
+    for bs, chunk in ((16, -1), (100, 7)):
+        ev = EntityRankingEvaluator(m, E, [g["train"], g["valid"]], g["test"], batch_size=bs, chunk_size=chunk,
+                                    hits_at_k_s=(1, 3, 10), device="cuda")
+        met = ev.evaluate(g["valid"])
+        for suffix in ("", "_filtered", "_filtered_with_test"):
+            for k in ("mean_rank", "mean_reciprocal_rank", "hits_at_1", "hits_at_3", "hits_at_10"):
+                want = float(g["valid_" + k + suffix])
+                assert abs(met[k + suffix] - want) <= 1e-6 * max(1.0, abs(want)), (k + suffix, met[k + suffix], want)
+
+
+@pytest.mark.parametrize("model", ["complex", "transe"])
+def test_job_traces_on_gpu(eng, model):
+    """Job-level traces of the reference (tests/golden/jobs_*.npz) through validated entry points only: 1vsAll
+    epoch loss, KvsAll epochs with multi-hot / smoothed labels.  Gated until it has run once on a B200."""
+    g = _load(f"jobs_{model}.npz")
+    ent, rel, train = g["ent"].cuda(), g["rel"].cuda(), g["train"].long().cuda()
+    E = ent.shape[0]
+    for loss in ("bce", "kl"):
+        got = float(eng.train_1vsall_forward(model, ent, rel, train, loss))
+        want = float(g[f"avg_loss_{loss}"])
+        assert abs(got - want) <= 1e-4 * abs(want), (loss, got, want)
+
+    def examples(key_cols, val_col):
+        keys, inv = torch.unique(train[:, key_cols], dim=0, return_inverse=True)
+        labels = torch.zeros((keys.shape[0], E), device="cuda")
+        labels.index_put_((inv, train[:, val_col]), torch.ones(len(train), device="cuda"), accumulate=True)
+        return keys, labels
+
+    sp_keys, sp_lab = examples([S, P], O)
+    po_keys, po_lab = examples([P, O], S)
+    n = sp_keys.shape[0] + po_keys.shape[0]
+    for loss, eps in (("kl", 0.0), ("kl", 0.2), ("bce", 0.2)):
+        lab = (lambda y: (1.0 - eps) * y + 1.0 / E) if eps > 0 else (lambda y: y)
+        l_sp = eng.score_1vsN_loss(model, "sp_", ent, rel, ent, lab(sp_lab), sp_keys[:, 0].contiguous(),
+                                   sp_keys[:, 1].contiguous(), None, loss, 0.0)
+        l_po = eng.score_1vsN_loss(model, "_po", ent, rel, ent, lab(po_lab), po_keys[:, 1].contiguous(),
+                                   po_keys[:, 0].contiguous(), None, loss, 0.0)
+        got = (float(l_sp) + float(l_po)) / n
+        want = float(g[f"kvsall_avg_loss_{loss}_{int(eps * 10)}"])
+        assert abs(got - want) <= 1e-4 * abs(want), (loss, eps, got, want)
+
+
+@pytest.mark.parametrize("model", ["complex", "rotate"])
+def test_ns_job_batch_on_gpu(eng, model):
+    g = _load(f"nsjob_{model}.npz")
+    ent, rel, tri = g["ent"].cuda(), g["rel"].cuda(), g["triples"].long().cuda()
+    n, off = tri.shape[0], float(g["offset"])
+    total = 0.0
+    for slot, nm in ((S, "s"), (P, "p"), (O, "o")):
+        neg = g[f"neg_{nm}"].long().cuda()
+        scores = eng.ns_score(model, ent, rel, tri, neg, slot, True)
+        labels = torch.zeros_like(scores)
+        labels[:, 0] = 1.0
+        total += float(eng.loss_dense(scores, labels, "bce", off)) / n
+    assert abs(total - float(g["avg_loss"])) <= 1e-4 * abs(float(g["avg_loss"])), (total, float(g["avg_loss"]))
+
+
+@pytest.mark.parametrize("base", ["complex", "transe"])
+def test_reciprocal_model_on_gpu(base):
+    """kge_b200.ReciprocalRelationsModel (index arithmetic over validated `sp_` entry points) against the live
+    reference's ReciprocalRelationsModel.  Gated until it has run once on a B200."""
+    from kge_b200 import ReciprocalRelationsModel
+
+    g = _load(f"reciprocal_{base}.npz")
+    E, D = g["ent"].shape
+    R = int(g["num_relations"])
+    m = ReciprocalRelationsModel(base, E, R, D).cuda()
+    with torch.no_grad():
+        m.get_s_embedder().weight.copy_(g["ent"].cuda())
+        m.get_p_embedder().weight.copy_(g["rel2"].cuda())
+    tri, sub = g["triples"].long().cuda(), g["subset"].long().cuda()
+    s, p, o = tri[:, S].contiguous(), tri[:, P].contiguous(), tri[:, O].contiguous()
+    _assert_close(m.score_spo(s, p, o, "o"), g["spo_o"], "spo o")
+    _assert_close(m.score_spo(s, p, o, "s"), g["spo_s"], "spo s")
+    _assert_close(m.score_sp(s, p), g["sp"], "sp")
+    _assert_close(m.score_po(p, o), g["po"], "po")
+    _assert_close(m.score_po(p, o, sub), g["po_subset"], "po subset")
+    _assert_close(m.score_sp_po(s, p, o), g["sp_po"], "sp_po")
+    _assert_close(m.score_sp_po(s, p, o, sub), g["sp_po_subset"], "sp_po subset")
+
+
+def test_penalties_and_normalisation_golden(eng):
+    """Row kernels for Lp / N3 penalties and normalisation against the live reference (penalties.npz)."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from gen_golden import PENALTY_CASES
+
+    g = _load("penalties.npz")
+    for tag, model, eo, ro in PENALTY_CASES:
+        space = "complex" if model == "complex" else "euclidean"
+        ent, rel, tri = g[f"{tag}_ent"].cuda(), g[f"{tag}_rel"].cuda(), g[f"{tag}_triples"].long().cuda()
+
+        def pen(w, o, idx):
+            return float(eng.lookup_penalty(w, o["regularize"], o["regularize_weight"], float(o["p"]), o["weighted"],
+                                              idx if o["weighted"] else None, space))
+
+        total = pen(rel, ro, tri[:, P])
+        total += pen(ent, eo, tri[:, [S, O]]) if eo["weighted"] else 2.0 * pen(ent, eo, None)
+        want = float(g[f"{tag}_total"])
+        assert abs(total - want) <= 1e-5 * abs(want), (tag, total, want)
+    for pn in (1, 2):
+        w = g["normalize_in"].cuda().clone()
+        eng.normalize_rows_(w, float(pn))
+        assert torch.allclose(w.cpu(), g[f"normalize_p{pn}"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("model,D", [("complex", 128), ("distmult", 32), ("rescal", 24), ("cp", 64), ("transe", 64), ("rotate", 64)])
+@pytest.mark.parametrize("loss", ["bce", "kl"])
+def test_loss_with_csr_labels(eng, model, D, loss):
+    """KvsAll losses with CSR multi-hot labels (duplicates, empty rows, label smoothing) against the oracle on the
+    densified label matrix; both directions."""
+    E, R, n = 3001, 5, 200
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.3)
+    tri = orc.make_triples(E, R, n)
+    g = torch.Generator().manual_seed(3)
+    counts = (torch.rand((n, E), generator=g) < 0.004).float()
+    counts[torch.arange(n), tri[:, O]] += 1.0
+    counts[5, int(tri[5, O])] += 1.0          # a duplicate triple: label 2
+    counts[7] = 0.0                            # a row without labels
+    rows, cols = torch.nonzero(counts, as_tuple=True)
+    rep = counts[rows, cols].long()
+    cols_rep = torch.repeat_interleave(cols, rep)
+    rows_rep = torch.repeat_interleave(rows, rep)
+    offs = torch.zeros(n + 1, dtype=torch.int64)
+    offs[1:] = torch.cumsum(torch.bincount(rows_rep, minlength=n), 0)
+    ce, cr = ent.cuda(), rel.cuda()
+    off = 1.0 if loss == "bce" else 0.0
+    fn = (lambda x, y: orc.bce_loss(x, y, off)) if loss == "bce" else orc.kl_loss
+    dot = model in ("complex", "distmult", "rescal", "cp")
+    for combine, qi, sc in (("sp_", tri[:, S], orc.score_sp(model, ent, rel, tri[:, S], tri[:, P])),
+                            ("_po", tri[:, O], orc.score_po(model, ent, rel, tri[:, P], tri[:, O]))):
+        for eps in ((0.0, 0.1) if dot else (0.0,)):
+            lab = orc.kvsall_smooth_labels(counts, eps) if eps > 0 else counts
+            ref = float(fn(sc, lab))
+            got, rws = eng.score_1vsN_loss_csr(model, combine, ce, cr, ce, offs.cuda(), cols_rep.cuda(), qi.cuda(),
+                                                 tri[:, P].cuda(), loss, off, eps, return_rows=True)
+            assert abs(float(got) - ref) <= 1e-4 * abs(ref), (model, loss, combine, eps, float(got), ref)
+            assert abs(float(rws.sum()) - ref) <= 1e-4 * abs(ref)
