@@ -169,6 +169,26 @@ int b200kge_score_1vsN_rank(int model, int combine, float l_norm, int precision,
                             int64_t* rank, int64_t* ties, void* workspace, size_t workspace_bytes,
                             b200kge_stream_t stream);
 
+/* Both directions of the ranking of one batch in ONE launch sequence: rows 0..n-1 are the sp_ queries (ranked
+ * against true_score[0..n)), rows n..2n-1 the _po queries (true_score[n..2n)); rank/ties are int64 [2n] in the
+ * same order and are ACCUMULATED INTO; filter (optional) is [2n, ldf] in the same row order.  This is what
+ * EntityRankingJob does per chunk with score_sp_po + _filter_and_rank + _get_ranks_and_num_ties
+ * (eval_entity_ranking.py:222-229,533-596) without materialising the [n, 2m] scores.  CP (whose directions read
+ * different candidate columns) returns B200KGE_ERR_UNSUPPORTED: call b200kge_score_1vsN_rank per direction. */
+int b200kge_rank_sp_po(int model, float l_norm, int precision, const b200kge_rows_t* s,
+                       const b200kge_rows_t* p, const b200kge_rows_t* o, const b200kge_rows_t* cand,
+                       int64_t n, const float* true_score, const float* filter, int64_t ldf, float rtol,
+                       float atol, int64_t* rank, int64_t* ties, void* workspace, size_t workspace_bytes,
+                       b200kge_stream_t stream);
+
+/* Entity-sharded tables: this rank owns global rows [lo, lo + shard->rows) of the entity table.
+ * out[i, :] = shard row (idx[i] - lo) if the rank owns global id idx[i], else zeros — the contribution of this rank
+ * to the query-row exchange (sum over ranks == the gathered rows, exactly: every other rank adds zeros).  One
+ * kernel, no host synchronisation (the reference's LookupEmbedder.embed, lookup_embedder.py:96-97, on a
+ * partitioned table). */
+int b200kge_shard_gather_rows(const b200kge_rows_t* shard, int64_t lo, const int64_t* idx, int64_t n,
+                              float* out, int64_t ldo, b200kge_stream_t stream);
+
 /* Dense-score epilogues (for callers that already hold a score matrix) ------------------------ */
 /* KgeLoss on a dense [n,m] score matrix: loss.py:153-159 (BCE) / :198-213 (KL). */
 int b200kge_loss_dense(const float* scores, int64_t lds, int64_t n, int64_t m,

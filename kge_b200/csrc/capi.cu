@@ -259,6 +259,16 @@ __global__ void unpack_triples_kernel(const int64_t* __restrict__ tri, int64_t n
   }
 }
 
+__global__ void __launch_bounds__(128)
+shard_gather_rows_kernel(Rows shard, int64_t lo, const int64_t* __restrict__ idx, float* __restrict__ out, int64_t ldo) {
+  const int64_t i = blockIdx.x;
+  const int64_t g = idx[i] - lo;
+  const bool mine = g >= 0 && g < shard.rows;
+  const float* __restrict__ src = shard.base + (mine ? g : 0) * shard.ld;
+  float* __restrict__ dst = out + i * ldo;
+  for (int k = threadIdx.x; k < shard.dim; k += blockDim.x) dst[k] = mine ? src[k] : 0.f;
+}
+
 }  // namespace
 }  // namespace b200kge
 
@@ -396,6 +406,36 @@ int b200kge_score_1vsN_rank(int model, int combine, float l_norm, int precision,
   P.ties = reinterpret_cast<unsigned long long*>(ties);
   Block B{model, combine, &Q, nullptr, &Pr, &C, n};
   return run_block(B, l_norm, precision, EPI_RANK, P, ws, (cudaStream_t)stream, nullptr);
+}
+
+int b200kge_rank_sp_po(int model, float l_norm, int precision, const b200kge_rows_t* s,
+                       const b200kge_rows_t* p, const b200kge_rows_t* o, const b200kge_rows_t* cand,
+                       int64_t n, const float* true_score, const float* filter, int64_t ldf, float rtol,
+                       float atol, int64_t* rank, int64_t* ties, void* workspace, size_t workspace_bytes,
+                       b200kge_stream_t stream) {
+  int rc = check_1vsN_args(model, B200KGE_SP_, s, p, cand, n); if (rc) return rc;
+  if ((rc = check_1vsN_args(model, B200KGE__PO, o, p, cand, n))) return rc;
+  if ((rc = validate_norm(model, l_norm))) return rc;
+  if (!true_score || !rank || !ties) { set_error("null rank operand"); return B200KGE_ERR_INVALID; }
+  Rows Sr = to_rows(s), Pr = to_rows(p), Or = to_rows(o), C = to_rows(cand);
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  EpiParams P = empty_epi();
+  P.true_score = true_score; P.filter = filter; P.ldf = ldf; P.rtol = rtol; P.atol = atol;
+  P.rank = reinterpret_cast<unsigned long long*>(rank);
+  P.ties = reinterpret_cast<unsigned long long*>(ties);
+  Block B{model, B200KGE_SP_, &Sr, &Or, &Pr, &C, n};
+  return run_block(B, l_norm, precision, EPI_RANK, P, ws, (cudaStream_t)stream, nullptr);
+}
+
+int b200kge_shard_gather_rows(const b200kge_rows_t* shard, int64_t lo, const int64_t* idx, int64_t n,
+                              float* out, int64_t ldo, b200kge_stream_t stream) {
+  if (!shard || (!idx && n > 0) || (!out && n > 0)) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  if (shard->idx) { set_error("shard must be a plain table (idx == NULL)"); return B200KGE_ERR_INVALID; }
+  if (ldo < shard->dim) { set_error("output row stride smaller than the row width"); return B200KGE_ERR_INVALID; }
+  if (n <= 0) return 0;
+  shard_gather_rows_kernel<<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(to_rows(shard), lo, idx, out, ldo);
+  B2K_LAUNCH_CHECK("shard_gather_rows_kernel");
+  return 0;
 }
 
 int b200kge_loss_dense(const float* scores, int64_t lds, int64_t n, int64_t m,

@@ -48,7 +48,8 @@ constexpr int TMEM_COLS = 512;
 struct Tc4Params {
   int64_t nq, m;
   int nk;                          // K chunks of 64 halfs
-  int q_tiles, e_tiles, echunks;   // q tiles of 256 rows, e tiles of 256 rows
+  int q_tiles, e_tiles, echunks;   // q tiles of 256 rows, e tiles of tn rows
+  int tn;                          // entities per cluster tile (multiple of 32, <= 256); each CTA stages tn/2
   const float* q_scale;            // [nq]
   const float* t_scale;            // [m + 32], zero beyond m
   EpiParams epi;
@@ -113,12 +114,13 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
     // ================================ TMA producer (both CTAs) ==============================
     if (lane == 0) {
       uint32_t c = 0;
+      const uint32_t slot_tx = (uint32_t)(A_BYTES + (prm.tn >> 1) * TKH * 2);   // bytes one CTA lands per slot
       for (int w = cluster_id; w < total_work; w += nclusters) {
         int qt, et0, et1, ec;
         work_range(w, qt, et0, et1, ec);
         const int q_row = qt * 256 + (int)rank * TM;
         for (int et = et0; et < et1; ++et) {
-          const int e_row = et * TN + (int)rank * TNH;
+          const int e_row = et * prm.tn + (int)rank * (prm.tn >> 1);
           for (int kc = 0; kc < nk; ++kc, ++c) {
             const int s0 = slot_of(c);
             const uint32_t ph = phase_of(c);
@@ -130,11 +132,11 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
               if (DIRECT) {
                 // completion of BOTH CTAs' boxes is counted on the leader's barrier
                 const uint32_t bar = ptx::mapa(ptx::smem_u32(&full[s]), 0);
-                if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * SLOT_BYTES);
+                if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * slot_tx);
                 ptx::tma_load_2d_cluster_bar(sp, h ? &tmQl : &tmQh, bar, kc * TKH, q_row);
                 ptx::tma_load_2d_cluster_bar(sp + A_BYTES, h ? &tmTl : &tmTh, bar, kc * TKH, e_row);
               } else {
-                ptx::mbar_arrive_expect_tx(&full[s], SLOT_BYTES);
+                ptx::mbar_arrive_expect_tx(&full[s], slot_tx);
                 ptx::tma_load_2d(sp, h ? &tmQl : &tmQh, &full[s], kc * TKH, q_row);
                 ptx::tma_load_2d(sp + A_BYTES, h ? &tmTl : &tmTh, &full[s], kc * TKH, e_row);
               }
@@ -146,7 +148,7 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA only) ===========================
     if (rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_f16(256, TN);
+      const uint32_t idesc = ptx::umma_idesc_f16(256, prm.tn);
       uint64_t* ready = DIRECT ? full : landed;
       uint32_t c = 0, it = 0;
       for (int w = cluster_id; w < total_work; w += nclusters) {
@@ -223,10 +225,11 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
         const int b = it & 1;
         ptx::mbar_wait_cluster_bounded(&tfull[b], (it >> 1) & 1);
         ptx::tc_fence_after();
+        const int64_t tile_end = (int64_t)(et + 1) * prm.tn;
         tc::epilogue_tile<EPI, 4, true>(P, st, aux,
                                         tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TN + half * 128),
-                                        row0, (int64_t)et * TN + half * 128, prm.nq, prm.m, my_stg, lane, qs,
-                                        prm.t_scale);
+                                        row0, (int64_t)et * prm.tn + half * 128, prm.nq,
+                                        tile_end < prm.m ? tile_end : prm.m, my_stg, lane, qs, prm.t_scale);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty[b]), 0));
@@ -245,12 +248,25 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
   }
 }
 
-void plan4(int64_t nq, int64_t m, int& q_tiles, int& e_tiles, int& echunks) {
+// same policy as plan3 (pairwise_tc3.cu) with CTA pairs as the scheduling unit: tile width (multiple of 32 in
+// [128, 256]: each CTA stages tn/2 rows, which must stay a multiple of the 8-row swizzle atom) minimising the per-cluster makespan in columns; entity tiles split into `echunks` ranges so that
+// q_tiles * echunks ~ #clusters
+void plan4(int64_t nq, int64_t m, int& q_tiles, int& e_tiles, int& echunks, int& tn) {
   q_tiles = (int)((nq + 255) / 256);
   if (q_tiles < 1) q_tiles = 1;
-  e_tiles = (int)((m + TN - 1) / TN);
-  const int nclusters = tc::num_sms() / 2;
-  int per = nclusters / q_tiles;
+  const int units = tc::num_sms() / 2;
+  int64_t best_cost = -1;
+  tn = TN;
+  for (int cand = TN; cand >= 128; cand -= 32) {
+    const int64_t et = (m + cand - 1) / cand;
+    int per = units / q_tiles; if (per < 1) per = 1; if (per > et) per = (int)et;
+    const int64_t tiles_per_cl = (et + per - 1) / per;
+    const int64_t waves = ((int64_t)q_tiles * per + units - 1) / units;
+    const int64_t cost = waves * tiles_per_cl * cand + tiles_per_cl * 24;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; tn = cand; }
+  }
+  e_tiles = (int)((m + tn - 1) / tn);
+  int per = units / q_tiles;
   if (per < 1) per = 1;
   if (per > e_tiles) per = e_tiles;
   echunks = per;
@@ -280,8 +296,8 @@ int launch_e4(bool, const CUtensorMap& qh, const CUtensorMap& ql, const CUtensor
 }  // namespace
 
 int tc4_nchunks(int64_t nq, int64_t m) {
-  int qt, et, ec;
-  plan4(nq, m, qt, et, ec);
+  int qt, et, ec, tn;
+  plan4(nq, m, qt, et, ec, tn);
   return 2 * ec;
 }
 
@@ -291,14 +307,14 @@ int launch_pairwise_tc4(int epi_kind, const SplitSet& Q, const SplitSet& T, cons
   if (Q.Kp != T.Kp || Q.Kp % TKH != 0) { set_error("operand planes disagree on the padded reduction length"); return B200KGE_ERR_INVALID; }
   Tc4Params prm;
   prm.nq = nq; prm.m = m; prm.nk = Q.Kp / TKH;
-  plan4(nq, m, prm.q_tiles, prm.e_tiles, prm.echunks);
+  plan4(nq, m, prm.q_tiles, prm.e_tiles, prm.echunks, prm.tn);
   prm.q_scale = Q.inv_scale; prm.t_scale = T.inv_scale;
   CUtensorMap mQh, mQl, mTh, mTl;
   int rc;
   if ((rc = tc::make_map_f16(&mQh, Q.hi, nq, Q.Kp, Q.Kp, TM))) return rc;
   if ((rc = tc::make_map_f16(&mQl, Q.lo, nq, Q.Kp, Q.Kp, TM))) return rc;
-  if ((rc = tc::make_map_f16(&mTh, T.hi, m, T.Kp, T.Kp, TNH))) return rc;
-  if ((rc = tc::make_map_f16(&mTl, T.lo, m, T.Kp, T.Kp, TNH))) return rc;
+  if ((rc = tc::make_map_f16(&mTh, T.hi, m, T.Kp, T.Kp, prm.tn >> 1))) return rc;
+  if ((rc = tc::make_map_f16(&mTl, T.lo, m, T.Kp, T.Kp, prm.tn >> 1))) return rc;
   prm.epi = P;
   prm.epi.nchunks = 2 * prm.echunks;   // two epilogue warps (column halves) per row
   const char* e = getenv("B200KGE_TC4_DIRECT");

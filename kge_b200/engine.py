@@ -134,19 +134,72 @@ def score_1vsN(model: str, combine: str, q_tab, rel, cand_tab, q=None, p=None, c
 
 
 def score_sp_po(model: str, ent, rel, s, p, o, entity_subset=None, l_norm: float = 1.0,
-                precision: str = "auto"):
-    """[n, 2m] = [score_sp | score_po] in one launch sequence (kge_model.py:749-789)."""
+                precision: str = "auto", out: Optional[torch.Tensor] = None, ent_o=None, cand_tab=None):
+    """[n, 2m] = [score_sp | score_po] in one launch sequence (kge_model.py:749-789).
+
+    Index level: ent / rel are the tables, s / p / o index vectors.  Embedding level (s = p = o = None): ent, rel,
+    ent_o are already-gathered [n, .] subject / relation / object rows and cand_tab the candidate table.
+    `out` (optional) is a caller-owned [n, >= 2m] float32 block with unit column stride (e.g. a slice of an
+    all-gather buffer): the two halves are written at columns [0, m) and [m, 2m)."""
     _require_cuda(ent, rel)
     lib, k = _lib.load(), _Keep()
-    rs, rp, ro = k.rows(ent, s), k.rows(rel, p), k.rows(ent, o)
-    rc = k.rows(ent, entity_subset)
+    rs, rp, ro = k.rows(ent, s), k.rows(rel, p), k.rows(ent if ent_o is None else ent_o, o)
+    rc = k.rows(ent if cand_tab is None else cand_tab, entity_subset)
     n, m = int(rs.rows), int(rc.rows)
     dev = ent.device
-    out = torch.empty((n, 2 * m), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((n, 2 * m), dtype=torch.float32, device=dev)
+    elif out.dtype != torch.float32 or out.stride(1) != 1 or out.shape[0] < n or out.shape[1] < 2 * m:
+        raise ValueError("out must be a float32 [n, >= 2m] block with unit column stride")
     ws = _workspace(MODELS[model], n, m, rs.dim, entity_subset is not None, dev)
     _lib.check(lib.b200kge_score_sp_po(MODELS[model], l_norm, PREC[precision], C.byref(rs), C.byref(rp),
                                        C.byref(ro), C.byref(rc), n, out.data_ptr(), out.stride(0),
                                        ws.data_ptr(), ws.numel(), _stream(dev)))
+    return out
+
+
+def rank_sp_po(model: str, s_tab, rel, o_tab, cand_tab, true_scores, s=None, p=None, o=None, cand=None,
+               filter_labels=None, rtol: float = 1e-4, atol: float = 1e-5, l_norm: float = 1.0,
+               precision: str = "auto", rank=None, ties=None):
+    """Both directions of one batch's ranking against one chunk of candidates in ONE launch sequence: rows
+    0..n-1 = sp_ queries, n..2n-1 = _po queries; true_scores / rank / ties are [2n] in that order (rank / ties
+    int64, accumulated into); filter_labels (optional) [2n, m]."""
+    _require_cuda(s_tab, rel, o_tab, cand_tab, true_scores, filter_labels)
+    lib, k = _lib.load(), _Keep()
+    rs, rp, ro, rc = k.rows(s_tab, s), k.rows(rel, p), k.rows(o_tab, o), k.rows(cand_tab, cand)
+    n, m = int(rs.rows), int(rc.rows)
+    dev = s_tab.device
+    t = true_scores.reshape(-1).float().contiguous()
+    if t.numel() != 2 * n:
+        raise ValueError("true_scores must hold 2n values: sp_ rows first, then _po rows")
+    if rank is None:
+        rank = torch.zeros(2 * n, dtype=torch.int64, device=dev)
+    if ties is None:
+        ties = torch.zeros(2 * n, dtype=torch.int64, device=dev)
+    f = None
+    if filter_labels is not None:
+        f = filter_labels if (filter_labels.dtype == torch.float32 and filter_labels.stride(1) == 1) \
+            else filter_labels.float().contiguous()
+    ws = _workspace(MODELS[model], n, m, rs.dim, cand is not None, dev)
+    _lib.check(lib.b200kge_rank_sp_po(
+        MODELS[model], l_norm, PREC[precision], C.byref(rs), C.byref(rp), C.byref(ro), C.byref(rc), n, t.data_ptr(),
+        f.data_ptr() if f is not None else None, f.stride(0) if f is not None else 0, rtol, atol, rank.data_ptr(),
+        ties.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
+    return rank, ties
+
+
+def shard_gather_rows(shard: torch.Tensor, lo: int, idx: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """This rank's contribution to the query-row exchange of an entity-sharded table: out[i] = shard[idx[i] - lo]
+    if lo <= idx[i] < lo + rows else 0 (one kernel, no host synchronisation)."""
+    _require_cuda(shard, idx)
+    lib, k = _lib.load(), _Keep()
+    rsh = k.rows(shard)
+    ix = _i64(idx)
+    n = ix.numel()
+    if out is None:
+        out = torch.empty((n, shard.shape[1]), dtype=torch.float32, device=shard.device)
+    _lib.check(lib.b200kge_shard_gather_rows(C.byref(rsh), int(lo), ix.data_ptr(), n, out.data_ptr(), out.stride(0),
+                                             _stream(shard.device)))
     return out
 
 

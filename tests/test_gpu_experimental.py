@@ -30,6 +30,20 @@ def eng():
     return engine
 
 
+def _load(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    return {k: torch.from_numpy(z[k]) if z[k].ndim else z[k].item() for k in z.files}
+
+
+def _assert_close(got, ref, what, tol=TOL):
+    got = got.detach().cpu().double()
+    ref = ref.double()
+    assert got.shape == ref.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    rms = max(float(ref.pow(2).mean().sqrt()), 1e-6)
+    err = float((got - ref).abs().max()) if ref.numel() else 0.0
+    assert err <= tol * rms, f"{what}: max|d|={err:.3e} rms={rms:.3e} ratio={err / rms:.2e}"
+
+
 def test_x_gemm_nt_vs_fp64(eng):
     """Pre-split fp16 GEMM (the backward's building block; also exercises presplit + pairwise_tc3 on shapes
     the scorer never sees: long reductions, few rows, K not a multiple of 64, tiny and huge magnitudes)."""
