@@ -608,9 +608,15 @@ size_t planes_bytes(int64_t rows, int64_t rows_pad, int64_t Kp) {
 }
 
 // C[M,N] = A B^T on planes: A = "queries" (rows M), B = "table" (rows N, inv_scale padded to N+32)
+// Long reductions are split into 512-element segments accumulated in fp32 (C is zeroed here first).
 int gemm_planes(const SplitSet& A, const SplitSet& B, float* C, int64_t ldc, cudaStream_t st) {
   EpiParams P = empty_epi();
   P.out = C; P.ldo = ldc;
+  if (A.Kp > 512) {
+    P.accumulate_out = 1;
+    cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)B.rows * 4, (size_t)A.rows, st);
+    if (e != cudaSuccess) return check_cuda(e, "cudaMemset2DAsync(gemm output)");
+  }
   return launch_pairwise_tc3(EPI_STORE, A, B, P, st);
 }
 

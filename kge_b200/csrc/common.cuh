@@ -99,6 +99,8 @@ struct EpiParams {
   // r % n_rows_out and column block (r / n_rows_out) * col_block
   int64_t n_rows_out;
   int64_t col_block;
+  // EPI_STORE, GEMM use (pairwise_tc3.cu split-K): add into `out` (zeroed by the caller) instead of overwriting it
+  int accumulate_out;
 };
 
 #define B2K_NEG_HUGE (-3.0e38f)

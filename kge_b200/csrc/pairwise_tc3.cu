@@ -58,6 +58,8 @@ struct Tc3Params {
   int nk;           // K chunks of 64 halfs (planes are zero padded to nk * 64)
   int q_tiles, e_tiles, echunks;
   int tn;           // entities per tile (multiple of 16, <= TN)
+  int ksplit;       // > 1: split-K GEMM mode (EPI_STORE only): the reduction is cut into `ksplit` segments of `kseg`
+  int kseg;         //      K chunks; every (tile, segment) is its own work item and ADDS into the zeroed output
   const float* q_scale;   // [nq]
   const float* t_scale;   // [m + 32], zero beyond m
   EpiParams epi;
@@ -83,7 +85,7 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = prm.nk;
-  const int total_work = prm.q_tiles * prm.echunks;
+  const int total_work = prm.q_tiles * prm.echunks * prm.ksplit;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmQh);
@@ -106,7 +108,14 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  int k0 = 0, k1 = nk;      // K-chunk range of the current work item (split-K mode: one segment)
   auto work_range = [&](int w, int& qt, int& et0, int& et1, int& ec) {
+    if (prm.ksplit > 1) {
+      const int ks = w % prm.ksplit;
+      w /= prm.ksplit;
+      k0 = ks * prm.kseg;
+      k1 = (k0 + prm.kseg < nk) ? k0 + prm.kseg : nk;
+    }
     qt = w / prm.echunks;
     ec = w - qt * prm.echunks;
     const int base = prm.e_tiles / prm.echunks, rem = prm.e_tiles % prm.echunks;
@@ -123,7 +132,7 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
         int qt, et0, et1, ec;
         work_range(w, qt, et0, et1, ec);
         for (int et = et0; et < et1; ++et) {
-          for (int kc = 0; kc < nk; ++kc, ++c) {
+          for (int kc = k0; kc < k1; ++kc, ++c) {
             const uint32_t par = ((c / NPAIR) & 1) ^ 1;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -151,7 +160,7 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
           ptx::mbar_wait_bounded(&tempty[b], ((it >> 1) & 1) ^ 1);   // epilogue drained this accumulator
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(b * TN);
-          for (int kc = 0; kc < nk; ++kc, ++c) {
+          for (int kc = k0; kc < k1; ++kc, ++c) {
             const int sh = 2 * (int)(c % NPAIR), sl = sh + 1;
             const uint32_t par = (c / NPAIR) & 1;
             const uint32_t a_hi = ptx::smem_u32(smem + sh * SLOT_BYTES), b_hi = a_hi + A_BYTES;
@@ -161,7 +170,7 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
 #pragma unroll
             for (int k = 0; k < TKH / 16; ++k)
               ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc,
-                             (kc > 0 || k > 0) ? 1u : 0u);
+                             (kc > k0 || k > 0) ? 1u : 0u);
             ptx::mbar_wait_bounded(&full[sl], par);
             ptx::tc_fence_after();
 #pragma unroll
@@ -282,6 +291,16 @@ int launch_pairwise_tc3(int epi_kind, const SplitSet& Q, const SplitSet& T, cons
   Tc3Params prm;
   prm.nq = nq; prm.m = m; prm.nk = Q.Kp / tkh;
   plan3(nq, m, prm.q_tiles, prm.e_tiles, prm.echunks, prm.tn);
+  prm.ksplit = 1; prm.kseg = prm.nk;
+  if (P.accumulate_out) {
+    // split-K GEMM: segments of 8 chunks (512 reduction elements) bound the tensor core's accumulator error, which
+    // grows with the reduction length (2.4e-5 of rms at K=512, 2.8e-4 at K=14541: profiles/r2_summary.md); segment
+    // results are added in fp32 by the epilogue (red.global.add).  One entity tile per work item.
+    if (epi_kind != EPI_STORE) { set_error("split-K accumulation is a GEMM (store) mode"); return B200KGE_ERR_INVALID; }
+    prm.kseg = 8;
+    prm.ksplit = (prm.nk + prm.kseg - 1) / prm.kseg;
+    prm.echunks = prm.e_tiles;
+  }
   prm.q_scale = Q.inv_scale; prm.t_scale = T.inv_scale;
   CUtensorMap mQh, mQl, mTh, mTl;
   int rc;
@@ -291,7 +310,7 @@ int launch_pairwise_tc3(int epi_kind, const SplitSet& Q, const SplitSet& T, cons
   if ((rc = tc::make_map_f16(&mTl, T.lo, m, T.Kp, T.Kp, prm.tn, tkh))) return rc;
   prm.epi = P;
   prm.epi.nchunks = 2 * prm.echunks;   // two epilogue warps (column halves) per row
-  const int total = prm.q_tiles * prm.echunks;
+  const int total = prm.q_tiles * prm.echunks * prm.ksplit;
   const int grid = total < num_sms() ? total : num_sms();
   switch (epi_kind) {
     case EPI_STORE: return launch_k3<EPI_STORE>(tkh, mQh, mQl, mTh, mTl, prm, grid, st);

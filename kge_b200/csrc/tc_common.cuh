@@ -259,7 +259,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& P, RowState<EPI>&
         float t[32];
 #pragma unroll
         for (int rr = 0; rr < 32; ++rr) t[rr] = my_stg[rr * STG_LD + lane];
-        if (col < m) {
+        if (col < m && P.accumulate_out) {
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr)
+            if (rr < nrows) atomicAdd(p + rr * P.ldo, t[rr]);
+        } else if (col < m) {
           if (nrows == 32) {
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr) p[rr * P.ldo] = t[rr];

@@ -32,6 +32,20 @@ import torch.distributed as dist
 class EngineBackend:
     """Local-shard scoring on the GPU through libb200kge."""
 
+    def exchange_rows(self, shard, lo, idx):
+        from . import engine
+        return engine.shard_gather_rows(shard, lo, idx)
+
+    def score_sp_po(self, model, s_emb, rel, p, o_emb, cand, l_norm, precision, out=None):
+        from . import engine
+        return engine.score_sp_po(model, s_emb, rel, None, p, None, None, l_norm, precision, out=out, ent_o=o_emb,
+                                  cand_tab=cand)
+
+    def rank_sp_po(self, model, s_emb, rel, p, o_emb, cand, true2n, filter2n, rtol, atol, l_norm, precision):
+        from . import engine
+        return engine.rank_sp_po(model, s_emb, rel, o_emb, cand, true2n, None, p, None, None, filter2n, rtol, atol,
+                                 l_norm, precision)
+
     def score_1vsN(self, model, combine, q_emb, p_emb, cand, l_norm, precision):
         from . import engine
         return engine.score_1vsN(model, combine, q_emb, p_emb, cand, l_norm=l_norm, precision=precision)
@@ -84,61 +98,78 @@ class ShardedKgeModel:
 
     # -- step 1: query-row exchange ------------------------------------------------------------------
     def gather_entity_rows(self, idx: torch.Tensor) -> torch.Tensor:
-        """[n, D] rows of the GLOBAL entity table for global ids `idx`, on every rank."""
-        idx = idx.long()
-        out = torch.zeros((idx.numel(), self.ent.shape[1]), dtype=self.ent.dtype, device=self.ent.device)
-        mine = (idx >= self.lo) & (idx < self.hi)
-        if bool(mine.any()):
-            out[mine] = self.ent[idx[mine] - self.lo]
-        return self._all_reduce(out)          # every other rank contributed exact zeros: sum == copy
+        """[n, D] rows of the GLOBAL entity table for global ids `idx`, on every rank: each rank writes the rows it
+        owns (zeros elsewhere; one kernel, no host synchronisation), then one all-reduce(sum) — every other rank
+        contributed exact zeros, so the sum is a copy."""
+        out = self.backend.exchange_rows(self.ent, self.lo, idx.long())
+        return self._all_reduce(out)
 
     def _queries(self, s, p, o):
         both = self.gather_entity_rows(torch.cat([s.long(), o.long()]))
         n = s.numel()
-        return both[:n], self.rel[p.long()], both[n:]
+        return both[:n], p.long(), both[n:], both
 
     # -- full logits ---------------------------------------------------------------------------------
     def score_sp_po(self, s, p, o) -> torch.Tensor:
-        """[n, 2E] = [score_sp | score_po] (kge_model.py:749-789) assembled from per-shard logits."""
-        s_emb, p_emb, o_emb = self._queries(s, p, o)
+        """[n, 2E] = [score_sp | score_po] (kge_model.py:749-789) assembled from per-shard logits: both directions
+        of the shard are scored by ONE stacked launch straight into this rank's slot of the all-gather buffer."""
+        s_emb, pi, o_emb, _ = self._queries(s, p, o)
         n = s.numel()
-        loc = torch.zeros((2, n, self.per), dtype=torch.float32, device=self.ent.device)
         m = self.hi - self.lo
-        if m > 0:
-            loc[0, :, :m] = self.backend.score_1vsN(self.model, "sp_", s_emb, p_emb, self.ent, self.l_norm, self.precision)
-            loc[1, :, :m] = self.backend.score_1vsN(self.model, "_po", o_emb, p_emb, self.ent, self.l_norm, self.precision)
+        dev = self.ent.device
+        buf = torch.empty((self.world, n, 2 * self.per), dtype=torch.float32, device=dev)
+        mine = buf[self.rank]
+        if m == self.per:
+            self.backend.score_sp_po(self.model, s_emb, self.rel, pi, o_emb, self.ent, self.l_norm, self.precision,
+                                     out=mine)
+        else:                                     # ragged last shard: pad its columns
+            mine.zero_()
+            if m > 0:
+                loc = self.backend.score_sp_po(self.model, s_emb, self.rel, pi, o_emb, self.ent, self.l_norm,
+                                               self.precision)
+                mine[:, :m] = loc[:, :m]
+                mine[:, self.per:self.per + m] = loc[:, m:]
         if self.world > 1:
-            parts = [torch.empty_like(loc) for _ in range(self.world)]
-            dist.all_gather(parts, loc, group=self.group)
-        else:
-            parts = [loc]
-        sp = torch.cat([q[0] for q in parts], 1)[:, : self.E]
-        po = torch.cat([q[1] for q in parts], 1)[:, : self.E]
-        return torch.cat([sp, po], 1)
+            dist.all_gather_into_tensor(buf.view(-1), mine.reshape(-1), group=self.group)
+        # [world, n, 2, per] -> [n, 2, world * per] -> [n, 2E]: the one re-layout copy of the call
+        full = buf.view(self.world, n, 2, self.per).permute(1, 2, 0, 3).reshape(n, 2, self.world * self.per)
+        return full[:, :, : self.E].reshape(n, 2 * self.E)
 
     # -- ranking -------------------------------------------------------------------------------------
     def true_scores(self, s, p, o):
-        """Scores of the true triples, identical on every rank (computed from the exchanged rows)."""
-        s_emb, p_emb, o_emb = self._queries(s, p, o)
-        t = self.backend.score_spo(self.model, s_emb, p_emb, o_emb, self.l_norm)
-        return t, (s_emb, p_emb, o_emb)
+        """((t_sp [n], t_po [n]), rows): scores of the true triples computed WITH THE 1-vs-N CODE PATH against the
+        exchanged answer rows — the reference does the same to keep tie handling consistent
+        (eval_entity_ranking.py:184-203: "scoring with spo vs sp and po can lead to slight differences for ties");
+        identical on every rank (same rows, same deterministic kernels)."""
+        s_emb, pi, o_emb, both = self._queries(s, p, o)
+        n = s.numel()
+        # one stacked launch against the 2n exchanged rows [s ; o]: sp block column n+i is o_i, po block column i is s_i
+        x = self.backend.score_sp_po(self.model, s_emb, self.rel, pi, o_emb, both, self.l_norm, self.precision)
+        ar = torch.arange(n, device=x.device)
+        t_sp = x[ar, n + ar].contiguous()
+        t_po = x[ar, 2 * n + ar].contiguous()
+        return (t_sp, t_po), (s_emb, pi, o_emb)
 
     def rank_sp_po(self, s, p, o, filter_sp=None, filter_po=None, rtol=1e-4, atol=1e-5):
         """(s_rank, s_ties, o_rank, o_ties) over ALL entities; filter_* are this rank's column slices
         [n, E_local] of the reference's +inf label matrix (eval_entity_ranking.py:287-290,561-566).
-        Integer all-reduce => bit-exact and 8*n bytes per counter instead of moving logits."""
-        t, (s_emb, p_emb, o_emb) = self.true_scores(s, p, o)
+        One stacked score+rank launch on the shard, then an integer all-reduce => bit-exact, 32*n bytes instead
+        of moving logits."""
+        (t_sp, t_po), (s_emb, pi, o_emb) = self.true_scores(s, p, o)
         n = s.numel()
         dev = self.ent.device
-        counts = torch.zeros((4, n), dtype=torch.int64, device=dev)
+        counts = torch.zeros((2, 2 * n), dtype=torch.int64, device=dev)
         if self.hi > self.lo:
-            o_rank, o_ties = self.backend.rank_1vsN(self.model, "sp_", s_emb, p_emb, self.ent, t, filter_sp, rtol,
-                                                    atol, self.l_norm, self.precision)
-            s_rank, s_ties = self.backend.rank_1vsN(self.model, "_po", o_emb, p_emb, self.ent, t, filter_po, rtol,
-                                                    atol, self.l_norm, self.precision)
-            counts[0], counts[1], counts[2], counts[3] = s_rank, s_ties, o_rank, o_ties
+            filt = None
+            if filter_sp is not None or filter_po is not None:
+                z = lambda f: f if f is not None else torch.zeros((n, self.hi - self.lo), device=dev)
+                filt = torch.cat([z(filter_sp), z(filter_po)], 0)
+            r, t = self.backend.rank_sp_po(self.model, s_emb, self.rel, pi, o_emb, self.ent,
+                                           torch.cat([t_sp, t_po]), filt, rtol, atol, self.l_norm, self.precision)
+            counts[0], counts[1] = r, t
         self._all_reduce(counts)
-        return counts[0], counts[1], counts[2], counts[3]
+        # rows 0..n-1 ranked the objects (sp_), rows n..2n-1 the subjects (_po)
+        return counts[0, n:], counts[1, n:], counts[0, :n], counts[1, :n]
 
     # -- duck-typed model interface of kge_b200.evaluate.EntityRankingEvaluator ------------------------
     # (filtered entity ranking over a sharded table: every rank runs the same evaluator on the same batches;
@@ -189,7 +220,8 @@ class ShardedKgeModel:
     def loss_1vsall_bce(self, s, p, o, offset: float = 0.0):
         """(BCE(score_sp, o) + BCE(score_po, s)) / n with sum reductions (train_1vsAll.py:48-82): BCE is
         additive over columns, so each rank reduces its shard and one scalar is all-reduced."""
-        s_emb, p_emb, o_emb = self._queries(s, p, o)
+        s_emb, pi, o_emb, _ = self._queries(s, p, o)
+        p_emb = self.rel[pi]
         n = s.numel()
 
         def local(idx):

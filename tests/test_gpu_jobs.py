@@ -139,3 +139,31 @@ def test_training_epoch_through_plugin(model, splits):
     for tag in ("plugin", "fused"):
         assert losses[tag][0] == pytest.approx(losses["ref"][0], rel=REL)
         assert losses[tag][1] == pytest.approx(losses["ref"][1], rel=1e-3)
+
+
+@pytest.mark.parametrize("model", ["complex", "distmult", "simple", "cp", "rescal"])
+@pytest.mark.parametrize("loss", ["kl", "bce"])
+def test_training_epoch_native_backward(model, loss, splits):
+    """The fused job with the gradient kernels of libb200kge (b200kge_x_train_1vsall_backward: recompute, G planes,
+    two split-K tensor-core GEMMs, unfold) instead of the reference's autograd: two epochs track the reference."""
+    torch.manual_seed(0)
+    init = ju.make_job(model, E, R, D, splits, device="cpu", train_type="1vsAll", loss=loss, batch_size=64)
+    losses = {}
+    for tag, dev in (("ref", "cpu"), ("native", "cuda")):
+        name = model if tag == "ref" else "b200_" + model
+        kw = {"job_class": "B200TrainingJob1vsAll"} if tag == "native" else {}
+        job = ju.make_job(name, E, R, D, splits, device=dev, train_type="1vsAll", loss=loss, batch_size=64,
+                          forward_only=False, **kw)
+        if tag == "native":
+            job.model.b200_backward = "native"
+        ju.copy_tables(init, job)
+        out = []
+        for ep in range(2):
+            job.epoch += 1
+            if job.loader is None:
+                job._prepare()
+            ju.seed_all(10 + ep)
+            out.append(job.run_epoch()["avg_loss"])
+        losses[tag] = out
+    assert losses["native"][0] == pytest.approx(losses["ref"][0], rel=REL)
+    assert losses["native"][1] == pytest.approx(losses["ref"][1], rel=1e-3)

@@ -22,10 +22,17 @@ def test_sharded_world1_matches_oracle(model, D):
     ref = orc.score_sp_po(model, ent, rel, tri[:, 0], tri[:, 1], tri[:, 2])
     assert float((full - ref).abs().max()) <= 1e-4 * float(ref.pow(2).mean().sqrt())
     s_rank, s_ties, o_rank, o_ties = m.rank_sp_po(s, p, o)
-    tt, _ = m.true_scores(s, p, o)
-    rr, ti = orc.ranks_and_ties(full[:, :E], tt.cpu())
+    (t_sp, t_po), _ = m.true_scores(s, p, o)
+    # true scores through the 1-vs-N path are bit-identical to the corresponding logits => the true answer is
+    # always counted as a tie of itself (eval_entity_ranking.py:184-203)
+    ar = torch.arange(n)
+    assert torch.equal(t_sp.cpu(), full[ar, tri[:, 2]]) and torch.equal(t_po.cpu(), full[ar, E + tri[:, 0]])
+    rr, ti = orc.ranks_and_ties(full[:, :E], t_sp.cpu())
     # fused rank kernel vs rank arithmetic on the dense kernel's scores: identical kernels => exact
     assert torch.equal(o_rank.cpu(), rr) and torch.equal(o_ties.cpu(), ti)
+    rr, ti = orc.ranks_and_ties(full[:, E:], t_po.cpu())
+    assert torch.equal(s_rank.cpu(), rr) and torch.equal(s_ties.cpu(), ti)
+    assert int(o_ties.min()) >= 1 and int(s_ties.min()) >= 1
     got = float(m.loss_1vsall_bce(s, p, o))
     want = float(orc.train_1vsall_forward(model, ent, rel, tri, "bce"))
     assert abs(got - want) <= 1e-4 * abs(want)

@@ -13,6 +13,28 @@ from oracle import kge_oracle as orc
 
 
 class OracleBackend:
+    def exchange_rows(self, shard, lo, idx):
+        out = torch.zeros((idx.numel(), shard.shape[1]))
+        mine = (idx >= lo) & (idx < lo + shard.shape[0])
+        out[mine] = shard[idx[mine] - lo]
+        return out
+
+    def score_sp_po(self, model, s_emb, rel, p, o_emb, cand, l_norm, precision, out=None):
+        x = torch.cat([orc.score_emb(model, s_emb, rel[p], cand, "sp_", l_norm),
+                       orc.score_emb(model, cand, rel[p], o_emb, "_po", l_norm)], 1)
+        if out is not None:
+            out[:, : x.shape[1]] = x
+            return out
+        return x
+
+    def rank_sp_po(self, model, s_emb, rel, p, o_emb, cand, true2n, filter2n, rtol, atol, l_norm, precision):
+        n = s_emb.shape[0]
+        x = torch.cat([orc.score_emb(model, s_emb, rel[p], cand, "sp_", l_norm),
+                       orc.score_emb(model, cand, rel[p], o_emb, "_po", l_norm)], 0)
+        if filter2n is not None:
+            x = x - filter2n
+        return orc.ranks_and_ties(x, true2n, rtol, atol)
+
     def score_1vsN(self, model, combine, q, p, cand, l_norm, precision):
         if combine == "sp_":
             return orc.score_emb(model, q, p, cand, "sp_", l_norm)
@@ -70,7 +92,10 @@ def _worker(rank, world, port, model, E, R, D, n, out):
         filt[torch.rand((n, 2 * E), generator=g) < 0.03] = float("inf")
         filt[torch.arange(n), o] = 0.0
         filt[torch.arange(n), E + s] = 0.0
-        t, _ = m.true_scores(s, p, o)
+        (t_sp, t_po), _ = m.true_scores(s, p, o)
+        # the true scores come from the 1-vs-N path: they ARE entries of the gathered logits (ties >= 1 by construction)
+        ar = torch.arange(n)
+        assert torch.equal(t_sp, full[ar, o]) and torch.equal(t_po, full[ar, E + s])
         for f in (None, filt):
             fsp = None if f is None else f[:, lo:hi].contiguous()
             fpo = None if f is None else f[:, E + lo:E + hi].contiguous()
@@ -78,10 +103,11 @@ def _worker(rank, world, port, model, E, R, D, n, out):
             sp, po = full[:, :E], full[:, E:]
             if f is not None:
                 sp, po = sp - f[:, :E], po - f[:, E:]
-            rr, tt = orc.ranks_and_ties(sp, t)
+            rr, tt = orc.ranks_and_ties(sp, t_sp)
             assert torch.equal(o_rank, rr) and torch.equal(o_ties, tt)
-            rr, tt = orc.ranks_and_ties(po, t)
+            rr, tt = orc.ranks_and_ties(po, t_po)
             assert torch.equal(s_rank, rr) and torch.equal(s_ties, tt)
+            assert int(o_ties.min()) >= 1 and int(s_ties.min()) >= 1
         # 4. BCE
         got = float(m.loss_1vsall_bce(s, p, o, 0.5))
         want = float(orc.train_1vsall_forward(model, ent, rel, tri, "bce", 0.5))
