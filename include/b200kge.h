@@ -181,6 +181,20 @@ int b200kge_rank_sp_po(int model, float l_norm, int precision, const b200kge_row
                        float atol, int64_t* rank, int64_t* ties, void* workspace, size_t workspace_bytes,
                        b200kge_stream_t stream);
 
+/* b200kge_rank_sp_po with the filter as CSR instead of a dense [2n, m] matrix: stacked row r lists the (sorted)
+ * candidate columns filter_col[filter_off[r] .. filter_off[r+1]) that hold known answers; they are excluded from the
+ * counts exactly like the reference's "+inf label subtracted" (eval_entity_ranking.py:489-531,561-566), except the
+ * row's own answer own_col[r] (may be NULL; :287-290).  Columns are positions in `cand`, which must be a plain
+ * table or chunk (cand->idx == NULL).  The CSR is consumed by the epilogue of the pre-split tensor-core kernel (a
+ * per-thread cursor into the row's segment); models / shapes served by the CUDA-core kernel return
+ * B200KGE_ERR_UNSUPPORTED before anything is launched — pass the dense filter to b200kge_rank_sp_po instead. */
+int b200kge_rank_sp_po_csr(int model, float l_norm, int precision, const b200kge_rows_t* s,
+                           const b200kge_rows_t* p, const b200kge_rows_t* o, const b200kge_rows_t* cand,
+                           int64_t n, const float* true_score, const int64_t* filter_off,
+                           const int64_t* filter_col, const int64_t* own_col, float rtol, float atol,
+                           int64_t* rank, int64_t* ties, void* workspace, size_t workspace_bytes,
+                           b200kge_stream_t stream);
+
 /* Entity-sharded tables: this rank owns global rows [lo, lo + shard->rows) of the entity table.
  * out[i, :] = shard row (idx[i] - lo) if the rank owns global id idx[i], else zeros — the contribution of this rank
  * to the query-row exchange (sum over ranks == the gathered rows, exactly: every other rank adds zeros).  One
@@ -267,14 +281,14 @@ int b200kge_kvsall_gather(const int64_t* keys, const int64_t* offsets, const int
                           int64_t num_keys, const int64_t* examples, int64_t nb,
                           int64_t* queries_out, int64_t* offsets_out, int64_t* cols_out);
 
-/* ---- EXPERIMENTAL (prefix b200kge_x_) -------------------------------------------------------------
- * Prepared for the next round, NOT validated on hardware yet and not used by any entry point above.
+/* ---- gradients, penalties, CSR labels (validated on a B200 in round 2) -------------
  *
- * b200kge_x_gemm_nt: C[M,N] = A[M,K] * B[N,K]^T, fp32 in / fp32 out, computed on the f16 tensor pipe from
+ * b200kge_gemm_nt: C[M,N] = A[M,K] * B[N,K]^T, fp32 in / fp32 out, computed on the f16 tensor pipe from
  * hi/lo fp16 planes split once in HBM (presplit.cu + pairwise_tc3.cu) — the building block of the
- * backward GEMMs; fp32-equivalent (operand error ~5e-7 of the result's rms). */
-size_t b200kge_x_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K);
-int b200kge_x_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N,
+ * backward GEMMs; fp32-equivalent (operand error ~5e-7 of the result's rms).  Reductions longer than 512 run
+ * split-K: 512-element segments accumulated in fp32, which bounds the tensor core's accumulator error. */
+size_t b200kge_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int b200kge_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N,
                       int64_t K, float* C, int64_t ldc, void* workspace, size_t workspace_bytes,
                       b200kge_stream_t stream);
 
@@ -283,8 +297,8 @@ int b200kge_x_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, 
  * [R, ldr] of  (loss(score_sp, o) + loss(score_po, s)) / n.  Both buffers are overwritten (the reference
  * accumulates into .grad; add them there).  Recompute-based: scores, G = n dL/dz (sigmoid(z+off) - y | softmax(z) - y), two tensor-core
  * GEMMs (dT = G^T Q, dQ = G T), row-wise unfold of dQ through the relation fold (grad.cu). */
-size_t b200kge_x_train_1vsall_backward_workspace_bytes(int model, int64_t n, int64_t E, int32_t D);
-int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+size_t b200kge_train_1vsall_backward_workspace_bytes(int model, int64_t n, int64_t E, int32_t D);
+int b200kge_train_1vsall_backward(int model, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
                                     const int64_t* triples, int64_t n, int loss_kind, float offset,
                                     float* d_ent, int64_t lde, float* d_rel, int64_t ldr,
                                     void* workspace, size_t workspace_bytes, b200kge_stream_t stream);
@@ -293,8 +307,9 @@ int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const 
  * row i's labels are the columns csr_col[csr_off[i] .. csr_off[i+1]) (sorted; a repeated column counts as often
  * as it appears, like duplicate triples in the reference), optionally smoothed: y = (1 - eps) * count + 1/m.
  * *loss_out = sum_i loss(score row i, y_i) (BCE with offset | KL), row_loss_out (optional) the per-row terms.
- * Composition of the fused scorer (label-free pass) with row kernels over the nnz listed columns; cand must be a
- * plain table; eps > 0 needs a dot-family model.  Sizes: b200kge_score_1vsN_loss_csr_workspace_bytes. */
+ * On the pre-split tensor-core path (dot family) ONE fused pass scores, reduces the label-free loss terms and emits
+ * the nnz listed scores from its epilogue (per-thread cursor into the row's sorted segment); elsewhere the listed
+ * scores come from the row-wise triple kernel.  cand must be a plain table; eps > 0 needs a dot-family model.  Sizes: b200kge_score_1vsN_loss_csr_workspace_bytes. */
 size_t b200kge_score_1vsN_loss_csr_workspace_bytes(int model, int64_t n, int64_t m, int32_t D, int64_t nnz);
 int b200kge_score_1vsN_loss_csr(int model, int combine, float l_norm, int precision,
                                   const b200kge_rows_t* q, const b200kge_rows_t* p,
@@ -308,7 +323,7 @@ int b200kge_score_1vsN_loss_csr(int model, int combine, float l_norm, int precis
  * label 0), loss summed and divided by batch_size.  ADDS into d_ent [E, lde] and d_rel [R, ldr] (zero them before
  * the first slot).  slot 0 (S) or 2 (O); TransE with l_norm 1 or 2, RotatE with l_norm 1, and the dot family.
  * workspace: n * round_up(K_folded, 32) floats. */
-int b200kge_x_ns_backward(int model, float l_norm, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+int b200kge_ns_backward(int model, float l_norm, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
                           const int64_t* triples, int slot, const int64_t* neg, int64_t n, int64_t K,
                           float offset, int64_t batch_size, float* d_ent, int64_t lde, float* d_rel,
                           int64_t ldr, void* workspace, size_t workspace_bytes, b200kge_stream_t stream);

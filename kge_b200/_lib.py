@@ -52,6 +52,9 @@ SIGNATURES = {
     "b200kge_rank_sp_po": (C.c_int, [C.c_int, C.c_float, C.c_int, _RP, _RP, _RP, _RP, C.c_int64, C.c_void_p, C.c_void_p,
                                      C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                      C.c_void_p]),
+    "b200kge_rank_sp_po_csr": (C.c_int, [C.c_int, C.c_float, C.c_int, _RP, _RP, _RP, _RP, C.c_int64, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200kge_shard_gather_rows": (C.c_int, [_RP, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "b200kge_loss_dense": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(Labels), C.c_int,
                                      C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -72,18 +75,18 @@ SIGNATURES = {
     "b200kge_kvsall_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     # experimental (not validated on hardware yet)
-    "b200kge_x_gemm_nt_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
-    "b200kge_x_gemm_nt": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+    "b200kge_gemm_nt_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
+    "b200kge_gemm_nt": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
-    "b200kge_x_train_1vsall_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int64, C.c_int32]),
-    "b200kge_x_train_1vsall_backward": (C.c_int, [C.c_int, _RP, _RP, C.c_void_p, C.c_int64, C.c_int, C.c_float,
+    "b200kge_train_1vsall_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int64, C.c_int32]),
+    "b200kge_train_1vsall_backward": (C.c_int, [C.c_int, _RP, _RP, C.c_void_p, C.c_int64, C.c_int, C.c_float,
                                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                                   C.c_size_t, C.c_void_p]),
     "b200kge_score_1vsN_loss_csr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int64, C.c_int32, C.c_int64]),
     "b200kge_score_1vsN_loss_csr": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_int, _RP, _RP, _RP, C.c_int64,
                                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int, C.c_float,
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
-    "b200kge_x_ns_backward": (C.c_int, [C.c_int, C.c_float, _RP, _RP, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
+    "b200kge_ns_backward": (C.c_int, [C.c_int, C.c_float, _RP, _RP, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
                                         C.c_int64, C.c_float, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                         C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200kge_lookup_penalty": (C.c_int, [_RP, C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p,

@@ -133,6 +133,12 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
       tc_kind = 1; precision = B200KGE_PREC_TF32_BF16X2;
     } }
 
+  if (P.csr_off && (tc_kind != 3 || cols_differ || B.cand->idx)) {
+    // nothing has been launched or taken from the workspace yet: callers fall back to their dense / composed form
+    set_error("the CSR side input is consumed by the pre-split tensor-core epilogue only (dot family, plain candidate table)");
+    return B200KGE_ERR_UNSUPPORTED;
+  }
+
   if (cols_differ) {
     // run the two halves as separate blocks (CP reads different candidate columns per direction)
     Block h0 = B; h0.q1 = nullptr;
@@ -427,6 +433,27 @@ int b200kge_rank_sp_po(int model, float l_norm, int precision, const b200kge_row
   return run_block(B, l_norm, precision, EPI_RANK, P, ws, (cudaStream_t)stream, nullptr);
 }
 
+int b200kge_rank_sp_po_csr(int model, float l_norm, int precision, const b200kge_rows_t* s,
+                           const b200kge_rows_t* p, const b200kge_rows_t* o, const b200kge_rows_t* cand,
+                           int64_t n, const float* true_score, const int64_t* filter_off,
+                           const int64_t* filter_col, const int64_t* own_col, float rtol, float atol,
+                           int64_t* rank, int64_t* ties, void* workspace, size_t workspace_bytes,
+                           b200kge_stream_t stream) {
+  int rc = check_1vsN_args(model, B200KGE_SP_, s, p, cand, n); if (rc) return rc;
+  if ((rc = check_1vsN_args(model, B200KGE__PO, o, p, cand, n))) return rc;
+  if ((rc = validate_norm(model, l_norm))) return rc;
+  if (!true_score || !rank || !ties || !filter_off) { set_error("null rank operand"); return B200KGE_ERR_INVALID; }
+  Rows Sr = to_rows(s), Pr = to_rows(p), Or = to_rows(o), C = to_rows(cand);
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  EpiParams P = empty_epi();
+  P.true_score = true_score; P.rtol = rtol; P.atol = atol;
+  P.rank = reinterpret_cast<unsigned long long*>(rank);
+  P.ties = reinterpret_cast<unsigned long long*>(ties);
+  P.csr_off = filter_off; P.csr_col = filter_col; P.csr_skip = own_col;
+  Block B{model, B200KGE_SP_, &Sr, &Or, &Pr, &C, n};
+  return run_block(B, l_norm, precision, EPI_RANK, P, ws, (cudaStream_t)stream, nullptr);
+}
+
 int b200kge_shard_gather_rows(const b200kge_rows_t* shard, int64_t lo, const int64_t* idx, int64_t n,
                               float* out, int64_t ldo, b200kge_stream_t stream) {
   if (!shard || (!idx && n > 0) || (!out && n > 0)) { set_error("null operand"); return B200KGE_ERR_INVALID; }
@@ -592,9 +619,8 @@ int b200kge_train_1vsall_forward_host(int model, float l_norm, int precision,
 }  // extern "C"
 
 // ==================================================================================================
-// EXPERIMENTAL entry points (prefix b200kge_x_): pre-split fp16 GEMM and the analytic backward of the 1vsAll
-// step for the dot family (grad.cu).  Declared in include/b200kge.h under "experimental"; not validated on
-// hardware yet, not used by any default path.
+// Pre-split fp16 GEMM, the analytic backward of the 1vsAll step for the dot family (grad.cu), penalties, row
+// normalisation, negative-sampling backward, CSR-label losses: SURVEY 8f rows, validated on a B200 in round 2.
 namespace {
 
 bool take_planes(Arena& ws, SplitSet& S) {
@@ -684,12 +710,12 @@ size_t backward_block_bytes(int64_t nq, int64_t m, int64_t K, int64_t ldq) {
 
 extern "C" {
 
-size_t b200kge_x_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+size_t b200kge_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   const int64_t Kp = round_up(K, 64);
   return planes_bytes(M, M, Kp) + planes_bytes(N, N + 32, Kp) + 1024;
 }
 
-int b200kge_x_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+int b200kge_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
                       float* C, int64_t ldc, void* workspace, size_t workspace_bytes, b200kge_stream_t stream) {
   if (!A || !B || !C) { set_error("null operand"); return B200KGE_ERR_INVALID; }
   if (M < 0 || N < 0 || K <= 0 || N >= (1ll << 31)) { set_error("bad GEMM shape"); return B200KGE_ERR_INVALID; }
@@ -705,13 +731,13 @@ int b200kge_x_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, 
   return gemm_planes(SA, SB, C, ldc, st);
 }
 
-size_t b200kge_x_train_1vsall_backward_workspace_bytes(int model, int64_t n, int64_t E, int32_t D) {
+size_t b200kge_train_1vsall_backward_workspace_bytes(int model, int64_t n, int64_t E, int32_t D) {
   const int64_t K = (model == B200KGE_CP) ? D / 2 : D;
   const int64_t nq = 2 * n, ldq = round_up(K, 32);
   return (size_t)nq * ldq * 4 + (size_t)n * 5 * 8 + 4096 + backward_block_bytes(nq, E, K, ldq);
 }
 
-int b200kge_x_train_1vsall_backward(int model, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+int b200kge_train_1vsall_backward(int model, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
                                     const int64_t* triples, int64_t n, int loss_kind, float offset, float* d_ent,
                                     int64_t lde, float* d_rel, int64_t ldr, void* workspace, size_t workspace_bytes,
                                     b200kge_stream_t stream) {
@@ -779,7 +805,7 @@ int b200kge_normalize_rows(float* weight, int64_t ld, int64_t rows, int32_t dim,
 }
 
 
-int b200kge_x_ns_backward(int model, float l_norm, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+int b200kge_ns_backward(int model, float l_norm, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
                           const int64_t* triples, int slot, const int64_t* neg, int64_t n, int64_t K, float offset,
                           int64_t batch_size, float* d_ent, int64_t lde, float* d_rel, int64_t ldr, void* workspace,
                           size_t workspace_bytes, b200kge_stream_t stream) {
@@ -837,30 +863,45 @@ int b200kge_score_1vsN_loss_csr(int model, int combine, float l_norm, int precis
   void* scratch = ws.take(1024);
   if (!lab || !qsel || !psel || !esel || !zpos || !fused || !rows || !total || !scratch) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
   // 1. label-free fused pass: BCE with no label (index -1) -> sum_j softplus;  KL with the one-hot label at
-  //    column 0 -> lse_i - z_i0
+  //    column 0 -> lse_i - z_i0.  On the pre-split tensor-core path the SAME pass also emits the scores of the listed
+  //    columns (and z_i0) from its epilogue (per-thread cursor into the row's sorted CSR segment, tc_common.cuh):
+  //    DRAM traffic = table + queries + nnz * 12 bytes.
   B2K_CUDA(cudaMemsetAsync(lab, loss_kind == B200KGE_LOSS_BCE ? 0xFF : 0, (size_t)n * 8, st));
+  bool emitted = false;
   {
-    EpiParams P = empty_epi();
-    P.label_idx = lab;
-    P.offset = (loss_kind == B200KGE_LOSS_BCE) ? offset : 0.f;
-    Block B{model, combine, &Q, nullptr, &Pr, &C, n};
-    int nch = 0;
-    float* part = nullptr;
-    Arena w2 = ws;
     const int epi = (loss_kind == B200KGE_LOSS_BCE) ? EPI_BCE : EPI_KL;
-    if ((rc = run_block(B, l_norm, precision, epi, P, w2, st, &nch, &part))) return rc;
-    if ((rc = launch_loss_finalize(loss_kind, part, nch, n, total, fused, 1.0f, 0, scratch, 0, st))) return rc;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      EpiParams P = empty_epi();
+      P.label_idx = lab;
+      P.offset = (loss_kind == B200KGE_LOSS_BCE) ? offset : 0.f;
+      if (attempt == 0) {
+        P.csr_off = csr_off; P.csr_col = csr_col; P.csr_out = zpos; P.csr_nnz = nnz;
+        P.csr_extra = (loss_kind == B200KGE_LOSS_KL) ? 1 : 0;
+      }
+      Block B{model, combine, &Q, nullptr, &Pr, &C, n};
+      int nch = 0;
+      float* part = nullptr;
+      Arena w2 = ws;
+      rc = run_block(B, l_norm, precision, epi, P, w2, st, &nch, &part);
+      if (rc == B200KGE_ERR_UNSUPPORTED && attempt == 0) continue;      // not the pre-split path: compose below
+      if (rc) return rc;
+      emitted = (attempt == 0);
+      if ((rc = launch_loss_finalize(loss_kind, part, nch, n, total, fused, 1.0f, 0, scratch, 0, st))) return rc;
+      break;
+    }
   }
-  // 2. scores of the listed columns (and of column 0 for KL) through the row-wise triple kernel
-  if ((rc = launch_csr_expand(csr_off, csr_col, n, nnz, loss_kind == B200KGE_LOSS_KL ? 1 : 0, Q.idx, Pr.idx, qsel, psel,
-                              esel, st))) return rc;
-  if (tot > 0) {
-    Rows Qs = Q; Qs.idx = qsel; Qs.rows = tot;
-    Rows Ps = Pr; Ps.idx = psel; Ps.rows = tot;
-    Rows Es = C; Es.idx = esel; Es.rows = tot;
-    if (combine == B200KGE_SP_) rc = launch_spo(model, l_norm, Qs, Ps, Es, tot, zpos, 1, st);
-    else                        rc = launch_spo(model, l_norm, Es, Ps, Qs, tot, zpos, 1, st);
-    if (rc) return rc;
+  // 2. otherwise: scores of the listed columns (and of column 0 for KL) through the row-wise triple kernel
+  if (!emitted) {
+    if ((rc = launch_csr_expand(csr_off, csr_col, n, nnz, loss_kind == B200KGE_LOSS_KL ? 1 : 0, Q.idx, Pr.idx, qsel, psel,
+                                esel, st))) return rc;
+    if (tot > 0) {
+      Rows Qs = Q; Qs.idx = qsel; Qs.rows = tot;
+      Rows Ps = Pr; Ps.idx = psel; Ps.rows = tot;
+      Rows Es = C; Es.idx = esel; Es.rows = tot;
+      if (combine == B200KGE_SP_) rc = launch_spo(model, l_norm, Qs, Ps, Es, tot, zpos, 1, st);
+      else                        rc = launch_spo(model, l_norm, Es, Ps, Qs, tot, zpos, 1, st);
+      if (rc) return rc;
+    }
   }
   // 3. label smoothing: sum_j z_ij = Q_i . colsum(T)   (dot family)
   float* zsum = nullptr;

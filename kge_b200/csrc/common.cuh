@@ -101,7 +101,28 @@ struct EpiParams {
   int64_t col_block;
   // EPI_STORE, GEMM use (pairwise_tc3.cu split-K): add into `out` (zeroed by the caller) instead of overwriting it
   int accumulate_out;
+  // CSR side input: row r lists the sorted columns csr_col[csr_off[r] .. csr_off[r+1]) (duplicates
+  // allowed).  Losses: the raw scores at the listed columns are written to csr_out[t] (t = position in csr_col) —
+  // the multi-hot label terms are then sums over nnz values, no [n, m] label matrix exists (train_KvsAll.py:242-266);
+  // with csr_extra the score of column 0 of row r goes to csr_out[csr_nnz + r] (KL: lse_i - z_i0 comes back from
+  // the one-hot-at-0 pass).  Rank: listed columns are filtered (score -> -inf, eval_entity_ranking.py:561-566)
+  // except the row's own answer csr_skip[r] (:287-290).  Candidate columns must be table rows (cand.idx == NULL).
+  const int64_t* csr_off;
+  const int64_t* csr_col;
+  float* csr_out;
+  int64_t csr_nnz;
+  int csr_extra;
+  const int64_t* csr_skip;
 };
+
+// lower bound of `key` in the sorted segment col[lo, hi)
+__device__ __forceinline__ int64_t csr_lower_bound(const int64_t* __restrict__ col, int64_t lo, int64_t hi, int64_t key) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(col + mid) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
 
 #define B2K_NEG_HUGE (-3.0e38f)
 

@@ -1,5 +1,7 @@
-// csr_loss.cu — EXPERIMENTAL (device half): KvsAll losses with CSR multi-hot labels, composed
-// from the validated fused kernels plus the small row kernels below — no [n, E] label matrix is built or read.
+// csr_loss.cu — SURVEY §8 f-2, device half: KvsAll losses with CSR multi-hot labels — no [n, E] label matrix is
+// built or read.  The label-free part comes from the fused scorer; the scores of the listed columns are emitted by
+// the same pass's epilogue on the pre-split tensor-core path (tc_common.cuh, per-thread cursor into the row's sorted
+// CSR segment) or, for the CUDA-core families, by the row-wise triple kernel; the row kernels below combine them.
 //
 // With labels y_ij = a * c_ij + b  (c_ij = multiplicity of column j in row i's CSR segment, a = 1 - eps,
 // b = eps > 0 ? 1/E : 0; train_KvsAll.py:242-266) both losses split into a label-free part, which the fused

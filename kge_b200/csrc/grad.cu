@@ -1,6 +1,7 @@
-// grad.cu — EXPERIMENTAL ("next"): device pieces of the backward of the fused 1vsAll step for
-// the dot family.  Not on any default path and not validated on hardware yet; the math is pinned on the CPU
-// (oracle/kge_fold.py against autograd and against gradients of the live reference,
+// grad.cu — SURVEY §8 f-1: device pieces of the backward of the fused 1vsAll step for the dot family, of the
+// negative-sampling step, and the penalty / normalisation row kernels.  Validated on a B200 in round 2
+// (tests/test_gpu_backward.py, tests/test_gpu_jobs.py::test_training_epoch_native_backward); the math is pinned on
+// the CPU (oracle/kge_fold.py against autograd and against gradients of the live reference,
 // tests/test_fold_algebra.py), the kernels below transcribe it.
 //
 //   z  = Q T^T                       recomputed with the validated scorer (plain-store epilogue)
@@ -10,9 +11,10 @@
 //   dQ = G  T    [nq, K]             same on G and T^T planes
 //   (da, dp) = unfold(a, p, dQ)      unfold_kernel: row-wise vector-Jacobian products of the relation fold,
 //                                    atomically added into the entity / relation gradient tables
-// This first version trades HBM traffic for simplicity (scores and both G layouts are materialised, operands
-// are transposed through HBM); fusing the G pass into the scorer's epilogue and a split-K dQ are the
-// follow-ups once it is parity-green.
+// This version trades HBM traffic for simplicity (scores and both G layouts are materialised, operands are
+// transposed through HBM).  Both GEMMs run split-K (512-element segments added in fp32, pairwise_tc3.cu): the
+// tensor core's fp32 accumulator error grows with the reduction length (measured 2.8e-4 of rms at K = 14541
+// against 2.4e-5 at K = 512), and dQ = G T reduces over all E entities.
 #include <cuda_fp16.h>
 #include "fold.cuh"
 #include "tc_common.cuh"

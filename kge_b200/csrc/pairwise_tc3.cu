@@ -1,6 +1,6 @@
-// pairwise_tc3.cu — tcgen05 1-vs-N scorer on PRE-SPLIT fp16 operand planes.  EXPERIMENTAL: selected with
-// B200KGE_TC_VERSION=3 (the default is pairwise_tc.cu); same scores, losses and rank counts, different
-// operand path.
+// pairwise_tc3.cu — tcgen05 1-vs-N scorer on PRE-SPLIT fp16 operand planes: THE default kernel of the dot family
+// (B200KGE_PREC_AUTO / F16X3; measured 0.069 ms at the FB15k-237 headline shape against 0.118 ms for the in-kernel
+// split of pairwise_tc.cu, profiles/r2_summary.md).
 //
 //   S[q, e] = qs[q] * ts[e] * sum_k (Qh[q,k]*Th[e,k] + Qh[q,k]*Tl[e,k] + Ql[q,k]*Th[e,k])
 //
@@ -201,6 +201,7 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
       st.init();
       const float aux = row_ok ? epi_row_aux<EPI>(P, row) : 0.f;
       const float qs = row_ok ? __ldg(prm.q_scale + row) : 0.f;
+      const int64_t csr_end = (P.csr_off && row_ok) ? __ldg(P.csr_off + row + 1) : 0;
       for (int et = et0; et < et1; ++et, ++it) {
         const int b = it & 1;
         ptx::mbar_wait_bounded(&tfull[b], (it >> 1) & 1);
@@ -209,7 +210,8 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
         tc::epilogue_tile<EPI, 4, true>(P, st, aux,
                                         tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TN + half * 128),
                                         (int64_t)qt * TM + quad * 32, (int64_t)et * prm.tn + half * 128, prm.nq,
-                                        tile_end < prm.m ? tile_end : prm.m, my_stg, lane, qs, prm.t_scale);
+                                        tile_end < prm.m ? tile_end : prm.m, my_stg, lane, qs, prm.t_scale,
+                                        csr_end);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty[b]);

@@ -1,5 +1,6 @@
-// pairwise_tc4.cu — CTA-pair (tcgen05 cta_group::2) scorer on PRE-SPLIT fp16 operand planes.  EXPERIMENTAL:
-// selected with B200KGE_TC_VERSION=4 (the default is pairwise_tc.cu); same scores, losses and rank counts.
+// pairwise_tc4.cu — CTA-pair (tcgen05 cta_group::2) scorer on PRE-SPLIT fp16 operand planes, selected with
+// B200KGE_TC_VERSION=4 (the default is the 1-CTA pairwise_tc3.cu); same scores, losses and rank counts; parity-green
+// on B200 (tests/test_gpu_presplit.py), 2/3 of the L2->SM operand traffic, within +-3 % of the 1-CTA kernel's time.
 //
 // pairwise_tc3.cu (1 CTA, pre-split planes) has no shared-memory round trip left, which leaves two limits:
 // the L2->SM feed (each 128 x 256 tile pulls 384 operand rows) and the MMAs' own operand reads (96 of the
@@ -221,6 +222,7 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
       st.init();
       const float aux = row_ok ? epi_row_aux<EPI>(P, row) : 0.f;
       const float qs = row_ok ? __ldg(prm.q_scale + row) : 0.f;
+      const int64_t csr_end = (P.csr_off && row_ok) ? __ldg(P.csr_off + row + 1) : 0;
       for (int et = et0; et < et1; ++et, ++it) {
         const int b = it & 1;
         ptx::mbar_wait_cluster_bounded(&tfull[b], (it >> 1) & 1);
@@ -229,7 +231,8 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
         tc::epilogue_tile<EPI, 4, true>(P, st, aux,
                                         tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TN + half * 128),
                                         row0, (int64_t)et * prm.tn + half * 128, prm.nq,
-                                        tile_end < prm.m ? tile_end : prm.m, my_stg, lane, qs, prm.t_scale);
+                                        tile_end < prm.m ? tile_end : prm.m, my_stg, lane, qs, prm.t_scale,
+                                        csr_end);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty[b]), 0));
@@ -262,7 +265,9 @@ void plan4(int64_t nq, int64_t m, int& q_tiles, int& e_tiles, int& echunks, int&
     int per = units / q_tiles; if (per < 1) per = 1; if (per > et) per = (int)et;
     const int64_t tiles_per_cl = (et + per - 1) / per;
     const int64_t waves = ((int64_t)q_tiles * per + units - 1) / units;
-    const int64_t cost = waves * tiles_per_cl * cand + tiles_per_cl * 24;
+    // per-tile overhead of the pair (cross-CTA accumulator hand-over): measured 73.2 us with 9 tiles of 192 columns
+    // against 68.4 us with 7 tiles of 256 at the FB15k-237 shape => worth ~64 columns per tile
+    const int64_t cost = waves * tiles_per_cl * cand + tiles_per_cl * 64;
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; tn = cand; }
   }
   e_tiles = (int)((m + tn - 1) / tn);

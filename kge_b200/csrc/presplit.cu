@@ -1,5 +1,5 @@
-// presplit.cu — operand split for the pre-split fp16 tensor-core kernel (pairwise_tc3.cu).  EXPERIMENTAL:
-// selected with B200KGE_TC_VERSION=3, not part of the default path.
+// presplit.cu — operand split for the pre-split fp16 tensor-core kernels (pairwise_tc3.cu, pairwise_tc4.cu): the
+// default path of the dot family (B200KGE_PREC_AUTO / F16X3).
 //
 // A fp32 value x of row r is represented as  x = inv_scale[r] * (hi + lo),  hi = fp16_rn(x * 2^s),
 // lo = fp16_rn(x * 2^s - hi),  2^s chosen per row so that max|x * 2^s| lies in [2^13, 2^14): 22 significant

@@ -218,9 +218,13 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& P, RowState<EPI>&
                                               int64_t tile_row0 /* first row of this warp's 32 */,
                                               int64_t e0 /* global column of the first chunk */, int64_t nq,
                                               int64_t m, float* my_stg, int lane, float row_scale = 1.f,
-                                              const float* __restrict__ col_scale = nullptr) {
+                                              const float* __restrict__ col_scale = nullptr,
+                                              int64_t csr_end = 0 /* end of this row's CSR segment (0: none) */) {
   const int64_t row = tile_row0 + lane;
   const bool row_ok = row < nq;
+  // CSR side input: position of the first listed column >= e0 in this row's segment (one binary search per span)
+  int64_t csr_cur = 0;
+  if (csr_end > 0) csr_cur = csr_lower_bound(P.csr_col, __ldg(P.csr_off + row), csr_end, e0);
 #pragma unroll 1
   for (int j = 0; j < NCH; ++j) {
     const int64_t c0 = e0 + j * 32;
@@ -241,6 +245,31 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& P, RowState<EPI>&
       }
     } else {
       ptx::tmem_ld_wait();
+    }
+    if (csr_cur < csr_end) {
+      // listed columns of this row inside [c0, c0 + 32): emit their scores (losses) or filter them (rank)
+      int64_t cj = __ldg(P.csr_col + csr_cur);
+      while (cj < c0 + 32) {
+        const int rel = (int)(cj - c0);
+        if constexpr (EPI == EPI_RANK) {
+          if (!P.csr_skip || __ldg(P.csr_skip + row) != cj) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c == rel) v[c] = 0xff800000u;            // -inf: neither greater nor close (for a finite true score)
+          }
+        } else {
+          uint32_t x = 0;
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c == rel) x = v[c];
+          if (cj < m) P.csr_out[csr_cur] = __uint_as_float(x);
+        }
+        if (++csr_cur >= csr_end) break;
+        cj = __ldg(P.csr_col + csr_cur);
+      }
+    }
+    if constexpr (EPI == EPI_BCE || EPI == EPI_KL) {
+      if (P.csr_extra && c0 == 0 && row_ok) P.csr_out[P.csr_nnz + row] = __uint_as_float(v[0]);
     }
     if constexpr (EPI == EPI_STORE) {
       // transpose a 32x32 block through smem: each store instruction then writes 32 consecutive

@@ -188,6 +188,34 @@ def rank_sp_po(model: str, s_tab, rel, o_tab, cand_tab, true_scores, s=None, p=N
     return rank, ties
 
 
+def rank_sp_po_csr(model: str, s_tab, rel, o_tab, cand_tab, true_scores, filter_off, filter_col, own_col=None,
+                   s=None, p=None, o=None, rtol: float = 1e-4, atol: float = 1e-5, l_norm: float = 1.0,
+                   precision: str = "auto", rank=None, ties=None):
+    """rank_sp_po with the known-answer filter as CSR over the stacked rows (sp_ rows, then _po rows): row r lists
+    sorted candidate columns filter_col[filter_off[r]:filter_off[r+1]]; own_col[r] (the row's own answer) stays in.
+    Raises NotImplementedError when the shape / model is not served by the pre-split tensor-core kernel."""
+    _require_cuda(s_tab, rel, o_tab, cand_tab, true_scores, filter_off, filter_col, own_col)
+    lib, k = _lib.load(), _Keep()
+    rs, rp, ro, rc = k.rows(s_tab, s), k.rows(rel, p), k.rows(o_tab, o), k.rows(cand_tab)
+    n, m = int(rs.rows), int(rc.rows)
+    dev = s_tab.device
+    t = true_scores.reshape(-1).float().contiguous()
+    offs, cols = _i64(filter_off), _i64(filter_col)
+    own = _i64(own_col)
+    if t.numel() != 2 * n or offs.numel() != 2 * n + 1:
+        raise ValueError("true_scores / filter_off must cover the 2n stacked rows")
+    if rank is None:
+        rank = torch.zeros(2 * n, dtype=torch.int64, device=dev)
+    if ties is None:
+        ties = torch.zeros(2 * n, dtype=torch.int64, device=dev)
+    ws = _workspace(MODELS[model], n, m, rs.dim, False, dev)
+    _lib.check(lib.b200kge_rank_sp_po_csr(
+        MODELS[model], l_norm, PREC[precision], C.byref(rs), C.byref(rp), C.byref(ro), C.byref(rc), n, t.data_ptr(),
+        offs.data_ptr(), cols.data_ptr() if cols.numel() else None, own.data_ptr() if own is not None else None,
+        rtol, atol, rank.data_ptr(), ties.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
+    return rank, ties
+
+
 def shard_gather_rows(shard: torch.Tensor, lo: int, idx: torch.Tensor, out: Optional[torch.Tensor] = None):
     """This rank's contribution to the query-row exchange of an entity-sharded table: out[i] = shard[idx[i] - lo]
     if lo <= idx[i] < lo + rows else 0 (one kernel, no host synchronisation)."""
@@ -371,8 +399,8 @@ class HostStep:
         return float(self.loss_host[0])
 
 
-# ---- EXPERIMENTAL (b200kge_x_*): prepared for the next round, not validated on hardware yet -----------------
-def x_gemm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+# ---- SURVEY 8f rows (gradients, penalties, CSR labels): validated on a B200 in round 2 -------------------------
+def gemm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """C = A @ B^T (fp32 in/out) on the f16 tensor pipe from pre-split hi/lo fp16 planes."""
     _require_cuda(a, b)
     lib = _lib.load()
@@ -380,13 +408,13 @@ def x_gemm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     M, K = a.shape
     N = b.shape[0]
     out = torch.empty((M, N), dtype=torch.float32, device=a.device)
-    ws = torch.empty(lib.b200kge_x_gemm_nt_workspace_bytes(M, N, K), dtype=torch.uint8, device=a.device)
-    _lib.check(lib.b200kge_x_gemm_nt(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, out.data_ptr(),
+    ws = torch.empty(lib.b200kge_gemm_nt_workspace_bytes(M, N, K), dtype=torch.uint8, device=a.device)
+    _lib.check(lib.b200kge_gemm_nt(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, out.data_ptr(),
                                      out.stride(0), ws.data_ptr(), ws.numel(), _stream(a.device)))
     return out
 
 
-def x_train_1vsall_backward(model: str, ent, rel, triples, loss: str = "bce", offset: float = 0.0):
+def train_1vsall_backward(model: str, ent, rel, triples, loss: str = "bce", offset: float = 0.0):
     """(d_ent, d_rel): dense table gradients of train_1vsall_forward's loss (dot family, BCE)."""
     _require_cuda(ent, rel, triples)
     lib, k = _lib.load(), _Keep()
@@ -396,9 +424,9 @@ def x_train_1vsall_backward(model: str, ent, rel, triples, loss: str = "bce", of
     dev = ent.device
     d_ent = torch.empty_like(_f32(ent))
     d_rel = torch.empty_like(_f32(rel))
-    nbytes = lib.b200kge_x_train_1vsall_backward_workspace_bytes(MODELS[model], n, ent.shape[0], ent.shape[1])
+    nbytes = lib.b200kge_train_1vsall_backward_workspace_bytes(MODELS[model], n, ent.shape[0], ent.shape[1])
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    _lib.check(lib.b200kge_x_train_1vsall_backward(
+    _lib.check(lib.b200kge_train_1vsall_backward(
         MODELS[model], C.byref(re_), C.byref(rr), tri.data_ptr(), n, LOSS[loss], offset, d_ent.data_ptr(),
         d_ent.stride(0), d_rel.data_ptr(), d_rel.stride(0), ws.data_ptr(), ws.numel(), _stream(dev)))
     return d_ent, d_rel
@@ -448,7 +476,7 @@ def normalize_rows_(weight: torch.Tensor, p: float) -> torch.Tensor:
     return weight
 
 
-def x_ns_backward(model: str, ent, rel, triples, negatives: dict, offset: float = 0.0, l_norm: float = 1.0,
+def ns_backward(model: str, ent, rel, triples, negatives: dict, offset: float = 0.0, l_norm: float = 1.0,
                   batch_size: Optional[int] = None):
     """(d_ent, d_rel) of one negative-sampling batch with BCE; negatives = {slot: [n, K] ids}, slots 0 (S), 2 (O)."""
     _require_cuda(ent, rel, triples)
@@ -462,7 +490,7 @@ def x_ns_backward(model: str, ent, rel, triples, negatives: dict, offset: float 
     ws = torch.empty(n * (ent.shape[1] + 32) * 4 + 1024, dtype=torch.uint8, device=dev)
     for slot, neg in negatives.items():
         ng = neg if (neg.dtype == torch.int64 and neg.is_contiguous()) else neg.long().contiguous()
-        _lib.check(lib.b200kge_x_ns_backward(
+        _lib.check(lib.b200kge_ns_backward(
             MODELS[model], l_norm, C.byref(re_), C.byref(rr), tri.data_ptr(), int(slot), ng.data_ptr(), n, ng.shape[1],
             offset, batch_size or n, d_ent.data_ptr(), d_ent.stride(0), d_rel.data_ptr(), d_rel.stride(0),
             ws.data_ptr(), ws.numel(), _stream(dev)))

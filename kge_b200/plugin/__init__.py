@@ -142,9 +142,11 @@ class _B200ModelMixin:
 
     _b200_name = None
     _b200_scorer_cls = None
-    #: "native": gradient kernels of libb200kge where they exist (dot family, bce/kl); "reference": recompute
-    #: through the reference's dense torch expression (autograd)
-    b200_backward = "reference"
+    #: "native": gradient kernels of libb200kge where they exist (fused 1vsAll step of the dot family with bce / kl:
+    #: recompute, G planes, two split-K tensor-core GEMMs, unfold — validated against the reference's gradients);
+    #: "reference": recompute through the reference's dense torch expression (autograd) — also what every other
+    #: combination falls back to
+    b200_backward = "native"
 
     def __init__(self, config, dataset, configuration_key=None, init_for_load_only=False):
         super().__init__(config=config, dataset=dataset, configuration_key=configuration_key,
@@ -219,7 +221,7 @@ class _B200ModelMixin:
     def _b200_loss_1vsall_backward(self, ent_w, rel_w, triples, loss, offset):
         name = self._b200_name
         if self.b200_backward == "native" and name in ("complex", "distmult", "simple", "cp", "rescal"):
-            return engine.x_train_1vsall_backward(name, ent_w.detach(), rel_w.detach(), triples, loss, offset)
+            return engine.train_1vsall_backward(name, ent_w.detach(), rel_w.detach(), triples, loss, offset)
         e, r = ent_w.detach().requires_grad_(True), rel_w.detach().requires_grad_(True)
         n = triples.shape[0]
         s, p, o = triples[:, 0], triples[:, 1], triples[:, 2]

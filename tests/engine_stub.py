@@ -64,6 +64,12 @@ def loss_dense(scores, labels, loss="bce", offset=0.0, return_rows=False):
     return orc.bce_loss(scores, labels, offset) if loss == "bce" else orc.kl_loss(scores, labels)
 
 
+def train_1vsall_backward(model, ent, rel, triples, loss="bce", offset=0.0):
+    from oracle import kge_fold as kf
+
+    return kf.train_1vsall_backward(model, ent.detach(), rel.detach(), triples.long(), loss, offset)
+
+
 _counter = {"n": 0}
 
 
@@ -80,7 +86,7 @@ def installed():
     from kge_b200 import engine
 
     names = ["score_spo", "score_1vsN", "score_sp_po", "train_1vsall_forward", "score_1vsN_loss",
-             "score_1vsN_loss_csr", "ns_score", "loss_dense", "launch_count"]
+             "score_1vsN_loss_csr", "ns_score", "loss_dense", "train_1vsall_backward", "launch_count"]
     saved = {k: getattr(engine, k) for k in names}
     g = globals()
 

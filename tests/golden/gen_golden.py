@@ -441,6 +441,28 @@ def gen_grads(model, D, loss, tag):
     print("wrote grads", tag, float(out["loss"]))
 
 
+def gen_mid(model, E=5003, R=11, D=128, n=300, ncols=64):
+    """Mid-size outputs of the live reference (several K chunks and several tiles of the tensor-core kernels): the
+    tables are regenerated from seeds at replay time (kge_b200.synthetic / the oracle share the generator), only
+    sampled score columns, row sums and the row-wise scores are stored."""
+    if model == "rescal":
+        D = 48
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.5, seed=4321)
+    tri = orc.make_triples(E, R, n, seed=17)
+    m, _, _ = ref_shim.make_reference_model(model, E, R, D, ent, rel)
+    s, p, o = tri[:, S], tri[:, P], tri[:, O]
+    cols = torch.sort(torch.randperm(E, generator=torch.Generator().manual_seed(23))[:ncols]).values
+    with torch.no_grad():
+        sp, po = m.score_sp(s, p), m.score_po(p, o)
+        out = dict(E=np.int64(E), R=np.int64(R), D=np.int64(D), n=np.int64(n), cols=_np(cols),
+                   sp_cols=_np(sp[:, cols]), po_cols=_np(po[:, cols]),
+                   sp_rowsum=_np(sp.double().sum(1)), po_rowsum=_np(po.double().sum(1)),
+                   sp_rms=np.float64(sp.double().pow(2).mean().sqrt()), po_rms=np.float64(po.double().pow(2).mean().sqrt()),
+                   spo=_np(m.score_spo(s, p, o)))
+    np.savez_compressed(os.path.join(HERE, f"mid_{model}.npz"), **out)
+    print("wrote mid", model, {k: getattr(v, "shape", v) for k, v in out.items()})
+
+
 def main():
     torch.manual_seed(0)
     E, R, n = 97, 7, 13
@@ -466,6 +488,8 @@ def main():
         gen_grads(model, 8 if model == "rescal" else 16, "bce", f"{model}_bce")
     gen_grads("complex", 16, "kl", "complex_kl")
     gen_grads("rescal", 8, "kl", "rescal_kl")
+    for model in orc.MODELS:
+        gen_mid(model)
 
 
 if __name__ == "__main__":

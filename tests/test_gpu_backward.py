@@ -1,10 +1,7 @@
-"""Parity tests for EXPERIMENTAL kernels that are not on the default path yet (selected through
-B200KGE_TC_VERSION).  They run only with B200KGE_EXPERIMENTAL=1 so that the regular `-m gpu` suite covers
-exactly what ships; the bar is the same (floating point <= 1e-4 * rms, rank/tie counts bit-exact on the
-kernel's own scores).
-
-    B200KGE_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -x -q
-"""
+"""Parity tests of the gradient kernels, validated on a B200 in round 2: the pre-split fp16 GEMM with
+split-K accumulation, the analytic backward of the fused 1vsAll step (dot family, BCE and KL) against gradients
+of the live reference (tests/golden/grads_*.npz) and against the CPU algebra at medium sizes, and the fused
+negative-sampling backward."""
 import os
 
 import numpy as np
@@ -13,9 +10,7 @@ import torch
 
 from oracle import kge_oracle as orc
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200KGE_EXPERIMENTAL") != "1",
-                                 reason="experimental kernels: set B200KGE_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 S, P, O = 0, 1, 2
@@ -44,7 +39,7 @@ def _assert_close(got, ref, what, tol=TOL):
     assert err <= tol * rms, f"{what}: max|d|={err:.3e} rms={rms:.3e} ratio={err / rms:.2e}"
 
 
-def test_x_gemm_nt_vs_fp64(eng):
+def test_gemm_nt_vs_fp64(eng):
     """Pre-split fp16 GEMM (the backward's building block; also exercises presplit + pairwise_tc3 on shapes
     the scorer never sees: long reductions, few rows, K not a multiple of 64, tiny and huge magnitudes)."""
     g = torch.Generator().manual_seed(0)
@@ -53,18 +48,18 @@ def test_x_gemm_nt_vs_fp64(eng):
         a = torch.randn((M, K), generator=g) * sa
         b = torch.randn((N, K), generator=g) * sb
         ref = a.double() @ b.double().t()
-        got = eng.x_gemm_nt(a.cuda(), b.cuda())
+        got = eng.gemm_nt(a.cuda(), b.cuda())
         _assert_close(got, ref, f"gemm {M}x{N}x{K}")
 
 
 @pytest.mark.parametrize("fname", ["grads_complex_bce.npz", "grads_distmult_bce.npz", "grads_simple_bce.npz",
                                    "grads_cp_bce.npz", "grads_rescal_bce.npz", "grads_complex_kl.npz",
                                    "grads_rescal_kl.npz"])
-def test_x_backward_golden(eng, fname):
+def test_backward_golden(eng, fname):
     """Table gradients of one 1vsAll step (BCE with offset, KL) against the live reference's backward."""
     g = _load(fname)
     model, loss = fname[len("grads_"):-4].split("_")
-    d_ent, d_rel = eng.x_train_1vsall_backward(model, g["ent"].cuda(), g["rel"].cuda(), g["triples"].cuda(), loss,
+    d_ent, d_rel = eng.train_1vsall_backward(model, g["ent"].cuda(), g["rel"].cuda(), g["triples"].cuda(), loss,
                                                float(g["offset"]))
     _assert_close(d_ent, g["d_ent"], fname + " d_ent")
     _assert_close(d_rel, g["d_rel"], fname + " d_rel")
@@ -72,7 +67,7 @@ def test_x_backward_golden(eng, fname):
 
 @pytest.mark.parametrize("loss", ["bce", "kl"])
 @pytest.mark.parametrize("model,D", [("complex", 128), ("distmult", 64), ("simple", 128), ("cp", 64), ("rescal", 24)])
-def test_x_backward_medium(eng, model, D, loss):
+def test_backward_medium(eng, model, D, loss):
     """Ragged medium shapes with duplicate rows, against the analytic CPU assembly (oracle/kge_fold.py, itself
     pinned to autograd and to the reference's gradients)."""
     from oracle import kge_fold as kf
@@ -83,14 +78,14 @@ def test_x_backward_medium(eng, model, D, loss):
     tri[5] = tri[4]
     off = 0.5 if loss == "bce" else 0.0
     ref_e, ref_r = kf.train_1vsall_backward(model, ent.double(), rel.double(), tri, loss, off)
-    d_ent, d_rel = eng.x_train_1vsall_backward(model, ent.cuda(), rel.cuda(), tri.cuda(), loss, off)
+    d_ent, d_rel = eng.train_1vsall_backward(model, ent.cuda(), rel.cuda(), tri.cuda(), loss, off)
     _assert_close(d_ent, ref_e, f"{model} d_ent")
     _assert_close(d_rel, ref_r, f"{model} d_rel")
 
 
 @pytest.mark.parametrize("model,D,ln", [("complex", 64, 1.0), ("distmult", 32, 1.0), ("simple", 64, 1.0), ("cp", 64, 1.0),
                                         ("rescal", 16, 1.0), ("transe", 64, 1.0), ("transe", 64, 2.0), ("rotate", 64, 1.0)])
-def test_x_ns_backward(eng, model, D, ln):
+def test_ns_backward(eng, model, D, ln):
     """Fused negative-sampling backward (S and O slots, positive column included) against the CPU algebra
     (oracle/kge_fold.ns_backward, itself pinned to the reference job's gradients)."""
     from oracle import kge_fold as kf
@@ -101,7 +96,7 @@ def test_x_ns_backward(eng, model, D, ln):
     g = torch.Generator().manual_seed(3)
     negs = {S: torch.randint(0, E, (n, K), generator=g), O: torch.randint(0, E, (n, K + 7), generator=g)}
     ref_e, ref_r = kf.ns_backward(model, ent.double(), rel.double(), tri, negs, 0.25, ln)
-    d_ent, d_rel = eng.x_ns_backward(model, ent.cuda(), rel.cuda(), tri.cuda(), {k: v.cuda() for k, v in negs.items()},
+    d_ent, d_rel = eng.ns_backward(model, ent.cuda(), rel.cuda(), tri.cuda(), {k: v.cuda() for k, v in negs.items()},
                                      0.25, ln)
     _assert_close(d_ent, ref_e, f"{model} d_ent")
     _assert_close(d_rel, ref_r, f"{model} d_rel")

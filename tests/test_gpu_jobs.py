@@ -144,7 +144,7 @@ def test_training_epoch_through_plugin(model, splits):
 @pytest.mark.parametrize("model", ["complex", "distmult", "simple", "cp", "rescal"])
 @pytest.mark.parametrize("loss", ["kl", "bce"])
 def test_training_epoch_native_backward(model, loss, splits):
-    """The fused job with the gradient kernels of libb200kge (b200kge_x_train_1vsall_backward: recompute, G planes,
+    """The fused job with the gradient kernels of libb200kge (b200kge_train_1vsall_backward: recompute, G planes,
     two split-K tensor-core GEMMs, unfold) instead of the reference's autograd: two epochs track the reference."""
     torch.manual_seed(0)
     init = ju.make_job(model, E, R, D, splits, device="cpu", train_type="1vsAll", loss=loss, batch_size=64)

@@ -344,3 +344,28 @@ def test_edge_cases(eng):
     eng.score_1vsN("complex", "sp_", ce, cr, ce, one.int(), (one % 3).int(), out=big[:, :100])
     assert float(big[0, 100]) == -7.0
     _assert_close(big[:, :100], orc.score_sp("complex", ent, rel, one.cpu(), one.cpu() % 3), "strided out")
+
+
+@pytest.mark.parametrize("model", orc.MODELS)
+def test_mid_size_golden(eng, model):
+    """The CUDA path against outputs of the LIVE reference at a mid-size shape (E=5003, D=128, n=300; sampled
+    columns + row sums, tests/golden/mid_*.npz): closes the chain reference -> oracle -> CUDA at a shape where the
+    tensor-core kernels run several K chunks and tiles in both dimensions."""
+    import numpy as np
+    z = np.load(os.path.join(GOLDEN, f"mid_{model}.npz"))
+    E, R, D, n = int(z["E"]), int(z["R"]), int(z["D"]), int(z["n"])
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.5, seed=4321)
+    tri = orc.make_triples(E, R, n, seed=17).cuda()
+    ce, cr = ent.cuda(), rel.cuda()
+    s, p, o = tri[:, S].contiguous(), tri[:, P].contiguous(), tri[:, O].contiguous()
+    cols = torch.from_numpy(z["cols"])
+    x = eng.score_sp_po(model, ce, cr, s, p, o).cpu()
+    for got, key in ((x[:, :E], "sp"), (x[:, E:], "po")):
+        rms = float(z[key + "_rms"])
+        err = float((got[:, cols] - torch.from_numpy(z[key + "_cols"])).abs().max())
+        assert err <= TOL * rms, (model, key, err / rms)
+        # row sums: every column enters (errors add like sqrt(E) at worst)
+        serr = float((got.double().sum(1) - torch.from_numpy(z[key + "_rowsum"])).abs().max())
+        assert serr <= TOL * rms * E ** 0.5, (model, key, serr / rms)
+    spo = eng.score_spo(model, ce, cr, ce, s, p, o).cpu()
+    assert float((spo - torch.from_numpy(z["spo"])).abs().max()) <= TOL * float(z["sp_rms"])

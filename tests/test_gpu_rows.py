@@ -192,3 +192,52 @@ def test_loss_with_csr_labels(eng, model, D, loss):
                                                  tri[:, P].cuda(), loss, off, eps, return_rows=True)
             assert abs(float(got) - ref) <= 1e-4 * abs(ref), (model, loss, combine, eps, float(got), ref)
             assert abs(float(rws.sum()) - ref) <= 1e-4 * abs(ref)
+
+
+@pytest.mark.parametrize("model,D", [("complex", 128), ("distmult", 64), ("rescal", 24), ("simple", 64)])
+def test_rank_with_csr_filter_is_bit_identical_to_dense_filter(eng, model, D):
+    """Filtered ranking with the known answers as CSR (consumed by the tensor-core epilogue's per-thread cursor)
+    against the same call with the reference's dense +inf label matrix (eval_entity_ranking.py:489-531,561-566):
+    integer counts, bit-identical; the row's own answer stays in (:287-290); ragged tiles, empty rows, rows with
+    many listed columns, chunked candidates."""
+    E, R, n = 5003, 5, 150
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.5)
+    tri = orc.make_triples(E, R, n).cuda()
+    ce, cr = ent.cuda(), rel.cuda()
+    s, p, o = tri[:, S].contiguous(), tri[:, P].contiguous(), tri[:, O].contiguous()
+    both = torch.cat([s, o])
+    x = eng.score_sp_po(model, ce, cr, s, p, o, both)
+    ar = torch.arange(n, device="cuda")
+    true2n = torch.cat([x[ar, n + ar], x[ar, 2 * n + ar]]).contiguous()
+    g = torch.Generator().manual_seed(3)
+    counts = torch.randint(0, 40, (2 * n,), generator=g)
+    counts[5] = 0
+    counts[7] = 900
+    own = torch.cat([o, s]).cpu()
+    cols, offs = [], [0]
+    for r in range(2 * n):
+        c = torch.randperm(E, generator=g)[: int(counts[r])]
+        c = torch.unique(torch.cat([c, own[r:r + 1]]))          # sorted, contains the own answer
+        cols.append(c)
+        offs.append(offs[-1] + c.numel())
+    cols, offs = torch.cat(cols), torch.tensor(offs)
+    dense = torch.zeros((2 * n, E))
+    for r in range(2 * n):
+        dense[r, cols[offs[r]:offs[r + 1]]] = float("inf")
+    dense[torch.arange(2 * n), own] = 0.0
+    for lo, hi in ((0, E), (1000, 3333)):                          # whole table and one chunk of candidates
+        cand = ce[lo:hi]
+        keep = (cols >= lo) & (cols < hi)
+        rows = torch.repeat_interleave(torch.arange(2 * n), offs[1:] - offs[:-1])
+        coffs = torch.zeros(2 * n + 1, dtype=torch.int64)
+        coffs[1:] = torch.cumsum(torch.bincount(rows[keep], minlength=2 * n), 0)
+        r1, t1 = eng.rank_sp_po(model, ce, cr, ce, cand, true2n, s, p, o, None, dense[:, lo:hi].contiguous().cuda())
+        r2, t2 = eng.rank_sp_po_csr(model, ce, cr, ce, cand, true2n, coffs.cuda(), (cols[keep] - lo).cuda(),
+                                    (own - lo).cuda(), s, p, o)
+        assert torch.equal(r1, r2) and torch.equal(t1, t2)
+        if lo == 0:
+            assert int(t2.min()) >= 1                               # the own answer is a tie of itself
+    if model != "rescal":
+        with pytest.raises(NotImplementedError):                    # CUDA-core path: dense filter only
+            eng.rank_sp_po_csr(model, ce, cr, ce, ce, true2n[:16], coffs[:17].cuda() * 0, cols[:0].cuda(), None,
+                               s[:8], p[:8], o[:8])

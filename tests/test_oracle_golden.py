@@ -209,3 +209,23 @@ def test_reciprocal_relations_model_matches_reference(base):
     _close(orc.reciprocal_score_sp_po(base, ent, rel2, s, p, o, R, sub), g["sp_po_subset"], "sp_po subset")
     with pytest.raises(Exception, match="undirected"):
         orc.reciprocal_score_spo(base, ent, rel2, s, p, o, None, R)
+
+
+@pytest.mark.parametrize("model", orc.MODELS)
+def test_mid_size_scores_match_reference(model):
+    """Mid-size live-reference goldens (E=5003, D=128, n=300: several K chunks and tiles of the tensor-core
+    kernels): sampled score columns, row sums and row-wise scores pin the oracle at a shape where the CUDA path
+    runs its full pipeline (tests/test_gpu_parity.py::test_mid_size_golden replays them on the GPU)."""
+    z = np.load(os.path.join(GOLDEN, f"mid_{model}.npz"))
+    E, R, D, n = int(z["E"]), int(z["R"]), int(z["D"]), int(z["n"])
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.5, seed=4321)
+    tri = orc.make_triples(E, R, n, seed=17)
+    cols = torch.from_numpy(z["cols"])
+    sp = orc.score_sp(model, ent, rel, tri[:, 0], tri[:, 1])
+    po = orc.score_po(model, ent, rel, tri[:, 1], tri[:, 2])
+    for got, key in ((sp, "sp"), (po, "po")):
+        rms = float(z[key + "_rms"])
+        assert float((got[:, cols] - torch.from_numpy(z[key + "_cols"])).abs().max()) <= 2e-6 * rms
+        assert float((got.double().sum(1) - torch.from_numpy(z[key + "_rowsum"])).abs().max()) <= 2e-6 * rms * E ** 0.5
+    spo = orc.score_spo(model, ent, rel, tri[:, 0], tri[:, 1], tri[:, 2])
+    assert float((spo - torch.from_numpy(z["spo"])).abs().max()) <= 2e-6 * float(z["sp_rms"])
