@@ -539,6 +539,49 @@ int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
   const int epi = (loss_kind == B200KGE_LOSS_BCE) ? EPI_BCE : EPI_KL;
   const float scale = 1.0f / (float)n;       // "/ batch_size"   train_1vsAll.py:65,76
   Folded f0 = folded_problem(model, B200KGE_SP_, E.dim, l_norm), f1 = folded_problem(model, B200KGE__PO, E.dim, l_norm);
+  {
+    // Pre-split tensor-core path (dot family except CP, whose directions read different table columns): the whole
+    // step is TWO launches — prologue (gather + both folds + operand split of queries and table + labels) and the
+    // scorer with the loss reduction and its finalisation fused (last-CTA ticket).
+    const char* env_v = getenv("B200KGE_TC_VERSION");
+    const int tcv = env_v ? atoi(env_v) : 3;
+    const int K = f0.K;
+    const bool presplit = f0.col_off == f1.col_off && f0.pair_op == PAIR_DOT && model != B200KGE_CP &&
+                          (precision == B200KGE_PREC_AUTO || precision == B200KGE_PREC_F16X3) && K >= 32 && K <= 1024 &&
+                          n >= 16 && E.rows < (1ll << 31) && (tcv == 3 || tcv == 4) &&
+                          ((size_t)round_up(K, 64) + (model == B200KGE_RESCAL ? E.dim : 0)) * 4 <= 48 * 1024;
+    if (presplit) {
+      const int64_t nq = 2 * n, m = E.rows;
+      const int Kp = (int)round_up(K, 64);
+      SplitSet SQ{nullptr, 0, nullptr, 0, nq, nq, K, Kp, nullptr, nullptr, nullptr};
+      SplitSet ST{E.base, E.ld, nullptr, f0.col_off, m, m + 32, K, Kp, nullptr, nullptr, nullptr};
+      SQ.hi = ws.take((size_t)nq * Kp * 2); SQ.lo = ws.take((size_t)nq * Kp * 2);
+      SQ.inv_scale = (float*)ws.take((size_t)nq * 4);
+      ST.hi = ws.take((size_t)m * Kp * 2); ST.lo = ws.take((size_t)m * Kp * 2);
+      ST.inv_scale = (float*)ws.take((size_t)(m + 32) * 4);
+      int64_t* lab = (int64_t*)ws.take((size_t)n * 2 * 8);
+      uint8_t* scratch = (uint8_t*)ws.take(1024);
+      const int nch = tcv == 4 ? tc4_nchunks(nq, m) : tc3_nchunks(nq, m);
+      const int F = (loss_kind == B200KGE_LOSS_BCE) ? 2 : 5;
+      float* part = (float*)ws.take((size_t)nq * nch * F * 4);
+      if (!SQ.hi || !SQ.lo || !SQ.inv_scale || !ST.hi || !ST.lo || !ST.inv_scale || !lab || !scratch || !part) {
+        set_error("workspace too small");
+        return B200KGE_ERR_WORKSPACE;
+      }
+      unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + 512);
+      if ((rc = launch_prep_split_1vsall(model, E, R, triples, n, SQ, ST, lab, ticket, st))) return rc;
+      EpiParams P = empty_epi();
+      P.label_idx = lab;
+      P.offset = (loss_kind == B200KGE_LOSS_BCE) ? offset : 0.f;
+      P.part = part; P.nchunks = nch;
+      if (tcv == 4) {
+        if ((rc = launch_pairwise_tc4(epi, SQ, ST, P, st))) return rc;
+        return launch_loss_finalize(loss_kind, part, nch, nq, loss_out, nullptr, scale, 0, scratch, 1, st);
+      }
+      P.fin_out = loss_out; P.fin_ticket = ticket; P.fin_scale = scale; P.fin_rows = nq;
+      return launch_pairwise_tc3(epi, SQ, ST, P, st);
+    }
+  }
   if (f0.col_off == f1.col_off) {
     // sp_ and _po rows stacked into ONE problem of 2n query rows against the same table:
     // prologue (unpack + both folds + labels) = 1 launch, scoring + loss + finalisation = 1 launch

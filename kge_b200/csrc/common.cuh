@@ -113,6 +113,13 @@ struct EpiParams {
   int64_t csr_nnz;
   int csr_extra;
   const int64_t* csr_skip;
+  // fused finalisation (tensor-core kernels, losses): when fin_out != NULL the last CTA to finish (fin_ticket, zeroed
+  // by the caller's prologue) reduces the partials of all fin_rows rows in a fixed order and writes
+  // fin_scale * sum to fin_out[0] — the separate loss_finalize launch and its launch gap disappear
+  float* fin_out;
+  unsigned int* fin_ticket;
+  float fin_scale;
+  int64_t fin_rows;
 };
 
 // lower bound of `key` in the sorted segment col[lo, hi)
@@ -312,6 +319,32 @@ __device__ __forceinline__ float finalize_row(const float* __restrict__ part, in
   }
 }
 
+
+// same as finalize_row, reading the partials through L2 (they were written by other SMs of the same kernel)
+template <int LOSS>
+__device__ __forceinline__ float finalize_row_cg(const float* __restrict__ part, int nchunks, int64_t r) {
+  if constexpr (LOSS == B200KGE_LOSS_BCE) {
+    float a = 0.f, b = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(part + (r * nchunks + c) * 2));
+      a += v.x; b += v.y;
+    }
+    return a - b;
+  } else {
+    RowState<EPI_KL> st;
+    st.init();
+    for (int c = 0; c < nchunks; ++c) {
+      const float* p = part + (r * nchunks + c) * 5;
+      RowState<EPI_KL> o;
+      o.m = __ldcg(p); o.s = __ldcg(p + 1); o.y_sum = __ldcg(p + 2); o.yx = __ldcg(p + 3); o.ylogy = __ldcg(p + 4);
+      st.combine(o);
+    }
+    const float lse = st.m + logf(st.s);
+    const float yc = fmaxf(st.y_sum, 1e-12f);
+    const float w = st.y_sum / yc;
+    return (st.y_sum > 0.f) ? (st.ylogy / yc - w * logf(yc) - st.yx / yc + lse * w) : 0.f;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Internal kernels' host launchers (one per .cu file).

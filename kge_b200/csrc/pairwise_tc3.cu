@@ -222,11 +222,42 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
     }
   }
 
+  if constexpr (EPI == EPI_BCE || EPI == EPI_KL) {
+    if (prm.epi.fin_out) __threadfence();        // this CTA's partial row states are visible device-wide
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+  if constexpr (EPI == EPI_BCE || EPI == EPI_KL) {
+    // fused finalisation: the last CTA to get here sums all rows in a fixed order (thread t: rows t, t + 384, ...;
+    // shuffle tree; the 12 warp sums in index order) — deterministic, independent of which CTA happens to be last
+    const EpiParams& P = prm.epi;
+    if (P.fin_out) {
+      __shared__ int s_last;
+      __shared__ float s_red[NTHREADS3 / 32];
+      if (threadIdx.x == 0) s_last = (atomicAdd(P.fin_ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        constexpr int LOSS = (EPI == EPI_BCE) ? B200KGE_LOSS_BCE : B200KGE_LOSS_KL;
+        float acc = 0.f;
+        for (int64_t r = threadIdx.x; r < P.fin_rows; r += NTHREADS3) acc += finalize_row_cg<LOSS>(P.part, P.nchunks, r);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) s_red[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          float tot = 0.f;
+#pragma unroll
+          for (int w = 0; w < NTHREADS3 / 32; ++w) tot += s_red[w];
+          P.fin_out[0] = P.fin_scale * tot;
+          *P.fin_ticket = 0u;
+        }
+      }
+    }
   }
 }
 

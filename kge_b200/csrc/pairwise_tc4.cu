@@ -33,7 +33,6 @@ namespace b200kge {
 namespace {
 
 constexpr int TM = 128;     // query rows per CTA (cluster: 256)
-constexpr int TNH = 128;    // entity rows staged per CTA (cluster N: 256)
 constexpr int TN = 256;
 constexpr int TKH = 64;     // halfs per K chunk (128-byte swizzle atom)
 constexpr int NSLOT = 6;

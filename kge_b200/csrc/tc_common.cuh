@@ -427,6 +427,10 @@ struct SplitSet {
   void* hi; void* lo; float* inv_scale;
 };
 int launch_presplit(const SplitSet& A, const SplitSet& B, cudaStream_t st);   // B.rows may be 0
+// fold + split of the 2n stacked query rows of a 1vsAll batch AND the split of the table, labels, ticket: one launch
+int launch_prep_split_1vsall(int model, const Rows& ent, const Rows& rel, const int64_t* triples, int64_t n,
+                             const SplitSet& Qs, const SplitSet& Ts, int64_t* labels2n, unsigned int* ticket,
+                             cudaStream_t st);
 int tc3_nchunks(int64_t nq, int64_t m);
 int launch_pairwise_tc3(int epi_kind, const SplitSet& Q, const SplitSet& T, const EpiParams& P, cudaStream_t st);
 // CTA-pair version on the same planes (pairwise_tc4.cu), experimental: B200KGE_TC_VERSION=4.
