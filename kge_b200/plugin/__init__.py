@@ -137,6 +137,79 @@ class _Loss1vsAllFn(torch.autograd.Function):
         return d_ent * g, d_rel * g, None, None, None, None
 
 
+def _penalty_torch(emb, w, regularize, rw, p, weighted, indexes):
+    """LookupEmbedder.penalty's expression (lookup_embedder.py:123-177) on a weight tensor — the differentiable
+    form behind _PenaltyFn.backward."""
+    if not weighted:
+        par = emb._abs_complex(w) if (regularize == "n3" and emb.space == "complex") else w
+        return (rw / p * par.norm(p=p) ** p).sum()
+    uniq, counts = torch.unique(indexes, return_counts=True)
+    par = w[uniq.long()]
+    if regularize == "n3" and emb.space == "complex":
+        par = emb._abs_complex(par)
+    if (p % 2 == 1) and regularize != "n3":
+        par = torch.abs(par)
+    return (rw / p * (par ** p * counts.float().view(-1, 1))).sum() / len(indexes)
+
+
+class _PenaltyFn(torch.autograd.Function):
+    """Forward: the Lp / N3 row kernel (b200kge_lookup_penalty).  Backward: autograd of the reference expression."""
+
+    @staticmethod
+    def forward(ctx, w, emb, regularize, rw, p, weighted, indexes):
+        ctx.args = (emb, regularize, rw, p, weighted, indexes)
+        ctx.save_for_backward(w)
+        return engine.lookup_penalty(w.detach(), regularize, rw, float(p), weighted, indexes, emb.space)
+
+    @staticmethod
+    def backward(ctx, g):
+        (w,) = ctx.saved_tensors
+        wd = w.detach().requires_grad_(True)
+        with torch.enable_grad():
+            (gw,) = torch.autograd.grad(_penalty_torch(ctx.args[0], wd, *ctx.args[1:]), wd)
+        return gw * g, None, None, None, None, None, None
+
+
+def _install_embedder_kernels(emb):
+    """Serve a plain LookupEmbedder's penalty() and _normalize_embeddings() (lookup_embedder.py:64-69,122-177) from
+    the row kernels of libb200kge when its table lives on a CUDA device.  Patched on the INSTANCE: class, parameter
+    names and checkpoints stay the reference's; the post-batch normalisation hooks (prepare_job, :71-80) pick the
+    patched method up through `self`."""
+    if type(emb) is not LookupEmbedder or getattr(emb, "_b200_patched", False):
+        return
+    cls = type(emb)
+
+    def penalty(**kwargs):
+        w = emb._embeddings.weight
+        if (not w.is_cuda or emb.regularize not in ("lp", "n3") or emb.get_option("regularize_weight") == 0.0
+                or (emb.dropout.p > 0 and emb.training)):
+            return cls.penalty(emb, **kwargs)
+        if emb.regularize == "n3":
+            p = 3
+        else:
+            p = emb.get_option("regularize_args.p") if emb.has_option("regularize_args.p") else 2
+        weighted = bool(emb.get_option("regularize_args.weighted"))
+        indexes = kwargs.get("indexes") if weighted else None
+        rw = emb._get_regularize_weight()
+        if torch.is_grad_enabled() and w.requires_grad:
+            val = _PenaltyFn.apply(w, emb, emb.regularize, rw, p, weighted, indexes)
+        else:
+            val = engine.lookup_penalty(w.detach(), emb.regularize, rw, float(p), weighted, indexes, emb.space)
+        return super(cls, emb).penalty(**kwargs) + [(f"{emb.configuration_key}.L{p}_penalty", val)]
+
+    def _normalize_embeddings():
+        w = emb._embeddings.weight
+        if emb.normalize_p > 0 and w.is_cuda and w.is_contiguous():
+            with torch.no_grad():
+                engine.normalize_rows_(w.data, float(emb.normalize_p))
+        else:
+            cls._normalize_embeddings(emb)
+
+    emb.penalty = penalty
+    emb._normalize_embeddings = _normalize_embeddings
+    emb._b200_patched = True
+
+
 class _B200ModelMixin:
     """Index-level overrides (kge_model.py:663-789): read the tables in place when possible."""
 
@@ -153,6 +226,9 @@ class _B200ModelMixin:
                          init_for_load_only=init_for_load_only)
         # swap the reference scorer for ours (same configuration key, same options)
         self._scorer = self._b200_scorer_cls(config, dataset, self.configuration_key)
+        # penalties and row normalisation of plain LookupEmbedders through the row kernels
+        for emb in {id(e): e for e in (self.get_s_embedder(), self.get_p_embedder(), self.get_o_embedder())}.values():
+            _install_embedder_kernels(emb)
 
     # -- helpers
     def b200_fusable(self):

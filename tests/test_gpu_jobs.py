@@ -167,3 +167,44 @@ def test_training_epoch_native_backward(model, loss, splits):
         losses[tag] = out
     assert losses["native"][0] == pytest.approx(losses["ref"][0], rel=REL)
     assert losses["native"][1] == pytest.approx(losses["ref"][1], rel=1e-3)
+
+
+@pytest.mark.parametrize("model,extra", [
+    ("complex", {"entity_embedder.regularize": "n3", "entity_embedder.regularize_weight": 0.05,
+                 "entity_embedder.regularize_args.weighted": True,
+                 "relation_embedder.regularize": "lp", "relation_embedder.regularize_weight": 0.01}),
+    ("distmult", {"entity_embedder.regularize": "lp", "entity_embedder.regularize_weight": 0.02,
+                  "entity_embedder.regularize_args.p": 3, "entity_embedder.regularize_args.weighted": True}),
+    ("transe", {"entity_embedder.normalize.p": 2.0, "relation_embedder.regularize": "lp",
+                "relation_embedder.regularize_weight": 0.01}),
+])
+def test_training_with_penalties_and_normalisation(model, extra, splits):
+    """SURVEY 8f-3 through the jobs: Lp / N3 penalties (weighted and unweighted; forward by the row kernel, backward by
+    autograd of the reference expression) and the post-batch row normalisation hook on the plugin model reproduce the
+    reference's avg_penalty / avg_cost over two training epochs."""
+    torch.manual_seed(0)
+    init = ju.make_job(model, E, R, D, splits, device="cpu", train_type="1vsAll", loss="kl", batch_size=64)
+    traces = {}
+    for tag, dev in (("ref", "cpu"), ("plugin", "cuda")):
+        name = model if tag == "ref" else "b200_" + model
+        ex = {f"{name}.{k}": v for k, v in extra.items()}
+        kw = {"job_class": "B200TrainingJob1vsAll"} if tag == "plugin" else {}
+        job = ju.make_job(name, E, R, D, splits, device=dev, train_type="1vsAll", loss="kl", batch_size=64,
+                          forward_only=False, extra=ex, **kw)
+        ju.copy_tables(init, job)
+        if tag == "plugin":
+            assert getattr(job.model.get_s_embedder(), "_b200_patched", False)
+        out = []
+        for ep in range(2):
+            job.epoch += 1
+            if job.loader is None:
+                job._prepare()
+                for f in job.pre_run_hooks:          # Job.run() would call these (initial normalisation)
+                    f(job)
+            ju.seed_all(10 + ep)
+            tr = job.run_epoch()
+            out.append((tr["avg_loss"], tr["avg_penalty"], tr["avg_cost"]))
+        traces[tag] = out
+    for ep in range(2):
+        for a, b in zip(traces["plugin"][ep], traces["ref"][ep]):
+            assert a == pytest.approx(b, rel=1e-3 if ep else REL, abs=1e-7)
