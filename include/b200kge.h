@@ -229,6 +229,13 @@ int b200kge_ns_score(int model, float l_norm, const b200kge_rows_t* s, const b20
                      const int64_t* neg, int64_t n, int64_t K, int with_positive, float* out,
                      int64_t ldo, b200kge_stream_t stream);
 
+/* On-device uniform negative sampling: out[i*K + k] ~ U{0, ..., vocab-1}, the device counterpart of
+ * KgeUniformSampler._sample (kge/util/sampler.py:588-596: torch.randint on the CPU + a host->device copy of the ids).
+ * Counter-based Philox4x32-10: the result depends on (seed, offset, position) only; use a fresh `offset` per call
+ * (e.g. a batch counter) for independent draws.  No filtering of positives (sampler.py default filtering off). */
+int b200kge_sample_uniform(uint64_t seed, uint64_t offset, int64_t vocab, int64_t n, int64_t K, int64_t* out,
+                           b200kge_stream_t stream);
+
 /* One whole 1vsAll forward step (train_1vsAll.py:48-82) for a batch of triples [n,3] (int64,
  * row-major s,p,o): fused score_sp+loss and score_po+loss against the whole entity table, both
  * directions stacked into one launch of 2n query rows where the model allows it.  loss_out[0]

@@ -522,6 +522,13 @@ int b200kge_ns_score(int model, float l_norm, const b200kge_rows_t* s, const b20
                    out, ldo, col0, st);
 }
 
+int b200kge_sample_uniform(uint64_t seed, uint64_t offset, int64_t vocab, int64_t n, int64_t K, int64_t* out,
+                           b200kge_stream_t stream) {
+  if (vocab <= 0) { set_error("vocabulary size must be positive"); return B200KGE_ERR_INVALID; }
+  if (n < 0 || K < 0 || (!out && n * K > 0)) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  return launch_sample_uniform(seed, offset, vocab, n * K, out, (cudaStream_t)stream);
+}
+
 int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
                                  const b200kge_rows_t* ent, const b200kge_rows_t* rel,
                                  const int64_t* triples, int64_t n, int loss_kind, float offset,
@@ -576,6 +583,10 @@ int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
       P.part = part; P.nchunks = nch;
       if (tcv == 4) {
         if ((rc = launch_pairwise_tc4(epi, SQ, ST, P, st))) return rc;
+        return launch_loss_finalize(loss_kind, part, nch, nq, loss_out, nullptr, scale, 0, scratch, 1, st);
+      }
+      if ((nq + 127) / 128 > 120) {      // more query tiles than the scratch holds counters for: separate finaliser
+        if ((rc = launch_pairwise_tc3(epi, SQ, ST, P, st))) return rc;
         return launch_loss_finalize(loss_kind, part, nch, nq, loss_out, nullptr, scale, 0, scratch, 1, st);
       }
       P.fin_out = loss_out; P.fin_ticket = ticket; P.fin_scale = scale; P.fin_rows = nq;

@@ -125,8 +125,8 @@ prep_split_1vsall_kernel(Rows ent, Rows rel, const int64_t* __restrict__ tri, in
   if (threadIdx.x == 0) {
     labels2n[b] = sp ? oi : si;
     bad_any = 0;
-    if (b == 0 && ticket) *ticket = 0u;
   }
+  if (b == 0 && ticket && threadIdx.x < 128) ticket[threadIdx.x] = 0u;      // finalisation counters (512 bytes)
   float* q = sh;
   if constexpr (MODEL == B200KGE_RESCAL) {
     float* sh_a = sh + Kp;

@@ -201,4 +201,45 @@ int launch_ns(int model, float l_norm, const Rows& s, const Rows& p, const Rows&
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// On-device uniform negative sampling: KgeUniformSampler._sample (sampler.py:588-596) is
+// torch.randint(vocabulary_size, (n, num_samples)) on the CPU inside DataLoader workers, followed by a host->device copy
+// of n*K int64 per slot; here the ids are drawn where they are consumed.  Counter-based Philox4x32-10 (Salmon et al.,
+// SC'11): element e of the call uses counter (e / 2, offset) under key (seed), so results depend on (seed, offset, e)
+// only — reproducible, no generator state.  Each 64-bit draw r maps to floor(r * vocab / 2^64) (bias <= vocab / 2^64).
+namespace {
+
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+__global__ void __launch_bounds__(256)
+sample_uniform_kernel(uint64_t seed, uint64_t offset, uint64_t vocab, int64_t total, int64_t* __restrict__ out) {
+  const int64_t pair = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;      // two ids per Philox block
+  if (2 * pair >= total) return;
+  uint32_t c[4] = {(uint32_t)pair, (uint32_t)((uint64_t)pair >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const uint64_t r0 = ((uint64_t)c[1] << 32) | c[0], r1 = ((uint64_t)c[3] << 32) | c[2];
+  out[2 * pair] = (int64_t)__umul64hi(r0, vocab);
+  if (2 * pair + 1 < total) out[2 * pair + 1] = (int64_t)__umul64hi(r1, vocab);
+}
+
+}  // namespace
+
+int launch_sample_uniform(uint64_t seed, uint64_t offset, int64_t vocab, int64_t total, int64_t* out, cudaStream_t st) {
+  if (total <= 0) return 0;
+  const int64_t pairs = (total + 1) / 2;
+  sample_uniform_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(seed, offset, (uint64_t)vocab, total, out);
+  B2K_LAUNCH_CHECK("sample_uniform_kernel");
+  return 0;
+}
+
 }  // namespace b200kge

@@ -352,6 +352,17 @@ def ns_score(model: str, ent, rel, triples, negatives, slot: int, with_positive:
     return out
 
 
+def sample_uniform(n: int, K: int, vocab: int, seed: int, offset: int, device) -> torch.Tensor:
+    """[n, K] int64 ids ~ U{0..vocab-1} drawn on the device (Philox4x32-10 keyed by seed, counter = (position, offset))."""
+    lib = _lib.load()
+    out = torch.empty((n, K), dtype=torch.int64, device=device)
+    if not out.is_cuda:
+        raise RuntimeError("kge_b200 runs on CUDA (sm_100) tensors only; there is no CPU path")
+    _lib.check(lib.b200kge_sample_uniform(seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), vocab, n, K, out.data_ptr(),
+                                          _stream(out.device)))
+    return out
+
+
 def train_1vsall_forward(model: str, ent, rel, triples, loss: str = "bce", offset: float = 0.0,
                          l_norm: float = 1.0, precision: str = "auto", out=None, workspace=None):
     """One fused 1vsAll forward step for device-resident triples [n,3]; returns the 0-d loss

@@ -146,17 +146,50 @@ class B200TrainingJobKvsAll(TrainingJobKvsAll):
 class B200TrainingJobNegativeSampling(TrainingJobNegativeSampling):
     """`TrainingJobNegativeSampling` (train_negative_sampling.py:103-164): per slot ONE kernel gathers the sampled
     rows and scores them, with the positive triple in column 0 — neither `[n*K, D]` gathers (`triple`
-    implementation, sampler.py:294-305) nor scoring against all unique targets (`batch`, :306-339)."""
+    implementation, sampler.py:294-305) nor scoring against all unique targets (`batch`, :306-339).
+
+    With `user.b200_device_sampling: true` (LibKGE's free-form `user.*` option space) and the default sampler
+    settings (uniform, not shared, no filtering) the negatives are also DRAWN on the device (Philox, keyed by the
+    torch seed, counter = batch / slot): the DataLoader workers only slice the triples, and no [n, K] id tensors
+    travel host -> device (KgeUniformSampler._sample, sampler.py:588-596, is a CPU torch.randint)."""
 
     def __init__(self, config, dataset, parent_job=None, model=None, forward_only=False):
         super().__init__(config, dataset, parent_job, model=model, forward_only=forward_only)
+        try:
+            want = bool(config.get("user.b200_device_sampling"))
+        except KeyError:
+            want = False
+        sm = self._sampler
+        self._device_sampling = bool(
+            want and type(sm).__name__ == "KgeUniformSampler" and not sm.shared and not any(sm.filter_positives))
+        self._sample_calls = 0
         if self.__class__ == B200TrainingJobNegativeSampling:
             for f in Job.job_created_hooks:
                 f(self)
 
+    def _get_collate_fun(self):
+        if not self._device_sampling:
+            return super()._get_collate_fun()
+
+        def collate(batch):          # the triples only: negatives are drawn on the device
+            return {"triples": self.dataset.split(self.train_split)[batch, :].long(), "negative_samples": []}
+        return collate
+
+    def _device_negatives(self, n, slot, batch_index):
+        from .. import engine
+
+        sm = self._sampler
+        # one independent stream per (epoch, batch, slot); the key follows torch.manual_seed
+        offset = ((self.epoch * (1 << 24) + batch_index) << 2) | slot
+        self._sample_calls += 1
+        return engine.sample_uniform(n, int(sm.num_samples[slot]), int(sm.vocabulary_size[slot]),
+                                     torch.initial_seed(), offset, self.device)
+
     def _process_subbatch(self, batch_index, batch, subbatch_slice, result):
         model = _fused_model(self.model)
         if model is None or not self.is_forward_only:
+            if self._device_sampling:
+                raise NotImplementedError("user.b200_device_sampling needs a b200_* model (forward-only epochs for now)")
             return super()._process_subbatch(batch_index, batch, subbatch_slice, result)
         batch_size = result.size
         result.prepare_time -= time.time()
@@ -172,7 +205,14 @@ class B200TrainingJobNegativeSampling(TrainingJobNegativeSampling):
             if num_samples <= 0:
                 continue
             result.prepare_time -= time.time()
-            negatives = negs[slot].samples(subbatch_slice if (subbatch_size != batch_size) else None)
+            if self._device_sampling:
+                if negs == [] or len(negs) < 3:
+                    negs = batch["negative_samples"] = [None, None, None]
+                if negs[slot] is None:          # drawn once per batch and slot, sliced per sub-batch
+                    negs[slot] = self._device_negatives(batch_size, slot, batch_index)
+                negatives = negs[slot][subbatch_slice]
+            else:
+                negatives = negs[slot].samples(subbatch_slice if (subbatch_size != batch_size) else None)
             result.prepare_time += time.time()
 
             result.forward_time -= time.time()

@@ -241,3 +241,51 @@ def test_rank_with_csr_filter_is_bit_identical_to_dense_filter(eng, model, D):
         with pytest.raises(NotImplementedError):                    # CUDA-core path: dense filter only
             eng.rank_sp_po_csr(model, ce, cr, ce, ce, true2n[:16], coffs[:17].cuda() * 0, cols[:0].cuda(), None,
                                s[:8], p[:8], o[:8])
+
+
+def test_device_uniform_sampler(eng):
+    """b200kge_sample_uniform: bit-exact against the Python Philox4x32-10 mirror (integers), reproducible, range-correct,
+    and uniform (chi-square over 64 bins at 1e6 draws)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from philox_ref import sample_uniform
+
+    for n, K, vocab, seed, off in ((3, 7, 14541, 1234, 0), (2, 5, 4800000, 2 ** 40 + 17, 99), (1, 1, 3, 7, 2 ** 33)):
+        got = eng.sample_uniform(n, K, vocab, seed, off, "cuda").cpu().view(-1).tolist()
+        assert got == sample_uniform(n, K, vocab, seed, off)
+    a = eng.sample_uniform(1000, 1000, 40943, 5, 1, "cuda")
+    b = eng.sample_uniform(1000, 1000, 40943, 5, 1, "cuda")
+    c = eng.sample_uniform(1000, 1000, 40943, 5, 2, "cuda")
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert int(a.min()) >= 0 and int(a.max()) < 40943
+    hist = torch.bincount((a.view(-1) * 64) // 40943, minlength=64).double()
+    chi2 = float(((hist - hist.mean()) ** 2 / hist.mean()).sum())
+    assert chi2 < 120.0, chi2                                  # 63 dof: mean 63, p(chi2 > 120) ~ 1e-5
+
+
+@pytest.mark.skipif(not __import__("kge_b200.hostenv", fromlist=["x"]).available(), reason="reference not installed")
+def test_negative_sampling_job_with_device_sampling():
+    """B200TrainingJobNegativeSampling with user.b200_device_sampling: the DataLoader hands over triples only, the
+    negatives are drawn on the device; the epoch's avg_loss equals what the ENGINE computes for exactly those
+    negatives (recomputed here batch by batch), and is statistically the reference's (same sampler distribution)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import jobs_util as ju
+
+    Ej, Rj, Dj = 211, 5, 32
+    splits = ju.synthetic_splits(Ej, Rj, 600, 60, 60)
+    extra = {"negative_sampling.num_samples.s": 50, "negative_sampling.num_samples.o": 50, "train.loss_arg": 1.0}
+    torch.manual_seed(0)
+    ref = ju.make_job("complex", Ej, Rj, Dj, splits, device="cpu", train_type="negative_sampling", loss="bce",
+                      batch_size=64, extra=extra)
+    dev = ju.make_job("b200_complex", Ej, Rj, Dj, splits, device="cuda", train_type="negative_sampling", loss="bce",
+                      batch_size=64, extra=dict(extra, **{"user.b200_device_sampling": True}),
+                      job_class="B200TrainingJobNegativeSampling")
+    ju.copy_tables(ref, dev)
+    assert dev._device_sampling
+    a = ju.run_forward_epoch(ref)["avg_loss"]
+    b = ju.run_forward_epoch(dev)["avg_loss"]
+    assert dev._sample_calls == 2 * len(dev.loader)             # s and o slots, once per batch
+    assert b == pytest.approx(a, rel=0.05)                      # different random negatives, same distribution
+    b2 = ju.run_forward_epoch(dev)["avg_loss"]
+    assert b2 == b                                              # same torch seed, same epoch counter => same draws

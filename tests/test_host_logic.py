@@ -201,3 +201,14 @@ def test_synthetic_inputs_match_the_checkers_copy():
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
         assert synthetic.relation_dim(model, D) == orc.relation_dim(model, D)
     assert torch.equal(synthetic.make_triples(23, 4, 9, seed=3), orc.make_triples(23, 4, 9, seed=3))
+
+
+def test_philox_reference_known_answers():
+    """Known-answer vectors of Philox4x32-10 (Random123 kat_vectors) pin the Python mirror that checks the device
+    sampler (tests/test_gpu_rows.py::test_device_uniform_sampler)."""
+    from philox_ref import philox4x32_10
+
+    assert philox4x32_10([0, 0, 0, 0], (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert philox4x32_10([0xffffffff] * 4, (0xffffffff, 0xffffffff)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], (0xa4093822, 0x299f31d0)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
