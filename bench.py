@@ -545,6 +545,30 @@ def sharded_bench(engine, torch, dist, dev, rank, world, flush, peaks, iters=6):
     lg = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
     dist.all_reduce(lg, op=dist.ReduceOp.MAX)
     shape = list(full.shape)
+    # the same logits with the all-gather fused into the scoring kernel (epilogue stores to the peers' symmetric
+    # buffers): must be bit-identical
+    fused = None
+    try:
+        for _ in range(2):
+            ff = m.score_sp_po_fused(s[:nl], p[:nl], o[:nl])
+        same_logits = bool(torch.equal(ff, full))
+        torch.cuda.synchronize()
+        dist.barrier()
+        a2 = ev()
+        ff = m.score_sp_po_fused(s[:nl], p[:nl], o[:nl])
+        b2 = ev()
+        torch.cuda.synchronize()
+        lf = torch.tensor([a2.elapsed_time(b2)], dtype=torch.float64, device=dev)
+        dist.all_reduce(lf, op=dist.ReduceOp.MAX)
+        ok = torch.tensor([1 if same_logits else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        fused = {"op": "scoring kernel whose epilogue stores into every rank's symmetric [n, 2E] buffer over NVLink "
+                       "(peer-mapped pointers; torch symmetric memory for allocation + barriers)",
+                 "ms_per_call": float(lf), "bit_identical_to_nccl_path": bool(int(ok) == 1),
+                 "bytes_stored_to_peers_per_rank": nl * 2 * rows * 4 * (world - 1)}
+        del ff
+    except Exception as ex:
+        fused = {"error": repr(ex)}
     del full
 
     # exactness at a small shape: N-rank ranks / logits == the same quantities on one rank over the whole table
@@ -573,6 +597,7 @@ def sharded_bench(engine, torch, dist, dev, rank, world, flush, peaks, iters=6):
                        "counts": {"op": "ncclAllReduce(sum, i64)", "bytes_per_call": 2 * 2 * n5 * 8}},
         "logits_all_gather": {"op": "ncclAllGather(f32) + one re-layout copy", "n": nl, "shape": shape,
                               "bytes_gathered_per_rank": nl * 2 * rows * 4 * world, "ms_per_call": float(lg)},
+        "logits_fused_all_gather": fused,
         "ranks_bit_identical_to_single_gpu": bool(int(flag) == 1),
     }
 

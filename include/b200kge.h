@@ -195,6 +195,19 @@ int b200kge_rank_sp_po_csr(int model, float l_norm, int precision, const b200kge
                            int64_t* rank, int64_t* ties, void* workspace, size_t workspace_bytes,
                            b200kge_stream_t stream);
 
+/* b200kge_score_sp_po FUSED WITH THE ALL-GATHER of an entity-sharded table: `cand` is this rank's shard; the two
+ * halves are written at out[i*ldo + j] (sp_) and out[i*ldo + col_block + j] (_po), j < cand->rows, AND at the same
+ * offsets into each of the n_peers (<= 7) buffers peer_out[g] — peer-mapped device pointers to the other ranks'
+ * symmetric output buffers (NVLink / NVSwitch).  With out = base + lo (lo = first global row of the shard),
+ * ldo = 2 * E_total and col_block = E_total every rank's [n, 2E_total] logits matrix (kge_model.py:749-789 layout)
+ * is complete once all ranks have passed a barrier: the kernel's own epilogue stores replace ncclAllGather and the
+ * re-layout copy.  CP is not offered. */
+int b200kge_score_sp_po_bcast(int model, float l_norm, int precision, const b200kge_rows_t* s,
+                              const b200kge_rows_t* p, const b200kge_rows_t* o, const b200kge_rows_t* cand,
+                              int64_t n, float* out, float* const* peer_out, int n_peers, int64_t ldo,
+                              int64_t col_block, void* workspace, size_t workspace_bytes,
+                              b200kge_stream_t stream);
+
 /* Entity-sharded tables: this rank owns global rows [lo, lo + shard->rows) of the entity table.
  * out[i, :] = shard row (idx[i] - lo) if the rank owns global id idx[i], else zeros — the contribution of this rank
  * to the query-row exchange (sum over ranks == the gathered rows, exactly: every other rank adds zeros).  One

@@ -43,6 +43,9 @@ SIGNATURES = {
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200kge_score_sp_po": (C.c_int, [C.c_int, C.c_float, C.c_int, _RP, _RP, _RP, _RP, C.c_int64,
                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200kge_score_sp_po_bcast": (C.c_int, [C.c_int, C.c_float, C.c_int, _RP, _RP, _RP, _RP, C.c_int64, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t,
+                                            C.c_void_p]),
     "b200kge_score_1vsN_loss": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_int, _RP, _RP, _RP, C.c_int64,
                                           C.POINTER(Labels), C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -367,6 +367,27 @@ int b200kge_score_sp_po(int model, float l_norm, int precision, const b200kge_ro
   return run_block(B, l_norm, precision, EPI_STORE, P, ws, (cudaStream_t)stream, nullptr);
 }
 
+int b200kge_score_sp_po_bcast(int model, float l_norm, int precision, const b200kge_rows_t* s,
+                              const b200kge_rows_t* p, const b200kge_rows_t* o, const b200kge_rows_t* cand,
+                              int64_t n, float* out, float* const* peer_out, int n_peers, int64_t ldo,
+                              int64_t col_block, void* workspace, size_t workspace_bytes,
+                              b200kge_stream_t stream) {
+  int rc = check_1vsN_args(model, B200KGE_SP_, s, p, cand, n); if (rc) return rc;
+  if ((rc = check_1vsN_args(model, B200KGE__PO, o, p, cand, n))) return rc;
+  if ((rc = validate_norm(model, l_norm))) return rc;
+  if (n_peers < 0 || n_peers > 7 || (n_peers > 0 && !peer_out)) { set_error("0..7 peer buffers"); return B200KGE_ERR_INVALID; }
+  if (col_block < cand->rows) { set_error("col_block smaller than the number of candidates"); return B200KGE_ERR_INVALID; }
+  Rows Sr = to_rows(s), Pr = to_rows(p), Or = to_rows(o), C = to_rows(cand);
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  EpiParams P = empty_epi();
+  P.out = out; P.ldo = ldo; P.n_rows_out = n; P.col_block = col_block;
+  P.n_peers = n_peers;
+  for (int g = 0; g < n_peers; ++g) P.out_peer[g] = peer_out[g];
+  if (model == B200KGE_CP) { set_error("the broadcast store is not offered for CP"); return B200KGE_ERR_UNSUPPORTED; }
+  Block B{model, B200KGE_SP_, &Sr, &Or, &Pr, &C, n};
+  return run_block(B, l_norm, precision, EPI_STORE, P, ws, (cudaStream_t)stream, nullptr);
+}
+
 int b200kge_score_1vsN_loss(int model, int combine, float l_norm, int precision,
                             const b200kge_rows_t* q, const b200kge_rows_t* p,
                             const b200kge_rows_t* cand, int64_t n, const b200kge_labels_t* labels,
@@ -548,8 +569,8 @@ int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
   Folded f0 = folded_problem(model, B200KGE_SP_, E.dim, l_norm), f1 = folded_problem(model, B200KGE__PO, E.dim, l_norm);
   {
     // Pre-split tensor-core path (dot family except CP, whose directions read different table columns): the whole
-    // step is TWO launches — prologue (gather + both folds + operand split of queries and table + labels) and the
-    // scorer with the loss reduction and its finalisation fused (last-CTA ticket).
+    // step is THREE launches — prologue (gather + both folds + operand split of queries and table + labels), the
+    // scorer with the loss reduction in its epilogue, and the fixed-order finaliser.
     const char* env_v = getenv("B200KGE_TC_VERSION");
     const int tcv = env_v ? atoi(env_v) : 3;
     const int K = f0.K;
@@ -581,16 +602,10 @@ int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
       P.label_idx = lab;
       P.offset = (loss_kind == B200KGE_LOSS_BCE) ? offset : 0.f;
       P.part = part; P.nchunks = nch;
-      if (tcv == 4) {
-        if ((rc = launch_pairwise_tc4(epi, SQ, ST, P, st))) return rc;
-        return launch_loss_finalize(loss_kind, part, nch, nq, loss_out, nullptr, scale, 0, scratch, 1, st);
-      }
-      if ((nq + 127) / 128 > 120) {      // more query tiles than the scratch holds counters for: separate finaliser
-        if ((rc = launch_pairwise_tc3(epi, SQ, ST, P, st))) return rc;
-        return launch_loss_finalize(loss_kind, part, nch, nq, loss_out, nullptr, scale, 0, scratch, 1, st);
-      }
-      P.fin_out = loss_out; P.fin_ticket = ticket; P.fin_scale = scale; P.fin_rows = nq;
-      return launch_pairwise_tc3(epi, SQ, ST, P, st);
+      // (finalising inside the scorer — last CTA per query tile, then last tile — was measured: +8 us in the kernel
+      // against 5.8 us for the separate fixed-order finaliser, profiles/r2_summary.md; the finaliser stays separate)
+      if ((rc = tcv == 4 ? launch_pairwise_tc4(epi, SQ, ST, P, st) : launch_pairwise_tc3(epi, SQ, ST, P, st))) return rc;
+      return launch_loss_finalize(loss_kind, part, nch, nq, loss_out, nullptr, scale, 0, scratch, 1, st);
     }
   }
   if (f0.col_off == f1.col_off) {

@@ -113,13 +113,12 @@ struct EpiParams {
   int64_t csr_nnz;
   int csr_extra;
   const int64_t* csr_skip;
-  // fused finalisation (tensor-core kernels, losses): when fin_out != NULL the last CTA to finish (fin_ticket, zeroed
-  // by the caller's prologue) reduces the partials of all fin_rows rows in a fixed order and writes
-  // fin_scale * sum to fin_out[0] — the separate loss_finalize launch and its launch gap disappear
-  float* fin_out;
-  unsigned int* fin_ticket;
-  float fin_scale;
-  int64_t fin_rows;
+  // EPI_STORE fused with the all-gather of an entity-sharded table: every score is also stored, at the
+  // same offset, into the symmetric output buffers of the n_peers other ranks (peer-mapped pointers over
+  // NVLink / NVSwitch) — the shard's logits land in place in everybody's [n, 2E] matrix, no NCCL all-gather, no
+  // re-layout copy
+  float* out_peer[7];
+  int n_peers;
 };
 
 // lower bound of `key` in the sorted segment col[lo, hi)
@@ -195,7 +194,9 @@ __device__ __forceinline__ void epi_elem(const EpiParams& P, RowState<KIND>& st,
   if constexpr (KIND == EPI_STORE) {
     int64_t r = row, cb = 0;
     if (P.n_rows_out > 0 && row >= P.n_rows_out) { r = row - P.n_rows_out; cb = P.col_block; }
-    P.out[r * P.ldo + cb + col] = x;
+    const int64_t at = r * P.ldo + cb + col;
+    P.out[at] = x;
+    for (int g = 0; g < P.n_peers; ++g) P.out_peer[g][at] = x;
   } else if constexpr (KIND == EPI_BCE) {
     float z = x + P.offset;
     st.a += softplus_f(z);
@@ -319,32 +320,6 @@ __device__ __forceinline__ float finalize_row(const float* __restrict__ part, in
   }
 }
 
-
-// same as finalize_row, reading the partials through L2 (they were written by other SMs of the same kernel)
-template <int LOSS>
-__device__ __forceinline__ float finalize_row_cg(const float* __restrict__ part, int nchunks, int64_t r) {
-  if constexpr (LOSS == B200KGE_LOSS_BCE) {
-    float a = 0.f, b = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      const float2 v = __ldcg(reinterpret_cast<const float2*>(part + (r * nchunks + c) * 2));
-      a += v.x; b += v.y;
-    }
-    return a - b;
-  } else {
-    RowState<EPI_KL> st;
-    st.init();
-    for (int c = 0; c < nchunks; ++c) {
-      const float* p = part + (r * nchunks + c) * 5;
-      RowState<EPI_KL> o;
-      o.m = __ldcg(p); o.s = __ldcg(p + 1); o.y_sum = __ldcg(p + 2); o.yx = __ldcg(p + 3); o.ylogy = __ldcg(p + 4);
-      st.combine(o);
-    }
-    const float lse = st.m + logf(st.s);
-    const float yc = fmaxf(st.y_sum, 1e-12f);
-    const float w = st.y_sum / yc;
-    return (st.y_sum > 0.f) ? (st.ylogy / yc - w * logf(yc) - st.yx / yc + lse * w) : 0.f;
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Internal kernels' host launchers (one per .cu file).

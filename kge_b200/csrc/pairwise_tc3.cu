@@ -222,110 +222,11 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
     }
   }
 
-  if constexpr (EPI == EPI_BCE || EPI == EPI_KL) {
-    if (prm.epi.fin_out) __threadfence();        // this CTA's partial row states are visible device-wide
-  }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
-  }
-  if constexpr (EPI == EPI_BCE || EPI == EPI_KL) {
-    // Fused finalisation, two levels, deterministic whatever the completion order:
-    //   (1) the CTA that completes the LAST work item of a query tile (per-tile counter) reduces that tile's 128 rows
-    //       over all their chunk partials: thread = (row, third of the chunks), loads issued in batches of 8 before
-    //       any use (an in-order warp otherwise pays one L2 round trip per chunk), thirds and rows combined in a fixed
-    //       order -> tile_sum[qt];
-    //   (2) the CTA that completes the last tile adds the tile sums in index order.
-    const EpiParams& P = prm.epi;
-    if (P.fin_out) {
-      constexpr int F = RowState<EPI>::F;
-      // the operand ring is idle now (every TMA load was consumed before the barrier above): reuse it
-      int& s_flag = *reinterpret_cast<int*>(smem);
-      float (*s_part)[TM][F] = reinterpret_cast<float (*)[TM][F]>(smem + 64);
-      float* s_row = reinterpret_cast<float*>(smem + 64 + 3 * TM * F * 4);
-      float* tile_sum = reinterpret_cast<float*>(P.fin_ticket) - 128;      // scratch: 128 floats, then the counters
-      unsigned int* tile_cnt = P.fin_ticket + 1;                           // [q_tiles]; fin_ticket[0] counts tiles
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int qt = w / prm.echunks;
-        if (threadIdx.x == 0) s_flag = (atomicAdd(tile_cnt + qt, 1u) == (unsigned)prm.echunks - 1) ? 1 : 0;
-        __syncthreads();
-        const bool mine = s_flag != 0;
-        __syncthreads();
-        if (!mine) continue;
-        __threadfence();
-        const int lr = threadIdx.x % TM, third = threadIdx.x / TM;          // 384 threads = 128 rows x 3
-        const int64_t r = (int64_t)qt * TM + lr;
-        RowState<EPI> st;
-        st.init();
-        if (r < P.fin_rows) {
-          for (int c0 = third; c0 < P.nchunks; c0 += 24) {
-            float v[8][F];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int c = c0 + 3 * j;
-#pragma unroll
-              for (int f = 0; f < F; ++f) v[j][f] = (c < P.nchunks) ? __ldcg(P.part + (r * P.nchunks + c) * F + f) : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (c0 + 3 * j < P.nchunks) {
-                RowState<EPI> o;
-                if constexpr (EPI == EPI_BCE) { o.a = v[j][0]; o.b = v[j][1]; }
-                else { o.m = v[j][0]; o.s = v[j][1]; o.y_sum = v[j][2]; o.yx = v[j][3]; o.ylogy = v[j][4]; }
-                st.combine(o);
-              }
-            }
-          }
-        }
-        {
-          const float* sp = reinterpret_cast<const float*>(&st);
-#pragma unroll
-          for (int f = 0; f < F; ++f) s_part[third][lr][f] = sp[f];
-        }
-        __syncthreads();
-        if (threadIdx.x < TM) {
-          RowState<EPI> t0, o;
-          float* d = reinterpret_cast<float*>(&t0);
-#pragma unroll
-          for (int f = 0; f < F; ++f) d[f] = s_part[0][lr][f];
-#pragma unroll
-          for (int q = 1; q < 3; ++q) {
-            float* e = reinterpret_cast<float*>(&o);
-#pragma unroll
-            for (int f = 0; f < F; ++f) e[f] = s_part[q][lr][f];
-            t0.combine(o);
-          }
-          float rl = 0.f;
-          if (r < P.fin_rows) {
-            if constexpr (EPI == EPI_BCE) rl = t0.a - t0.b;
-            else {
-              const float lse = t0.m + logf(t0.s);
-              const float yc = fmaxf(t0.y_sum, 1e-12f), wgt = t0.y_sum / yc;
-              rl = (t0.y_sum > 0.f) ? (t0.ylogy / yc - wgt * logf(yc) - t0.yx / yc + lse * wgt) : 0.f;
-            }
-          }
-          s_row[lr] = rl;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          float tot = 0.f;
-          for (int i = 0; i < TM; ++i) tot += s_row[i];
-          tile_sum[qt] = tot;
-          tile_cnt[qt] = 0u;
-          __threadfence();
-          if (atomicAdd(P.fin_ticket, 1u) == (unsigned)prm.q_tiles - 1) {
-            __threadfence();
-            float all = 0.f;
-            for (int t = 0; t < prm.q_tiles; ++t) all += __ldcg(tile_sum + t);
-            P.fin_out[0] = P.fin_scale * all;
-            *P.fin_ticket = 0u;
-          }
-        }
-        __syncthreads();
-      }
-    }
   }
 }
 

@@ -99,8 +99,8 @@ presplit_kernel(const SplitSet A, const SplitSet B, const int blocks_a) {
 //                      (o_b, p_b) for _po (b >= n) into shared memory, row scale, hi/lo planes, inverse scale, and
 //                      the row's label (o_b | s_b); block 0 also zeroes the finalisation ticket
 //   blocks [2n, ...) : table rows, one warp per row (presplit_row)
-// replaces prep_1vsall_kernel + presplit_kernel (one launch and one launch gap less per step; the folded fp32 query
-// matrix never reaches HBM).
+// replaces prep_1vsall_kernel + presplit_kernel (one launch and one launch gap less per step: 15.0 us against
+// 5.3 + 11.7 us measured; the folded fp32 query matrix never reaches HBM).
 constexpr int PQ_THREADS = PS_WARPS * 32;
 
 template <int MODEL>
@@ -126,7 +126,7 @@ prep_split_1vsall_kernel(Rows ent, Rows rel, const int64_t* __restrict__ tri, in
     labels2n[b] = sp ? oi : si;
     bad_any = 0;
   }
-  if (b == 0 && ticket && threadIdx.x < 128) ticket[threadIdx.x] = 0u;      // finalisation counters (512 bytes)
+  if (b == 0 && ticket && threadIdx.x == 0) *ticket = 0u;                   // the finaliser's last-block counter
   float* q = sh;
   if constexpr (MODEL == B200KGE_RESCAL) {
     float* sh_a = sh + Kp;

@@ -301,6 +301,12 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& P, RowState<EPI>&
             for (int rr = 0; rr < 32; ++rr)
               if (rr < nrows) p[rr * P.ldo] = t[rr];
           }
+          for (int g = 0; g < P.n_peers; ++g) {        // same offsets in the peers' symmetric buffers
+            float* __restrict__ pp = P.out_peer[g] + (p - P.out);
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              if (rr < nrows) pp[rr * P.ldo] = t[rr];
+          }
         }
       } else if (col < m) {
         for (int rr = 0; rr < 32; ++rr) {
@@ -308,7 +314,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& P, RowState<EPI>&
           if (r < nq) {
             int64_t cb = 0;
             if (r >= P.n_rows_out) { r -= P.n_rows_out; cb = P.col_block; }
-            P.out[r * P.ldo + cb + col] = my_stg[rr * STG_LD + lane];
+            const int64_t at = r * P.ldo + cb + col;
+            const float xv = my_stg[rr * STG_LD + lane];
+            P.out[at] = xv;
+            for (int g = 0; g < P.n_peers; ++g) P.out_peer[g][at] = xv;
           }
         }
       }

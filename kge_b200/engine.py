@@ -158,6 +158,23 @@ def score_sp_po(model: str, ent, rel, s, p, o, entity_subset=None, l_norm: float
     return out
 
 
+def score_sp_po_bcast(model: str, s_emb, rel, p, o_emb, cand_tab, out_ptr: int, peer_ptrs, ldo: int, col_block: int,
+                      l_norm: float = 1.0, precision: str = "auto"):
+    """score_sp_po whose epilogue stores go to this rank's buffer (raw device address out_ptr, already offset to the
+    shard's first column) AND to the peer-mapped buffers `peer_ptrs` of the other ranks at the same offsets — the
+    all-gather of per-shard logits fused into the scoring kernel (include/b200kge.h: b200kge_score_sp_po_bcast)."""
+    _require_cuda(s_emb, rel, o_emb, cand_tab)
+    lib, k = _lib.load(), _Keep()
+    rs, rp, ro, rc = k.rows(s_emb), k.rows(rel, p), k.rows(o_emb), k.rows(cand_tab)
+    n, m = int(rs.rows), int(rc.rows)
+    dev = s_emb.device
+    arr = (C.c_void_p * max(1, len(peer_ptrs)))(*[C.c_void_p(int(x)) for x in peer_ptrs])
+    ws = _workspace(MODELS[model], n, m, rs.dim, False, dev)
+    _lib.check(lib.b200kge_score_sp_po_bcast(MODELS[model], l_norm, PREC[precision], C.byref(rs), C.byref(rp),
+                                             C.byref(ro), C.byref(rc), n, C.c_void_p(int(out_ptr)), arr,
+                                             len(peer_ptrs), ldo, col_block, ws.data_ptr(), ws.numel(), _stream(dev)))
+
+
 def rank_sp_po(model: str, s_tab, rel, o_tab, cand_tab, true_scores, s=None, p=None, o=None, cand=None,
                filter_labels=None, rtol: float = 1e-4, atol: float = 1e-5, l_norm: float = 1.0,
                precision: str = "auto", rank=None, ties=None):

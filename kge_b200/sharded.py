@@ -135,6 +135,40 @@ class ShardedKgeModel:
         full = buf.view(self.world, n, 2, self.per).permute(1, 2, 0, 3).reshape(n, 2, self.world * self.per)
         return full[:, :, : self.E].reshape(n, 2 * self.E)
 
+    # -- full logits, compute + collective in one kernel ---------------------------------------------------
+    def _symm_logits(self, n):
+        """A symmetric [n, 2E] buffer (torch.distributed._symmetric_memory: same allocation on every rank, mapped
+        into every peer's address space over NVLink) and the peers' device pointers to it; cached per n."""
+        cache = self.__dict__.setdefault("_symm_cache", {})
+        if n not in cache:
+            import torch.distributed._symmetric_memory as symm
+
+            buf = symm.empty((n, 2 * self.E), dtype=torch.float32, device=self.ent.device)
+            hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            cache[n] = (buf, hdl, [int(x) for x in hdl.buffer_ptrs])
+        return cache[n]
+
+    def score_sp_po_fused(self, s, p, o) -> torch.Tensor:
+        """[n, 2E] logits like score_sp_po, with the all-gather FUSED into the scoring kernel: its epilogue stores
+        every score of the shard straight into the [n, 2E] matrices of all ranks (peer-mapped symmetric memory over
+        NVLink / NVSwitch) at their final positions — no NCCL all-gather, no re-layout copy, the transfer overlaps
+        the scoring tile by tile.  The returned tensor is the cached symmetric buffer (overwritten by the next call
+        with the same n)."""
+        s_emb, pi, o_emb, _ = self._queries(s, p, o)
+        n = s.numel()
+        if self.world == 1:
+            return self.score_sp_po(s, p, o)
+        buf, hdl, ptrs = self._symm_logits(n)
+        hdl.barrier(channel=0)                  # every rank is done with the previous contents
+        off = self.lo * 4
+        if self.hi > self.lo:
+            from . import engine
+            engine.score_sp_po_bcast(self.model, s_emb, self.rel, pi, o_emb, self.ent, ptrs[self.rank] + off,
+                                     [ptrs[g] + off for g in range(self.world) if g != self.rank], 2 * self.E,
+                                     self.E, self.l_norm, self.precision)
+        hdl.barrier(channel=1)                  # all shards have landed everywhere
+        return buf
+
     # -- ranking -------------------------------------------------------------------------------------
     def true_scores(self, s, p, o):
         """((t_sp [n], t_po [n]), rows): scores of the true triples computed WITH THE 1-vs-N CODE PATH against the
