@@ -119,6 +119,7 @@ struct EpiParams {
   // re-layout copy
   float* out_peer[7];
   int n_peers;
+  int store_vec4;      // set by launch_pairwise_simt: every destination row start is 16-byte aligned
 };
 
 // lower bound of `key` in the sorted segment col[lo, hi)

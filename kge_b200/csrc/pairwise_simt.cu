@@ -167,6 +167,39 @@ pairwise_simt_kernel(const float* __restrict__ Q, int64_t ldq, int64_t nq, Rows 
     }
 
     // ---- tile epilogue: thread owns rows ty*4 + 64*ii + r, cols tx*4 + 64*jj + c --------------
+    if constexpr (EPI == EPI_STORE) {
+      if (P.store_vec4) {
+        // 16-byte stores: the 4 consecutive columns a thread owns go out as one float4, so a half-warp writes 256
+        // contiguous bytes of one output row (the scalar form writes 4-byte words 16 bytes apart — tolerable into
+        // local HBM behind L2, ruinous for the peer stores of the fused all-gather over NVLink)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t row = row0 + ty * 4 + 64 * (i >> 2) + (i & 3);
+          if (row >= nq) continue;
+          int64_t r = row, cb = 0;
+          if (P.n_rows_out > 0 && row >= P.n_rows_out) { r = row - P.n_rows_out; cb = P.col_block; }
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int64_t col = col0 + tx * 4 + 64 * jj;
+            if (col >= m) continue;
+            const float4 v = make_float4(pair_finish<PAIR>(acc[i][jj * 4 + 0], p_norm), pair_finish<PAIR>(acc[i][jj * 4 + 1], p_norm),
+                                         pair_finish<PAIR>(acc[i][jj * 4 + 2], p_norm), pair_finish<PAIR>(acc[i][jj * 4 + 3], p_norm));
+            const int64_t at = r * P.ldo + cb + col;
+            if (col + 3 < m) {
+              *reinterpret_cast<float4*>(P.out + at) = v;
+              for (int g = 0; g < P.n_peers; ++g) *reinterpret_cast<float4*>(P.out_peer[g] + at) = v;
+            } else {
+              const float vv[4] = {v.x, v.y, v.z, v.w};
+              for (int c = 0; c < 4 && col + c < m; ++c) {
+                P.out[at + c] = vv[c];
+                for (int g = 0; g < P.n_peers; ++g) P.out_peer[g][at + c] = vv[c];
+              }
+            }
+          }
+        }
+        continue;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int64_t row = row0 + ty * 4 + 64 * (i >> 2) + (i & 3);
@@ -236,13 +269,20 @@ int launch_pairwise_simt(int epi_kind, int pair_op, float l_norm, const float* Q
   bool vec = (ldq % 4 == 0) && (cand.ld % 4 == 0) && (col_off % 4 == 0) &&
              ((reinterpret_cast<uintptr_t>(Q) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(cand.base) & 15) == 0) && (!cm || ((K / 2) % 4 == 0));
+  EpiParams Pv = P;
+  if (epi_kind == EPI_STORE) {
+    // float4 stores need 16-byte aligned row starts in every destination
+    bool ok = (P.ldo % 4 == 0) && (P.col_block % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0);
+    for (int g = 0; g < P.n_peers; ++g) ok = ok && ((reinterpret_cast<uintptr_t>(P.out_peer[g]) & 15) == 0);
+    Pv.store_vec4 = ok ? 1 : 0;
+  }
   switch (pair_op) {
-    case PAIR_DOT:     return launch_p<PAIR_DOT>(epi_kind, vec, grid, st, Q, ldq, nq, cand, col_off, K, l_norm, P);
-    case PAIR_L1:      return launch_p<PAIR_L1>(epi_kind, vec, grid, st, Q, ldq, nq, cand, col_off, K, l_norm, P);
-    case PAIR_L2:      return launch_p<PAIR_L2>(epi_kind, vec, grid, st, Q, ldq, nq, cand, col_off, K, l_norm, P);
-    case PAIR_LP:      return launch_p<PAIR_LP>(epi_kind, vec, grid, st, Q, ldq, nq, cand, col_off, K, l_norm, P);
-    case PAIR_CMOD_L1: return launch_p<PAIR_CMOD_L1>(epi_kind, vec, grid, st, Q, ldq, nq, cand, col_off, K, l_norm, P);
-    case PAIR_CMOD_LP: return launch_p<PAIR_CMOD_LP>(epi_kind, vec, grid, st, Q, ldq, nq, cand, col_off, K, l_norm, P);
+    case PAIR_DOT:     return launch_p<PAIR_DOT>(epi_kind, vec, grid, st, Q, ldq, nq, cand, col_off, K, l_norm, Pv);
+    case PAIR_L1:      return launch_p<PAIR_L1>(epi_kind, vec, grid, st, Q, ldq, nq, cand, col_off, K, l_norm, Pv);
+    case PAIR_L2:      return launch_p<PAIR_L2>(epi_kind, vec, grid, st, Q, ldq, nq, cand, col_off, K, l_norm, Pv);
+    case PAIR_LP:      return launch_p<PAIR_LP>(epi_kind, vec, grid, st, Q, ldq, nq, cand, col_off, K, l_norm, Pv);
+    case PAIR_CMOD_L1: return launch_p<PAIR_CMOD_L1>(epi_kind, vec, grid, st, Q, ldq, nq, cand, col_off, K, l_norm, Pv);
+    case PAIR_CMOD_LP: return launch_p<PAIR_CMOD_LP>(epi_kind, vec, grid, st, Q, ldq, nq, cand, col_off, K, l_norm, Pv);
   }
   set_error("bad pair op %d", pair_op);
   return B200KGE_ERR_INVALID;
