@@ -449,13 +449,15 @@ def transe_shard_bench(engine, torch, dev, flush, peaks, have_ref, fma_peak):
     def step5():
         return engine.rank_sp_po("transe", shard, rel, shard, shard, true2n, s, p, o)
     k_ms, call_ms = _timed_kernel(engine, torch, step5, flush, iters=5, warm=2)
-    ops = 2.0 * 3.0 * n5 * rows * D5                 # 3 fp32 ops per (i, j, k), both directions
+    # SURVEY 8d counts 3 fp32 ops per (i, j, k) (sub, abs, add); the kernel issues 2 instructions for them (|a - b| is a
+    # FADD with an operand modifier, then the accumulate), so the issue-slot roofline uses 2
+    ops = 2.0 * 2.0 * n5 * rows * D5
     byts = rows * D5 * 4.0
     entry = {"workload": f"TransE d={D5} L1, one Wikidata5M-shaped shard of {rows} entity rows, n={n5}: fused score_sp_po + "
                          "rank/tie counting (both directions stacked in one launch)",
              "ms_per_step": call_ms, "kernel_ms": k_ms, "value": 2.0 * n5 * rows / (call_ms * 1e-3), "unit": UNIT,
              "roofline": {"bound": "fp32 CUDA-core pipe (SURVEY 8d: ALU-bound for n >= 12)",
-                          "achieved": ops / (k_ms * 1e-3) / 1e12, "peak": fma_peak / 1e12, "unit": "Tops/s (fp32 issue slots)",
+                          "achieved": ops / (k_ms * 1e-3) / 1e12, "peak": fma_peak / 1e12, "unit": "T instr/s (fp32 issue slots)",
                           "frac": ops / (k_ms * 1e-3) / fma_peak,
                           "hbm_frac": byts / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                           "note": "north_star asks for the HBM fraction (hbm_frac: 1.23 GB table stream per call); the "
@@ -731,9 +733,10 @@ def run_ours(args):
     pair = os.environ.get("B200KGE_TC_VERSION", "3") == "4"
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "traffic": None,
-        "traffic_note": "not measured in this run; ncu --set full of the same command: profiles/r2_summary.md "
-                        "(dram__bytes_read 34.1 MB per launch = algorithmic: table 29.8 MB + folded queries 4.2 MB as planes)",
+        "traffic": 34.1e6,
+        "traffic_from": "profiles/r2_raw_tc3.csv (ncu --set full of this command: dram__bytes_read.sum 34.10 MB + "
+                        "dram__bytes_write.sum 0 per launch) — NOT measured in this run; algorithmic bytes = table "
+                        "planes 29.8 MB + query planes 4.2 MB",
         "kernel": "pairwise_tc4_kernel<BCE> (CTA pair)" if pair else "pairwise_tc3_kernel<BCE>",
         "kernel_ms": k_ms,
         "peak_name": f"dense bf16 burst, {peaks['source']}",
