@@ -48,8 +48,9 @@ constexpr int TMEM_COLS = 512;
 struct Tc4Params {
   int64_t nq, m;
   int nk;                          // K chunks of 64 halfs
-  int q_tiles, e_tiles, echunks;   // q tiles of 256 rows, e tiles of tn rows
-  int tn;                          // entities per cluster tile (multiple of 32, <= 256); each CTA stages tn/2
+  int q_tiles, echunks;            // q tiles of 256 rows; each q tile's columns are cut into `echunks` ranges
+  int cols_per;                    // columns per range (multiple of 32): a range = full 256-column tiles + ONE narrower
+                                   // last tile (width multiple of 32) — no quantisation to whole 256-column tiles
   const float* q_scale;            // [nq]
   const float* t_scale;            // [m + 32], zero beyond m
   EpiParams epi;
@@ -99,12 +100,18 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto work_range = [&](int w, int& qt, int& et0, int& et1, int& ec) {
+  // work item w -> query tile qt, column range [c_lo, c_hi) (ec-th range); tile t of the range starts at
+  // c_lo + 256 t and is tile_n(c_lo, c_hi, t) columns wide
+  auto work_range = [&](int w, int& qt, int64_t& c_lo, int64_t& c_hi, int& ec, int& ntiles) {
     qt = w / prm.echunks;
     ec = w - qt * prm.echunks;
-    const int base = prm.e_tiles / prm.echunks, rem = prm.e_tiles % prm.echunks;
-    et0 = ec * base + (ec < rem ? ec : rem);
-    et1 = et0 + base + (ec < rem ? 1 : 0);
+    c_lo = (int64_t)ec * prm.cols_per;
+    c_hi = c_lo + prm.cols_per < prm.m ? c_lo + prm.cols_per : prm.m;
+    ntiles = c_hi > c_lo ? (int)((c_hi - c_lo + TN - 1) / TN) : 0;
+  };
+  auto tile_n = [](int64_t c_lo, int64_t c_hi, int t) {      // UMMA N of tile t: 256, or the remainder rounded up to 32
+    const int64_t left = c_hi - (c_lo + (int64_t)t * TN);
+    return (int)(left >= TN ? TN : ((left + 31) / 32) * 32);
   };
   // slot pair and phase of K chunk c: slots 2c%6, 2c%6+1; both on their (c/3)-th use
   auto slot_of = [](uint32_t c) { return (int)((2 * c) % NSLOT); };
@@ -114,13 +121,15 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
     // ================================ TMA producer (both CTAs) ==============================
     if (lane == 0) {
       uint32_t c = 0;
-      const uint32_t slot_tx = (uint32_t)(A_BYTES + (prm.tn >> 1) * TKH * 2);   // bytes one CTA lands per slot
       for (int w = cluster_id; w < total_work; w += nclusters) {
-        int qt, et0, et1, ec;
-        work_range(w, qt, et0, et1, ec);
+        int qt, ec, ntiles;
+        int64_t c_lo, c_hi;
+        work_range(w, qt, c_lo, c_hi, ec, ntiles);
         const int q_row = qt * 256 + (int)rank * TM;
-        for (int et = et0; et < et1; ++et) {
-          const int e_row = et * prm.tn + (int)rank * (prm.tn >> 1);
+        for (int t = 0; t < ntiles; ++t) {
+          // this CTA stages rows [rank * N/2, (rank + 1) * N/2) of the tile; the box always has TM rows (rows beyond
+          // N/2 land in the slot unused, rows beyond the table are zero-filled)
+          const int e_row = (int)(c_lo + (int64_t)t * TN) + (int)rank * (tile_n(c_lo, c_hi, t) >> 1);
           for (int kc = 0; kc < nk; ++kc, ++c) {
             const int s0 = slot_of(c);
             const uint32_t ph = phase_of(c);
@@ -129,17 +138,11 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
               const int s = s0 + h;
               ptx::mbar_wait_cluster_bounded(&empty[s], ph ^ 1);
               uint8_t* sp = smem + s * SLOT_BYTES;
-              if (DIRECT) {
-                // completion of BOTH CTAs' boxes is counted on the leader's barrier
-                const uint32_t bar = ptx::mapa(ptx::smem_u32(&full[s]), 0);
-                if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * slot_tx);
-                ptx::tma_load_2d_cluster_bar(sp, h ? &tmQl : &tmQh, bar, kc * TKH, q_row);
-                ptx::tma_load_2d_cluster_bar(sp + A_BYTES, h ? &tmTl : &tmTh, bar, kc * TKH, e_row);
-              } else {
-                ptx::mbar_arrive_expect_tx(&full[s], slot_tx);
-                ptx::tma_load_2d(sp, h ? &tmQl : &tmQh, &full[s], kc * TKH, q_row);
-                ptx::tma_load_2d(sp + A_BYTES, h ? &tmTl : &tmTh, &full[s], kc * TKH, e_row);
-              }
+              // completion of BOTH CTAs' boxes is counted on the leader's barrier
+              const uint32_t bar = ptx::mapa(ptx::smem_u32(&full[s]), 0);
+              if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * SLOT_BYTES);
+              ptx::tma_load_2d_cluster_bar(sp, h ? &tmQl : &tmQh, bar, kc * TKH, q_row);
+              ptx::tma_load_2d_cluster_bar(sp + A_BYTES, h ? &tmTl : &tmTh, bar, kc * TKH, e_row);
             }
           }
         }
@@ -148,13 +151,13 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA only) ===========================
     if (rank == 0 && lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_f16(256, prm.tn);
-      uint64_t* ready = DIRECT ? full : landed;
       uint32_t c = 0, it = 0;
       for (int w = cluster_id; w < total_work; w += nclusters) {
-        int qt, et0, et1, ec;
-        work_range(w, qt, et0, et1, ec);
-        for (int et = et0; et < et1; ++et, ++it) {
+        int qt, ec, ntiles;
+        int64_t c_lo, c_hi;
+        work_range(w, qt, c_lo, c_hi, ec, ntiles);
+        for (int t = 0; t < ntiles; ++t, ++it) {
+          const uint32_t idesc = ptx::umma_idesc_f16(256, tile_n(c_lo, c_hi, t));
           const int b = it & 1;
           ptx::mbar_wait_cluster_bounded(&tempty[b], ((it >> 1) & 1) ^ 1);
           ptx::tc_fence_after();
@@ -164,13 +167,13 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
             const uint32_t ph = phase_of(c);
             const uint32_t a_hi = ptx::smem_u32(smem + sh * SLOT_BYTES), b_hi = a_hi + A_BYTES;
             const uint32_t a_lo = ptx::smem_u32(smem + sl * SLOT_BYTES), b_lo = a_lo + A_BYTES;
-            ptx::mbar_wait_cluster_bounded(&ready[sh], ph);
+            ptx::mbar_wait_cluster_bounded(&full[sh], ph);
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TKH / 16; ++k)
               ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
                                   (kc > 0 || k > 0) ? 1u : 0u);
-            ptx::mbar_wait_cluster_bounded(&ready[sl], ph);
+            ptx::mbar_wait_cluster_bounded(&full[sl], ph);
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TKH / 16; ++k) {
@@ -184,26 +187,6 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
         }
       }
     }
-  } else if (warp == 2) {
-    // ================================ forwarder (both CTAs, FORWARD signalling) ==============
-    if (!DIRECT && lane == 0) {
-      uint32_t c = 0;
-      for (int w = cluster_id; w < total_work; w += nclusters) {
-        int qt, et0, et1, ec;
-        work_range(w, qt, et0, et1, ec);
-        for (int et = et0; et < et1; ++et) {
-          for (int kc = 0; kc < nk; ++kc, ++c) {
-            const int s0 = slot_of(c);
-            const uint32_t ph = phase_of(c);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              ptx::mbar_wait_bounded(&full[s0 + h], ph);
-              ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&landed[s0 + h]), 0));
-            }
-          }
-        }
-      }
-    }
   } else if (warp >= 4) {
     // ================================ epilogue (both CTAs) ===================================
     const int quad = warp & 3;                // TMEM lanes [32*quad, +32)
@@ -212,8 +195,9 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
     const EpiParams& P = prm.epi;
     uint32_t it = 0;
     for (int w = cluster_id; w < total_work; w += nclusters) {
-      int qt, et0, et1, ec;
-      work_range(w, qt, et0, et1, ec);
+      int qt, ec, ntiles;
+      int64_t c_lo, c_hi;
+      work_range(w, qt, c_lo, c_hi, ec, ntiles);
       const int64_t row0 = (int64_t)qt * 256 + (int64_t)rank * TM + quad * 32;
       const int64_t row = row0 + lane;
       const bool row_ok = row < prm.nq;
@@ -222,15 +206,15 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
       const float aux = row_ok ? epi_row_aux<EPI>(P, row) : 0.f;
       const float qs = row_ok ? __ldg(prm.q_scale + row) : 0.f;
       const int64_t csr_end = (P.csr_off && row_ok) ? __ldg(P.csr_off + row + 1) : 0;
-      for (int et = et0; et < et1; ++et, ++it) {
+      for (int t = 0; t < ntiles; ++t, ++it) {
         const int b = it & 1;
         ptx::mbar_wait_cluster_bounded(&tfull[b], (it >> 1) & 1);
         ptx::tc_fence_after();
-        const int64_t tile_end = (int64_t)(et + 1) * prm.tn;
+        const int64_t tile_lo = c_lo + (int64_t)t * TN;
+        const int64_t tile_end = tile_lo + TN < c_hi ? tile_lo + TN : c_hi;     // valid columns only (<= m)
         tc::epilogue_tile<EPI, 4, true>(P, st, aux,
                                         tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TN + half * 128),
-                                        row0, (int64_t)et * prm.tn + half * 128, prm.nq,
-                                        tile_end < prm.m ? tile_end : prm.m, my_stg, lane, qs, prm.t_scale,
+                                        row0, tile_lo + half * 128, prm.nq, tile_end, my_stg, lane, qs, prm.t_scale,
                                         csr_end);
         ptx::tc_fence_before();
         __syncwarp();
@@ -250,30 +234,19 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
   }
 }
 
-// same policy as plan3 (pairwise_tc3.cu) with CTA pairs as the scheduling unit: tile width (multiple of 32 in
-// [128, 256]: each CTA stages tn/2 rows, which must stay a multiple of the 8-row swizzle atom) minimising the per-cluster makespan in columns; entity tiles split into `echunks` ranges so that
-// q_tiles * echunks ~ #clusters
-void plan4(int64_t nq, int64_t m, int& q_tiles, int& e_tiles, int& echunks, int& tn) {
+// CTA pairs as the scheduling unit: every query tile's columns are cut into `echunks` equal ranges (multiples of 32
+// columns) so that q_tiles * echunks ~ #clusters; a range runs as full 256-column tiles plus one narrower last tile.
+// (Whole-tile ranges lose 10 % at the FB15k-237 shape: 7 x 256 columns per cluster for 14 541 / 9 = 1616 needed.)
+void plan4(int64_t nq, int64_t m, int& q_tiles, int& echunks, int& cols_per) {
   q_tiles = (int)((nq + 255) / 256);
   if (q_tiles < 1) q_tiles = 1;
   const int units = tc::num_sms() / 2;
-  int64_t best_cost = -1;
-  tn = TN;
-  for (int cand = TN; cand >= 128; cand -= 32) {
-    const int64_t et = (m + cand - 1) / cand;
-    int per = units / q_tiles; if (per < 1) per = 1; if (per > et) per = (int)et;
-    const int64_t tiles_per_cl = (et + per - 1) / per;
-    const int64_t waves = ((int64_t)q_tiles * per + units - 1) / units;
-    // per-tile overhead of the pair (cross-CTA accumulator hand-over): measured 73.2 us with 9 tiles of 192 columns
-    // against 68.4 us with 7 tiles of 256 at the FB15k-237 shape => worth ~64 columns per tile
-    const int64_t cost = waves * tiles_per_cl * cand + tiles_per_cl * 64;
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; tn = cand; }
-  }
-  e_tiles = (int)((m + tn - 1) / tn);
   int per = units / q_tiles;
   if (per < 1) per = 1;
-  if (per > e_tiles) per = e_tiles;
-  echunks = per;
+  const int64_t max_ranges = (m + 127) / 128;          // at least 128 columns per range
+  if (per > max_ranges) per = (int)max_ranges;
+  cols_per = (int)(((m + per - 1) / per + 31) / 32 * 32);
+  echunks = (int)((m + cols_per - 1) / cols_per);
 }
 
 template <int EPI, bool DIRECT>
@@ -300,8 +273,8 @@ int launch_e4(bool, const CUtensorMap& qh, const CUtensorMap& ql, const CUtensor
 }  // namespace
 
 int tc4_nchunks(int64_t nq, int64_t m) {
-  int qt, et, ec, tn;
-  plan4(nq, m, qt, et, ec, tn);
+  int qt, ec, cp;
+  plan4(nq, m, qt, ec, cp);
   return 2 * ec;
 }
 
@@ -311,14 +284,14 @@ int launch_pairwise_tc4(int epi_kind, const SplitSet& Q, const SplitSet& T, cons
   if (Q.Kp != T.Kp || Q.Kp % TKH != 0) { set_error("operand planes disagree on the padded reduction length"); return B200KGE_ERR_INVALID; }
   Tc4Params prm;
   prm.nq = nq; prm.m = m; prm.nk = Q.Kp / TKH;
-  plan4(nq, m, prm.q_tiles, prm.e_tiles, prm.echunks, prm.tn);
+  plan4(nq, m, prm.q_tiles, prm.echunks, prm.cols_per);
   prm.q_scale = Q.inv_scale; prm.t_scale = T.inv_scale;
   CUtensorMap mQh, mQl, mTh, mTl;
   int rc;
   if ((rc = tc::make_map_f16(&mQh, Q.hi, nq, Q.Kp, Q.Kp, TM))) return rc;
   if ((rc = tc::make_map_f16(&mQl, Q.lo, nq, Q.Kp, Q.Kp, TM))) return rc;
-  if ((rc = tc::make_map_f16(&mTh, T.hi, m, T.Kp, T.Kp, prm.tn >> 1))) return rc;
-  if ((rc = tc::make_map_f16(&mTl, T.lo, m, T.Kp, T.Kp, prm.tn >> 1))) return rc;
+  if ((rc = tc::make_map_f16(&mTh, T.hi, m, T.Kp, T.Kp, TM))) return rc;      // box = 128 rows: half of a full tile
+  if ((rc = tc::make_map_f16(&mTl, T.lo, m, T.Kp, T.Kp, TM))) return rc;
   prm.epi = P;
   prm.epi.nchunks = 2 * prm.echunks;   // two epilogue warps (column halves) per row
   const char* e = getenv("B200KGE_TC4_DIRECT");

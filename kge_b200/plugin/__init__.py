@@ -210,6 +210,28 @@ def _install_embedder_kernels(emb):
     emb._b200_patched = True
 
 
+class _NsSlotLossFn(torch.autograd.Function):
+    """One slot of a negative-sampling batch with BCE: forward = fused gather+score [n, 1+K] and the dense-loss kernel;
+    backward = the fused NS gradient kernel (b200kge_ns_backward: per-row fold, per-column recompute, scatter)."""
+
+    @staticmethod
+    def forward(ctx, ent_w, rel_w, model, triples, negatives, slot, offset, batch_size):
+        ctx.args = (model, slot, offset, batch_size)
+        ctx.save_for_backward(ent_w, rel_w, triples, negatives)
+        ln = model._b200_args()[0]
+        scores = engine.ns_score(model._b200_name, ent_w.detach(), rel_w.detach(), triples, negatives, slot, True, ln)
+        lab = torch.zeros(triples.shape[0], dtype=torch.int64, device=triples.device)
+        return engine.loss_dense(scores, lab, "bce", offset) / batch_size
+
+    @staticmethod
+    def backward(ctx, g):
+        ent_w, rel_w, triples, negatives = ctx.saved_tensors
+        model, slot, offset, batch_size = ctx.args
+        d_ent, d_rel = engine.ns_backward(model._b200_name, ent_w.detach(), rel_w.detach(), triples, {slot: negatives},
+                                          offset, model._b200_args()[0], batch_size)
+        return d_ent * g, d_rel * g, None, None, None, None, None, None
+
+
 class _B200ModelMixin:
     """Index-level overrides (kge_model.py:663-789): read the tables in place when possible."""
 
@@ -366,6 +388,20 @@ class _B200ModelMixin:
 
     def loss_dense(self, scores, labels, loss="bce", offset=0.0):
         return engine.loss_dense(scores, labels, loss, offset)
+
+    def b200_ns_native_backward_ok(self, slot):
+        """The fused NS gradient kernel covers the S / O slots of the dot family, TransE (L1, L2) and RotatE (L1)."""
+        if self.b200_backward != "native" or slot not in (0, 2):
+            return False
+        ln = self._b200_args()[0]
+        return {"transe": ln in (1.0, 2.0), "rotate": ln == 1.0}.get(self._b200_name, True)
+
+    def loss_negatives(self, triples, negatives, slot, offset, batch_size):
+        """BCE of one slot's [n, 1+K] block (positive first) / batch_size, differentiable through the gradient kernel
+        (train_negative_sampling.py:139-164)."""
+        ent_w, rel_w = self._b200_weights()
+        return _NsSlotLossFn.apply(ent_w, rel_w, self, triples.long().contiguous(), negatives.long().contiguous(),
+                                   int(slot), float(offset), int(batch_size))
 
     def score_sp_loss(self, s, p, labels, loss="bce", offset=0.0):
         ent, rel = self._b200_tables()

@@ -187,9 +187,14 @@ class B200TrainingJobNegativeSampling(TrainingJobNegativeSampling):
 
     def _process_subbatch(self, batch_index, batch, subbatch_slice, result):
         model = _fused_model(self.model)
-        if model is None or not self.is_forward_only:
+        kind = _fused_loss_kind(self.loss)
+        slots = [sl for sl in (S, P, O) if self._sampler.num_samples[sl] > 0]
+        trainable = (model is not None and kind is not None and kind[0] == "bce"
+                     and all(model.b200_ns_native_backward_ok(sl) for sl in slots))
+        if model is None or (not self.is_forward_only and not trainable):
             if self._device_sampling:
-                raise NotImplementedError("user.b200_device_sampling needs a b200_* model (forward-only epochs for now)")
+                raise NotImplementedError("user.b200_device_sampling needs a b200_* model whose slots the fused "
+                                          "gradient kernel covers (S / O slots, bce)")
             return super()._process_subbatch(batch_index, batch, subbatch_slice, result)
         batch_size = result.size
         result.prepare_time -= time.time()
@@ -198,7 +203,6 @@ class B200TrainingJobNegativeSampling(TrainingJobNegativeSampling):
         subbatch_size = len(triples)
         labels = batch["labels"]
         result.prepare_time += time.time()
-        kind = _fused_loss_kind(self.loss)
 
         for slot in [S, P, O]:
             num_samples = self._sampler.num_samples[slot]
@@ -216,6 +220,15 @@ class B200TrainingJobNegativeSampling(TrainingJobNegativeSampling):
             result.prepare_time += time.time()
 
             result.forward_time -= time.time()
+            if not self.is_forward_only:
+                # training: forward + the fused NS gradient kernel behind one autograd node
+                loss_value = model.loss_negatives(triples, negatives.to(self.device), slot, kind[1], batch_size)
+                result.avg_loss += loss_value.item()
+                result.forward_time += time.time()
+                result.backward_time -= time.time()
+                loss_value.backward()
+                result.backward_time += time.time()
+                continue
             scores = model.score_negatives(triples, negatives.to(self.device), slot)      # [n, 1+K], positive first
             if kind is not None and kind[0] == "bce":
                 # labels are 1 in column 0 and 0 elsewhere (train_negative_sampling.py:128-137): index labels

@@ -208,3 +208,33 @@ def test_training_with_penalties_and_normalisation(model, extra, splits):
     for ep in range(2):
         for a, b in zip(traces["plugin"][ep], traces["ref"][ep]):
             assert a == pytest.approx(b, rel=1e-3 if ep else REL, abs=1e-7)
+
+
+@pytest.mark.parametrize("model", ["complex", "transe", "rotate"])
+def test_negative_sampling_training_native_backward(model, splits):
+    """B200TrainingJobNegativeSampling in TRAINING mode: per slot one autograd node whose backward is the fused NS
+    gradient kernel (b200kge_ns_backward); two epochs (forward, backward, Adagrad) track the reference job, which draws
+    the same negatives from the same CPU sampler."""
+    extra = {"negative_sampling.num_samples.s": 11, "negative_sampling.num_samples.o": 13, "train.loss_arg": 1.0,
+             "negative_sampling.implementation": "triple"}
+    torch.manual_seed(0)
+    init = ju.make_job(model, E, R, D, splits, device="cpu", train_type="negative_sampling", loss="bce", batch_size=64,
+                       extra=extra)
+    losses = {}
+    for tag, dev in (("ref", "cpu"), ("native", "cuda")):
+        name = model if tag == "ref" else "b200_" + model
+        kw = {"job_class": "B200TrainingJobNegativeSampling"} if tag == "native" else {}
+        job = ju.make_job(name, E, R, D, splits, device=dev, train_type="negative_sampling", loss="bce", batch_size=64,
+                          forward_only=False, extra=extra, **kw)
+        ju.copy_tables(init, job)
+        out = []
+        for ep in range(2):
+            job.epoch += 1
+            if job.loader is None:
+                job._prepare()
+            ju.seed_all(10 + ep)
+            out.append(job.run_epoch()["avg_loss"])
+        losses[tag] = out
+    assert losses["ref"][1] < losses["ref"][0]
+    assert losses["native"][0] == pytest.approx(losses["ref"][0], rel=REL)
+    assert losses["native"][1] == pytest.approx(losses["ref"][1], rel=1e-3)
