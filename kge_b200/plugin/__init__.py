@@ -369,9 +369,15 @@ class _B200ModelMixin:
             need_grad = self._b200_needs_grad()
         if need_grad and self._b200_needs_grad():
             return _Loss1vsAllFn.apply(ent_w, rel_w, self, triples, loss, offset)
-        ln, prec = self._b200_args()
-        return engine.train_1vsall_forward(self._b200_name, ent_w.detach(), rel_w.detach(), triples, loss, offset,
-                                           ln, prec)
+        # forward only: a prepared step (table views, workspace, output scalar set up once per table storage)
+        st = self.__dict__.get("_b200_step")
+        n = triples.shape[0]
+        if st is None or st.cfg != (loss, offset) or not st.matches(ent_w, rel_w, n):
+            ln, prec = self._b200_args()
+            st = engine.Step1vsAll(self._b200_name, ent_w.detach(), rel_w.detach(), max(n, 1024), loss, offset, ln, prec)
+            st.cfg = (loss, offset)
+            self.__dict__["_b200_step"] = st
+        return st(triples)
 
     def loss_kvsall(self, combine, a, p, csr_offsets, csr_cols, loss="kl", offset=0.0, label_smoothing=0.0):
         """Sum over rows of the KvsAll loss with CSR multi-hot labels (train_KvsAll.py:242-294); forward only."""

@@ -70,6 +70,21 @@ def train_1vsall_backward(model, ent, rel, triples, loss="bce", offset=0.0):
     return kf.train_1vsall_backward(model, ent.detach(), rel.detach(), triples.long(), loss, offset)
 
 
+class Step1vsAll:
+    """Stand-in of engine.Step1vsAll (prepared fused step)."""
+
+    def __init__(self, model, ent, rel, max_n, loss="bce", offset=0.0, l_norm=1.0, precision="auto"):
+        self.model, self.ent, self.rel, self.max_n = model, ent, rel, max_n
+        self.loss, self.offset, self.l_norm = loss, offset, l_norm
+
+    def matches(self, ent, rel, n):
+        return n <= self.max_n and ent.data_ptr() == self.ent.data_ptr() and rel.data_ptr() == self.rel.data_ptr()
+
+    def __call__(self, triples):
+        _counter["n"] += 1
+        return orc.train_1vsall_forward(self.model, self.ent, self.rel, triples.long(), self.loss, self.offset, self.l_norm)
+
+
 _counter = {"n": 0}
 
 
@@ -98,6 +113,8 @@ def installed():
 
     for k in names:
         setattr(engine, k, g[k] if k == "launch_count" else counted(g[k]))
+    saved["Step1vsAll"] = engine.Step1vsAll
+    engine.Step1vsAll = Step1vsAll
     try:
         yield
     finally:
