@@ -45,16 +45,17 @@ void profile_end(cudaStream_t st) {
 
 namespace {
 
-// Which pre-split kernel scores a block with n query rows PER DIRECTION: the CTA-pair kernel (pairwise_tc4.cu) from
-// n = 128 up (two 128-row halves per cluster tile; measured 65.8 vs 67.6 us at the FB15k-237 headline shape), the 1-CTA
-// kernel (pairwise_tc3.cu) below.  Depends on n only — never on the candidate count or on stacking — so every call of
-// one batch (true scores on the unique targets, chunk scores, fused forms) runs the same kernel.
-// B200KGE_TC_VERSION=3 | 4 forces one of them.
-bool use_pair_kernel(int64_t n) {
+// Which pre-split kernel scores a block with n query rows PER DIRECTION and reduction length K: the CTA-pair kernel
+// (pairwise_tc4.cu) for n >= 128 and K > 448 (two 128-row halves per cluster tile; 65.8 vs 67.6 us at the FB15k-237
+// headline shape, K = 512), the 1-CTA kernel (pairwise_tc3.cu) otherwise (short reductions make the pair's per-tile
+// cross-CTA hand-over visible: RESCAL d=200 KvsAll 0.186 vs 0.146 ms).  Depends on n and K only — never on the
+// candidate count or on stacking — so every call of one batch (true scores on the unique targets, chunk scores, fused
+// forms) runs the same kernel.  B200KGE_TC_VERSION=3 | 4 forces one of them.
+bool use_pair_kernel(int64_t n, int K) {
   const char* env_v = getenv("B200KGE_TC_VERSION");
   if (env_v && atoi(env_v) == 3) return false;
   if (env_v && atoi(env_v) == 4) return true;
-  return n >= 128;
+  return n >= 128 && K > 448;
 }
 
 // bump allocator over the caller's workspace
@@ -124,7 +125,7 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
   //   AUTO    -> F16X3 (pre-split fp16 planes, pairwise_tc3.cu) for dot-product scorers with 32 <= K <= 1024 and
   //              n >= 16; fp32 SIMT otherwise (beyond K = 1024 the tensor core's fp32 accumulator error, which
   //              grows with the reduction length — 2.8e-4 of rms at K = 14541 — leaves too little margin)
-  //   F16X3   -> pairwise_tc4.cu (CTA pair) for n >= 128, pairwise_tc3.cu below (use_pair_kernel)
+  //   F16X3   -> pairwise_tc4.cu (CTA pair) for n >= 128 and K > 448, else pairwise_tc3.cu (use_pair_kernel)
   //   TF32_BF16X2 / 3XTF32 / TF32 -> pairwise_tc.cu (in-kernel split of raw fp32 tiles; needs TMA-able tables)
   int tc_kind = 0;       // 0 SIMT, 1 in-kernel split (pairwise_tc.cu), 3 pre-split planes
   if (f0.pair_op == PAIR_DOT && precision != B200KGE_PREC_FP32 && !cols_differ) {
@@ -178,7 +179,7 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
     if (tc_kind == 3) {
       // pre-split fp16 path (presplit.cu + pairwise_tc3.cu | pairwise_tc4.cu): one launch derives the hi/lo planes of
       // the folded queries and of the (gathered) candidate rows, one launch scores them.
-      const bool pair = use_pair_kernel(n);
+      const bool pair = use_pair_kernel(n, K);
       const int Kp = (int)round_up(K, 64);
       SplitSet SQ{Q, ldq, nullptr, 0, nq, nq, K, Kp, nullptr, nullptr, nullptr};
       SplitSet ST{B.cand->base, B.cand->ld, B.cand->idx, f0.col_off, m, m + 32, K, Kp, nullptr, nullptr, nullptr};
@@ -583,7 +584,7 @@ int b200kge_train_1vsall_forward(int model, float l_norm, int precision,
     // step is THREE launches — prologue (gather + both folds + operand split of queries and table + labels), the
     // scorer with the loss reduction in its epilogue, and the fixed-order finaliser.
     const char* env_v = getenv("B200KGE_TC_VERSION");
-    const int tcv = (env_v && atoi(env_v) == 1) ? 1 : (use_pair_kernel(n) ? 4 : 3);
+    const int tcv = (env_v && atoi(env_v) == 1) ? 1 : (use_pair_kernel(n, f0.K) ? 4 : 3);
     const int K = f0.K;
     const bool presplit = f0.col_off == f1.col_off && f0.pair_op == PAIR_DOT && model != B200KGE_CP &&
                           (precision == B200KGE_PREC_AUTO || precision == B200KGE_PREC_F16X3) && K >= 32 && K <= 1024 &&
