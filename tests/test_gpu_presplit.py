@@ -54,20 +54,6 @@ def variant(request, monkeypatch):
     return select
 
 
-def _load(name):
-    z = np.load(os.path.join(GOLDEN, name))
-    return {k: torch.from_numpy(z[k]) if z[k].ndim else z[k].item() for k in z.files}
-
-
-def _assert_close(got, ref, what, tol=TOL):
-    got = got.detach().cpu().double()
-    ref = ref.double()
-    assert got.shape == ref.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
-    rms = max(float(ref.pow(2).mean().sqrt()), 1e-6)
-    err = float((got - ref).abs().max()) if ref.numel() else 0.0
-    assert err <= tol * rms, f"{what}: max|d|={err:.3e} rms={rms:.3e} ratio={err / rms:.2e}"
-
-
 def test_presplit_fp16_golden(eng, variant):
     variant()
     for fname, model in (("scores_complex.npz", "complex"), ("scores_distmult.npz", "distmult"),
