@@ -323,6 +323,17 @@ int b200kge_train_1vsall_backward(int model, const b200kge_rows_t* ent, const b2
                                     float* d_ent, int64_t lde, float* d_rel, int64_t ldr,
                                     void* workspace, size_t workspace_bytes, b200kge_stream_t stream);
 
+/* Backward of b200kge_score_1vsN over the whole entity table for the dot family (the unfused route: a job computes a
+ * dense [n, E] score matrix, its loss, and autograd hands back grad_scores = dL/dscores [n, ldg]): dense gradients of
+ * the entity table d_ent [E, lde] and the relation table d_rel [R, ldr], both OVERWRITTEN.  Fold of the n query rows,
+ * fp16 hi/lo planes of grad_scores and of its transpose, two split-K tensor-core GEMMs (dT = G^T Q, dQ = G T) and the
+ * row-wise unfold — no cuBLAS, no [n, E, D] intermediate. */
+size_t b200kge_score_1vsN_backward_workspace_bytes(int model, int64_t n, int64_t E, int32_t D);
+int b200kge_score_1vsN_backward(int model, int combine, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+                                const int64_t* q_idx, const int64_t* p_idx, int64_t n, const float* grad_scores,
+                                int64_t ldg, float* d_ent, int64_t lde, float* d_rel, int64_t ldr, void* workspace,
+                                size_t workspace_bytes, b200kge_stream_t stream);
+
 /* KvsAll loss with CSR multi-hot labels (kge/job/train_KvsAll.py:242-300 without the densified label matrix):
  * row i's labels are the columns csr_col[csr_off[i] .. csr_off[i+1]) (sorted; a repeated column counts as often
  * as it appears, like duplicate triples in the reference), optionally smoothed: y = (1 - eps) * count + 1/m.

@@ -277,6 +277,15 @@ __global__ void unpack_triples_kernel(const int64_t* __restrict__ tri, int64_t n
   }
 }
 
+__global__ void pack_triples_kernel(const int64_t* __restrict__ q, const int64_t* __restrict__ p, int64_t n, int combine,
+                                    int64_t* __restrict__ tri) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  tri[3 * i + 1] = p[i];
+  tri[3 * i + (combine == B200KGE_SP_ ? 0 : 2)] = q[i];
+  tri[3 * i + (combine == B200KGE_SP_ ? 2 : 0)] = 0;
+}
+
 __global__ void __launch_bounds__(128)
 shard_gather_rows_kernel(Rows shard, int64_t lo, const int64_t* __restrict__ idx, float* __restrict__ out, int64_t ldo) {
   const int64_t i = blockIdx.x;
@@ -732,11 +741,24 @@ int gemm_planes(const SplitSet& A, const SplitSet& B, float* C, int64_t ldc, cud
 // [nq, ldq] into the caller's buffer.  dir as in launch_unfold.
 int backward_block(int model, const Rows& E, const Rows& R, const int64_t* triples, int64_t n, int dir,
                    const float* Q, int64_t ldq, const int64_t* lab, int col_off, int K, int loss_kind, float offset,
-                   float* d_ent, int64_t lde, float* dQ, Arena ws, cudaStream_t st) {
+                   float* d_ent, int64_t lde, float* dQ, Arena ws, cudaStream_t st,
+                   const float* Gdense = nullptr, int64_t ldg = 0) {
   const int64_t nq = dir < 0 ? 2 * n : n, m = E.rows;
   const int64_t ldz = round_up(m, 4), Ep = round_up(m, 64), Np = round_up(nq, 64);
   const int64_t ldE = round_up(m, 4), ldN = round_up(nq, 4);
   int rc;
+  SplitSet SG{nullptr, 0, nullptr, 0, nq, nq, (int)m, (int)Ep, nullptr, nullptr, nullptr};
+  SplitSet SGT{nullptr, 0, nullptr, 0, m, m, (int)nq, (int)Np, nullptr, nullptr, nullptr};
+  if (Gdense) {
+    // the caller's dL/dz (autograd through a dense score matrix): planes of G and of its transpose, row scaled
+    float* Gt = (float*)ws.take((size_t)m * ldN * 4);
+    if (!Gt) { set_error("workspace too small for the transposed gradient"); return B200KGE_ERR_WORKSPACE; }
+    if ((rc = launch_transpose(Gdense, ldg, nq, m, Gt, ldN, st))) return rc;
+    SG.src = Gdense; SG.ld = ldg;
+    SGT.src = Gt; SGT.ld = ldN;
+    if (!take_planes(ws, SG) || !take_planes(ws, SGT)) { set_error("workspace too small for the gradient planes"); return B200KGE_ERR_WORKSPACE; }
+    if ((rc = launch_presplit(SGT, SG, st))) return rc;
+  } else {
   // 1. scores through the validated scorer (plain-store epilogue)
   float* z = (float*)ws.take((size_t)nq * ldz * 4);
   if (!z) { set_error("workspace too small for the score matrix"); return B200KGE_ERR_WORKSPACE; }
@@ -750,8 +772,6 @@ int backward_block(int model, const Rows& E, const Rows& R, const int64_t* tripl
     if ((rc = run_block(B, 1.0f, B200KGE_PREC_AUTO, EPI_STORE, P, ws, st, nullptr))) return rc;
   }
   // 2. G = sigmoid(z + off) - y as planes, both layouts
-  SplitSet SG{nullptr, 0, nullptr, 0, nq, nq, (int)m, (int)Ep, nullptr, nullptr, nullptr};
-  SplitSet SGT{nullptr, 0, nullptr, 0, m, m, (int)nq, (int)Np, nullptr, nullptr, nullptr};
   if (!take_planes(ws, SG) || !take_planes(ws, SGT)) { set_error("workspace too small for the gradient planes"); return B200KGE_ERR_WORKSPACE; }
   float* row_stat = nullptr;
   if (loss_kind == B200KGE_LOSS_KL) {
@@ -761,6 +781,7 @@ int backward_block(int model, const Rows& E, const Rows& R, const int64_t* tripl
   if ((rc = launch_grad_planes(z, ldz, nq, m, lab, nullptr, 0, row_stat, loss_kind == B200KGE_LOSS_KL ? 0.f : offset,
                                1.0f / (float)n, SG.hi, SG.lo, Ep, SGT.hi, SGT.lo, Np, SG.inv_scale, SGT.inv_scale,
                                st))) return rc;
+  }
   // 3. transposed operands T^T [K, E] and Q^T [K, nq], then their planes
   float* Tt = (float*)ws.take((size_t)K * ldE * 4);
   float* Qt = (float*)ws.take((size_t)K * ldN * 4);
@@ -870,6 +891,45 @@ int b200kge_train_1vsall_backward(int model, const b200kge_rows_t* ent, const b2
   return 0;
 }
 
+
+size_t b200kge_score_1vsN_backward_workspace_bytes(int model, int64_t n, int64_t E, int32_t D) {
+  const int64_t K = (model == B200KGE_CP) ? D / 2 : D;
+  const int64_t ldq = round_up(K, 32);
+  return 2 * (size_t)n * ldq * 4 + (size_t)n * 4 * 8 + (size_t)E * round_up(n, 4) * 4 + 8192 + backward_block_bytes(n, E, K, ldq);
+}
+
+int b200kge_score_1vsN_backward(int model, int combine, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+                                const int64_t* q_idx, const int64_t* p_idx, int64_t n, const float* grad_scores,
+                                int64_t ldg, float* d_ent, int64_t lde, float* d_rel, int64_t ldr, void* workspace,
+                                size_t workspace_bytes, b200kge_stream_t stream) {
+  if (!ent || !rel || !q_idx || !p_idx || !grad_scores || !d_ent || !d_rel) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  if (ent->idx || rel->idx) { set_error("ent/rel must be plain tables"); return B200KGE_ERR_INVALID; }
+  if (combine != B200KGE_SP_ && combine != B200KGE__PO) { set_error("cannot handle combine=%d", combine); return B200KGE_ERR_INVALID; }
+  int rc = validate_model(model, to_rows(ent), to_rows(rel)); if (rc) return rc;
+  if (model > B200KGE_RESCAL) { set_error("the tensor-core backward covers the dot family only (model %d)", model); return B200KGE_ERR_UNSUPPORTED; }
+  if (lde < ent->dim || ldr < rel->dim || ldg < ent->rows) { set_error("leading dimensions too small"); return B200KGE_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Rows E = to_rows(ent), R = to_rows(rel);
+  B2K_CUDA(cudaMemsetAsync(d_rel, 0, (size_t)R.rows * ldr * 4, st));
+  B2K_CUDA(cudaMemsetAsync(d_ent, 0, (size_t)E.rows * lde * 4, st));
+  if (n <= 0) return 0;
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  Folded f = folded_problem(model, combine, E.dim, 1.0f);
+  const int64_t ldq = round_up(f.K, 32);
+  float* Q = (float*)ws.take((size_t)n * ldq * 4);
+  float* dQ = (float*)ws.take((size_t)n * ldq * 4);
+  int64_t* tri = (int64_t*)ws.take((size_t)n * 3 * 8);
+  if (!Q || !dQ || !tri) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+  // the unfold works on [n,3] triples: (q, p, .) for sp_, (., p, q) for _po
+  pack_triples_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q_idx, p_idx, n, combine, tri);
+  B2K_LAUNCH_CHECK("pack_triples_kernel");
+  Rows A = E; A.idx = q_idx; A.rows = n;
+  Rows Pr = R; Pr.idx = p_idx; Pr.rows = n;
+  if ((rc = launch_fold_queries(model, combine, A, Pr, n, 0, Q, ldq, st))) return rc;
+  if ((rc = backward_block(model, E, R, tri, n, combine, Q, ldq, nullptr, f.col_off, f.K, B200KGE_LOSS_BCE, 0.f, d_ent, lde, dQ,
+                           ws, st, grad_scores, ldg))) return rc;
+  return launch_unfold(model, E, R, tri, n, combine, dQ, ldq, d_ent, lde, d_rel, ldr, st);
+}
 
 int b200kge_lookup_penalty(const b200kge_rows_t* rows, const float* counts, float p, int complex_abs, float scale,
                              float* out, void* workspace, size_t workspace_bytes, b200kge_stream_t stream) {

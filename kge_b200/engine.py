@@ -495,6 +495,26 @@ def train_1vsall_backward(model: str, ent, rel, triples, loss: str = "bce", offs
     return d_ent, d_rel
 
 
+def score_1vsN_backward(model: str, combine: str, ent, rel, q, p, grad_scores):
+    """(d_ent, d_rel) of a dense [n, E] score block of the dot family given dL/dscores (fresh tensors)."""
+    _require_cuda(ent, rel, grad_scores)
+    lib, k = _lib.load(), _Keep()
+    re_, rr = k.rows(ent), k.rows(rel)
+    qi, pi = _i64(q), _i64(p)
+    g = grad_scores if (grad_scores.dtype == torch.float32 and grad_scores.stride(1) == 1) else grad_scores.float().contiguous()
+    n = qi.numel()
+    dev = ent.device
+    d_ent = torch.empty_like(_f32(ent))
+    d_rel = torch.empty_like(_f32(rel))
+    ws = torch.empty(lib.b200kge_score_1vsN_backward_workspace_bytes(MODELS[model], n, ent.shape[0], ent.shape[1]),
+                     dtype=torch.uint8, device=dev)
+    _lib.check(lib.b200kge_score_1vsN_backward(
+        MODELS[model], SP_ if combine == "sp_" else _PO, C.byref(re_), C.byref(rr), qi.data_ptr(), pi.data_ptr(), n,
+        g.data_ptr(), g.stride(0), d_ent.data_ptr(), d_ent.stride(0), d_rel.data_ptr(), d_rel.stride(0), ws.data_ptr(),
+        ws.numel(), _stream(dev)))
+    return d_ent, d_rel
+
+
 def lookup_penalty(weight: torch.Tensor, regularize: str = "lp", regularize_weight: float = 0.0, p: float = 2.0,
                      weighted: bool = False, indexes: Optional[torch.Tensor] = None, space: str = "euclidean"):
     """LookupEmbedder.penalty (lookup_embedder.py:123-177) as a 0-d tensor."""

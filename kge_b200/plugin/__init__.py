@@ -311,6 +311,17 @@ class _B200ModelMixin:
         return torch.cat((ref(ent[a[:n]], rel[p], cand, "sp_"), ref(cand, rel[p], ent[a[n:]], "_po")), dim=1)
 
     def _b200_score_backward(self, ent_w, rel_w, kind, a, p, b, grad_out):
+        name = self._b200_name
+        if (self.b200_backward == "native" and b is None and kind in ("sp_", "_po", "sp_po")
+                and name in ("complex", "distmult", "simple", "cp", "rescal")):
+            # dense [n, E] (or [n, 2E]) scores over the whole table: tensor-core gradient GEMMs + unfold
+            E_ = ent_w.shape[0]
+            if kind != "sp_po":
+                return engine.score_1vsN_backward(name, kind, ent_w.detach(), rel_w.detach(), a, p, grad_out)
+            n = p.numel()
+            de1, dr1 = engine.score_1vsN_backward(name, "sp_", ent_w.detach(), rel_w.detach(), a[:n], p, grad_out[:, :E_])
+            de2, dr2 = engine.score_1vsN_backward(name, "_po", ent_w.detach(), rel_w.detach(), a[n:], p, grad_out[:, E_:])
+            return de1 + de2, dr1 + dr2
         e, r = ent_w.detach().requires_grad_(True), rel_w.detach().requires_grad_(True)
         with torch.enable_grad():
             out = self._b200_ref_scores(e, r, kind, a, p, b)

@@ -70,6 +70,13 @@ def train_1vsall_backward(model, ent, rel, triples, loss="bce", offset=0.0):
     return kf.train_1vsall_backward(model, ent.detach(), rel.detach(), triples.long(), loss, offset)
 
 
+def score_1vsN_backward(model, combine, ent, rel, q, p, grad_scores):
+    e, r = ent.detach().clone().requires_grad_(True), rel.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        x = score_1vsN(model, combine, e, r, e, q, p, None)
+        return torch.autograd.grad(x, (e, r), grad_scores)
+
+
 class Step1vsAll:
     """Stand-in of engine.Step1vsAll (prepared fused step)."""
 
@@ -101,7 +108,7 @@ def installed():
     from kge_b200 import engine
 
     names = ["score_spo", "score_1vsN", "score_sp_po", "train_1vsall_forward", "score_1vsN_loss",
-             "score_1vsN_loss_csr", "ns_score", "loss_dense", "train_1vsall_backward", "launch_count"]
+             "score_1vsN_loss_csr", "ns_score", "loss_dense", "train_1vsall_backward", "score_1vsN_backward", "launch_count"]
     saved = {k: getattr(engine, k) for k in names}
     g = globals()
 

@@ -100,3 +100,24 @@ def test_ns_backward(eng, model, D, ln):
                                      0.25, ln)
     _assert_close(d_ent, ref_e, f"{model} d_ent")
     _assert_close(d_rel, ref_r, f"{model} d_rel")
+
+
+@pytest.mark.parametrize("model,D", [("complex", 128), ("distmult", 64), ("simple", 128), ("cp", 64), ("rescal", 24)])
+@pytest.mark.parametrize("combine", ["sp_", "_po"])
+def test_score_1vsN_backward_vs_autograd(eng, model, D, combine):
+    """Backward of a dense [n, E] score block given dL/dscores (the unfused route of a job: score_sp -> KgeLoss ->
+    autograd) against torch autograd of the oracle's expression in fp64."""
+    E, R, n = 3001, 5, 150
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.5)
+    tri = orc.make_triples(E, R, n)
+    q = tri[:, 0] if combine == "sp_" else tri[:, 2]
+    g = torch.randn((n, E), generator=torch.Generator().manual_seed(2)) * 0.1
+    e64, r64 = ent.double().requires_grad_(True), rel.double().requires_grad_(True)
+    if combine == "sp_":
+        x = orc.score_emb(model, e64[q], r64[tri[:, 1]], e64, "sp_")
+    else:
+        x = orc.score_emb(model, e64, r64[tri[:, 1]], e64[q], "_po")
+    ref_e, ref_r = torch.autograd.grad(x, (e64, r64), g.double())
+    d_ent, d_rel = eng.score_1vsN_backward(model, combine, ent.cuda(), rel.cuda(), q.cuda(), tri[:, 1].cuda(), g.cuda())
+    _assert_close(d_ent, ref_e, f"{model} {combine} d_ent")
+    _assert_close(d_rel, ref_r, f"{model} {combine} d_rel")
