@@ -432,6 +432,38 @@ def other_configs(engine, torch, dev, flush, peaks):
     return out
 
 
+def train_step_bench(torch, local, ent_c, rel_c, batches_host, flush, iters=10):
+    """The headline workload as a TRAINING step (forward + backward, no optimizer step) through the reference job's
+    `_process_batch` on the plugin with the gradient kernels; informational, not part of `value`."""
+    import torch as _t
+
+    if not _have_kge():
+        return {"skipped": "reference not installed"}
+    from kge_b200 import hostenv
+
+    hostenv.import_kge()
+    job = make_job("b200_" + MODEL, f"cuda:{local}", job_class="B200TrainingJob1vsAll", tables=(ent_c, rel_c))
+    job.is_forward_only = False
+    for i in range(3):
+        job._process_batch(i, {"triples": batches_host[i % 4]})
+    _t.cuda.synchronize()
+    ts = []
+    for i in range(iters):
+        flush.fill_(i & 0xFF)
+        _t.cuda.synchronize()
+        t0 = time.perf_counter()
+        job._process_batch(i, {"triples": batches_host[i % 4]})
+        _t.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    per = sum(ts) / len(ts)
+    g = job.model.get_s_embedder()._embeddings.weight.grad
+    return {"workload": "the headline batch as a training step: fused forward + native backward (recompute, G planes, two "
+                        "split-K tensor-core GEMMs, unfold) through B200TrainingJob1vsAll._process_batch; gradients "
+                        "accumulate into .grad, no optimizer step",
+            "ms_per_step": per * 1e3, "value": N_BATCH / per, "unit": "train triples/s",
+            "grad_finite": bool(g is not None and bool(_t.isfinite(g).all()))}
+
+
 def transe_shard_bench(engine, torch, dev, flush, peaks, have_ref, fma_peak):
     rows, D5, n5, R5 = 600000, 512, 128, 822
     g = torch.Generator(device=dev).manual_seed(1234)
@@ -771,6 +803,10 @@ def run_ours(args):
             line["configs"] = other_configs(engine, torch, dev, flush, peaks)
         except Exception as ex:
             line["configs"] = {"error": repr(ex)}
+        try:
+            line["configs"]["cfg2_train_fwd_bwd"] = train_step_bench(torch, local, ent_c, rel_c, batches_host, flush)
+        except Exception as ex:
+            line["configs"]["cfg2_train_fwd_bwd"] = {"error": repr(ex)}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
