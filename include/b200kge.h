@@ -185,9 +185,10 @@ int b200kge_rank_sp_po(int model, float l_norm, int precision, const b200kge_row
  * candidate columns filter_col[filter_off[r] .. filter_off[r+1]) that hold known answers; they are excluded from the
  * counts exactly like the reference's "+inf label subtracted" (eval_entity_ranking.py:489-531,561-566), except the
  * row's own answer own_col[r] (may be NULL; :287-290).  Columns are positions in `cand`, which must be a plain
- * table or chunk (cand->idx == NULL).  The CSR is consumed by the epilogue of the pre-split tensor-core kernel (a
- * per-thread cursor into the row's segment); models / shapes served by the CUDA-core kernel return
- * B200KGE_ERR_UNSUPPORTED before anything is launched — pass the dense filter to b200kge_rank_sp_po instead. */
+ * table or chunk (cand->idx == NULL).  The CSR is consumed inside the scoring kernels' epilogues (pre-split tensor-core
+ * kernels: one cursor per thread = row; CUDA-core kernel: one forward-moving cursor per owned row); CP and the in-kernel
+ * split precision modes return B200KGE_ERR_UNSUPPORTED before anything is launched — pass the dense filter to
+ * b200kge_rank_sp_po instead. */
 int b200kge_rank_sp_po_csr(int model, float l_norm, int precision, const b200kge_rows_t* s,
                            const b200kge_rows_t* p, const b200kge_rows_t* o, const b200kge_rows_t* cand,
                            int64_t n, const float* true_score, const int64_t* filter_off,

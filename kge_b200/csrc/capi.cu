@@ -146,9 +146,11 @@ int run_block(const Block& B, float l_norm, int precision, int epi_kind, EpiPara
       tc_kind = 1; precision = B200KGE_PREC_TF32_BF16X2;
     } }
 
-  if (P.csr_off && (tc_kind != 3 || cols_differ || B.cand->idx)) {
-    // nothing has been launched or taken from the workspace yet: callers fall back to their dense / composed form
-    set_error("the CSR side input is consumed by the pre-split tensor-core epilogue only (dot family, plain candidate table)");
+  if (P.csr_off && (cols_differ || B.cand->idx || tc_kind == 1 || (tc_kind == 0 && epi_kind != EPI_RANK))) {
+    // CSR side inputs: the pre-split tensor-core epilogue (losses and rank) and the CUDA-core kernel's rank epilogue.
+    // Nothing has been launched or taken from the workspace yet: callers fall back to their dense / composed form.
+    set_error("this CSR side input is not consumed by the kernel serving this call (losses: pre-split tensor-core path; "
+              "rank: that path or the CUDA-core kernel; plain candidate table)");
     return B200KGE_ERR_UNSUPPORTED;
   }
 

@@ -113,6 +113,21 @@ pairwise_simt_kernel(const float* __restrict__ Q, int64_t ldq, int64_t nq, Rows 
     const int64_t row = row0 + ty * 4 + 64 * (i >> 2) + (i & 3);
     aux[i] = (row < nq) ? epi_row_aux<EPI>(P, row) : 0.f;
   }
+  // CSR ranking filter: per owned row a cursor into its sorted segment of known answers; the CTA visits
+  // its column tiles in increasing order, so each cursor only moves forward (one binary search at the first tile, then
+  // ~one L1-resident load per row and tile)
+  int64_t ccur[8], cend[8];
+  if constexpr (EPI == EPI_RANK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t row = row0 + ty * 4 + 64 * (i >> 2) + (i & 3);
+      ccur[i] = 0; cend[i] = 0;
+      if (P.csr_off && row < nq) {
+        cend[i] = __ldg(P.csr_off + row + 1);
+        ccur[i] = csr_lower_bound(P.csr_col, __ldg(P.csr_off + row), cend[i], (int64_t)t0 * BN);
+      }
+    }
+  }
 
   for (int tile = t0; tile < t1; ++tile) {
     const int64_t col0 = (int64_t)tile * BN;
@@ -204,10 +219,27 @@ pairwise_simt_kernel(const float* __restrict__ Q, int64_t ldq, int64_t nq, Rows 
     for (int i = 0; i < 8; ++i) {
       const int64_t row = row0 + ty * 4 + 64 * (i >> 2) + (i & 3);
       const bool row_ok = row < nq;
+      unsigned filtered = 0u;          // bit j: element (i, j) is a known answer of this row (rank filter)
+      if constexpr (EPI == EPI_RANK) {
+        if (ccur[i] < cend[i]) {
+          const int64_t own = P.csr_skip ? __ldg(P.csr_skip + row) : -1;
+          int64_t cj = __ldg(P.csr_col + ccur[i]);
+          while (cj < col0 + BN) {                       // listed columns inside this tile
+            const int rel = (int)(cj - col0), jj = rel >> 6, c4 = rel & 63;
+            if ((c4 >> 2) == tx && cj != own) filtered |= 1u << (jj * 4 + (c4 & 3));
+            if (++ccur[i] >= cend[i]) break;
+            cj = __ldg(P.csr_col + ccur[i]);
+          }
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int64_t col = col0 + tx * 4 + 64 * (j >> 2) + (j & 3);
-        if (row_ok && col < m) epi_elem<EPI>(P, st[i], row, col, pair_finish<PAIR>(acc[i][j], p_norm), aux[i]);
+        float x = pair_finish<PAIR>(acc[i][j], p_norm);
+        if constexpr (EPI == EPI_RANK) {
+          if (filtered & (1u << j)) x = -INFINITY;       // eval_entity_ranking.py:561-566: score - inf
+        }
+        if (row_ok && col < m) epi_elem<EPI>(P, st[i], row, col, x, aux[i]);
       }
     }
   }

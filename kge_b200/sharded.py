@@ -43,6 +43,10 @@ class EngineBackend:
 
     def rank_sp_po(self, model, s_emb, rel, p, o_emb, cand, true2n, filter2n, rtol, atol, l_norm, precision):
         from . import engine
+        if isinstance(filter2n, tuple):          # CSR filter (offsets [2n+1], local columns, own local column [2n])
+            off, col, own = filter2n
+            return engine.rank_sp_po_csr(model, s_emb, rel, o_emb, cand, true2n, off, col, own, None, p, None, rtol, atol,
+                                         l_norm, precision)
         return engine.rank_sp_po(model, s_emb, rel, o_emb, cand, true2n, None, p, None, None, filter2n, rtol, atol,
                                  l_norm, precision)
 
@@ -184,9 +188,12 @@ class ShardedKgeModel:
         t_po = x[ar, 2 * n + ar].contiguous()
         return (t_sp, t_po), (s_emb, pi, o_emb)
 
-    def rank_sp_po(self, s, p, o, filter_sp=None, filter_po=None, rtol=1e-4, atol=1e-5):
+    def rank_sp_po(self, s, p, o, filter_sp=None, filter_po=None, rtol=1e-4, atol=1e-5, filter_csr=None):
         """(s_rank, s_ties, o_rank, o_ties) over ALL entities; filter_* are this rank's column slices
-        [n, E_local] of the reference's +inf label matrix (eval_entity_ranking.py:287-290,561-566).
+        [n, E_local] of the reference's +inf label matrix (eval_entity_ranking.py:287-290,561-566), or — without any
+        dense matrix — filter_csr = (offsets [2n+1], columns): the known answers of the 2n stacked rows (sp_ rows, then
+        _po rows) as GLOBAL entity ids, sorted per row; this rank keeps the ids of its shard (the row's own answer
+        stays in: :287-290).
         One stacked score+rank launch on the shard, then an integer all-reduce => bit-exact, 32*n bytes instead
         of moving logits."""
         (t_sp, t_po), (s_emb, pi, o_emb) = self.true_scores(s, p, o)
@@ -195,7 +202,15 @@ class ShardedKgeModel:
         counts = torch.zeros((2, 2 * n), dtype=torch.int64, device=dev)
         if self.hi > self.lo:
             filt = None
-            if filter_sp is not None or filter_po is not None:
+            if filter_csr is not None:
+                off, col = filter_csr
+                rows = torch.repeat_interleave(torch.arange(2 * n, device=dev), off[1:] - off[:-1])
+                keep = (col >= self.lo) & (col < self.hi)
+                loff = torch.zeros(2 * n + 1, dtype=torch.int64, device=dev)
+                loff[1:] = torch.cumsum(torch.bincount(rows[keep], minlength=2 * n), 0)
+                own = torch.cat([o.long(), s.long()]) - self.lo
+                filt = (loff, (col[keep] - self.lo).contiguous(), own.contiguous())
+            elif filter_sp is not None or filter_po is not None:
                 z = lambda f: f if f is not None else torch.zeros((n, self.hi - self.lo), device=dev)
                 filt = torch.cat([z(filter_sp), z(filter_po)], 0)
             r, t = self.backend.rank_sp_po(self.model, s_emb, self.rel, pi, o_emb, self.ent,

@@ -194,10 +194,12 @@ def test_loss_with_csr_labels(eng, model, D, loss):
             assert abs(float(rws.sum()) - ref) <= 1e-4 * abs(ref)
 
 
-@pytest.mark.parametrize("model,D", [("complex", 128), ("distmult", 64), ("rescal", 40), ("simple", 64)])
+@pytest.mark.parametrize("model,D", [("complex", 128), ("distmult", 64), ("rescal", 40), ("simple", 64), ("transe", 64),
+                                     ("rotate", 64), ("distmult", 16)])
 def test_rank_with_csr_filter_is_bit_identical_to_dense_filter(eng, model, D):
-    """Filtered ranking with the known answers as CSR (consumed by the tensor-core epilogue's per-thread cursor)
-    against the same call with the reference's dense +inf label matrix (eval_entity_ranking.py:489-531,561-566):
+    """Filtered ranking with the known answers as CSR (consumed by the epilogues' cursors: tensor-core kernels for the
+    dot family, CUDA-core kernel for TransE / RotatE and for K < 32) against the same call with the reference's dense
+    +inf label matrix (eval_entity_ranking.py:489-531,561-566):
     integer counts, bit-identical; the row's own answer stays in (:287-290); ragged tiles, empty rows, rows with
     many listed columns, chunked candidates."""
     E, R, n = 5003, 5, 150
@@ -237,10 +239,17 @@ def test_rank_with_csr_filter_is_bit_identical_to_dense_filter(eng, model, D):
         assert torch.equal(r1, r2) and torch.equal(t1, t2)
         if lo == 0:
             assert int(t2.min()) >= 1                               # the own answer is a tie of itself
-    if model != "rescal":
-        with pytest.raises(NotImplementedError):                    # CUDA-core path: dense filter only
-            eng.rank_sp_po_csr(model, ce, cr, ce, ce, true2n[:16], coffs[:17].cuda() * 0, cols[:0].cuda(), None,
-                               s[:8], p[:8], o[:8])
+
+
+def test_rank_csr_is_refused_where_no_kernel_consumes_it(eng):
+    """CP's two directions read different table columns (no stacked launch): the CSR form answers
+    NotImplementedError before anything is launched and the caller passes the dense filter instead."""
+    ent, rel = orc.make_tables("cp", 500, 3, 32)
+    tri = orc.make_triples(500, 3, 20).cuda()
+    z = torch.zeros(41, dtype=torch.int64, device="cuda")
+    with pytest.raises(NotImplementedError):
+        eng.rank_sp_po_csr("cp", ent.cuda(), rel.cuda(), ent.cuda(), ent.cuda(), torch.zeros(40, device="cuda"), z, z[:0], None,
+                           tri[:, 0].contiguous(), tri[:, 1].contiguous(), tri[:, 2].contiguous())
 
 
 def test_device_uniform_sampler(eng):

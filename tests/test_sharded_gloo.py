@@ -29,6 +29,14 @@ class OracleBackend:
 
     def rank_sp_po(self, model, s_emb, rel, p, o_emb, cand, true2n, filter2n, rtol, atol, l_norm, precision):
         n = s_emb.shape[0]
+        if isinstance(filter2n, tuple):          # CSR -> the dense matrix the kernels never build
+            off, col, own = filter2n
+            dense = torch.zeros((2 * n, cand.shape[0]))
+            rows = torch.repeat_interleave(torch.arange(2 * n), off[1:] - off[:-1])
+            dense[rows, col] = float("inf")
+            ok = (own >= 0) & (own < cand.shape[0])
+            dense[torch.arange(2 * n)[ok], own[ok]] = 0.0
+            filter2n = dense
         x = torch.cat([orc.score_emb(model, s_emb, rel[p], cand, "sp_", l_norm),
                        orc.score_emb(model, cand, rel[p], o_emb, "_po", l_norm)], 0)
         if filter2n is not None:
@@ -108,6 +116,17 @@ def _worker(rank, world, port, model, E, R, D, n, out):
             rr, tt = orc.ranks_and_ties(po, t_po)
             assert torch.equal(s_rank, rr) and torch.equal(s_ties, tt)
             assert int(o_ties.min()) >= 1 and int(s_ties.min()) >= 1
+            if f is not None:
+                # the same filter as CSR over the stacked rows (global ids; the own answers included, as the index has them)
+                fs = torch.cat([f[:, :E], f[:, E:]], 0).clone()
+                fs[torch.arange(n), o] = float("inf")
+                fs[n + torch.arange(n), s] = float("inf")
+                rr_, cc_ = torch.nonzero(torch.isinf(fs), as_tuple=True)
+                offc = torch.zeros(2 * n + 1, dtype=torch.int64)
+                offc[1:] = torch.cumsum(torch.bincount(rr_, minlength=2 * n), 0)
+                got = m.rank_sp_po(s, p, o, filter_csr=(offc, cc_))
+                for x, y in zip(got, (s_rank, s_ties, o_rank, o_ties)):
+                    assert torch.equal(x, y)
         # 4. BCE
         got = float(m.loss_1vsall_bce(s, p, o, 0.5))
         want = float(orc.train_1vsall_forward(model, ent, rel, tri, "bce", 0.5))
