@@ -328,6 +328,32 @@ def _parity(got, ref):
     return {"max_abs_err_over_rms": err / max(rms, 1e-30), "ok": bool(err <= 1e-4 * rms), "tolerance": 1e-4}
 
 
+def headline_parity(engine, torch, dev, ent_c, rel_c, rows=256):
+    """The headline shape against the LIVE reference on the CPU for a row sample: score error, and how often the rank
+    of the true answer (reference rank arithmetic, eval_entity_ranking.py:571-618) agrees — reported, not asserted."""
+    from kge_b200 import synthetic
+
+    tri = synthetic.make_triples(E, R, rows, seed=4242)
+    m = _ref_model(MODEL, E, R, D, ent_c, rel_c)
+    with torch.no_grad():
+        ref = m.score_sp(tri[:, 0], tri[:, 1])
+    ent, rel = ent_c.to(dev), rel_c.to(dev)
+    t = tri.to(dev)
+    got = engine.score_1vsN(MODEL, "sp_", ent, rel, ent, t[:, 0].contiguous(), t[:, 1].contiguous()).cpu()
+    out = _parity(got, ref)
+
+    def final_ranks(x):
+        tr = x[torch.arange(rows), tri[:, 2]].view(-1, 1)
+        close = torch.isclose(x, tr, rtol=1e-4, atol=1e-5)
+        rank = ((x > tr) & ~close).sum(1)
+        return rank + close.sum(1) // 2
+    a, b = final_ranks(got), final_ranks(ref)
+    out.update({"rows": rows, "rank_agreement": float((a == b).float().mean()), "max_rank_delta": int((a - b).abs().max()),
+                "against": f"reference ComplEx.score_sp on the CPU for {rows} rows of the headline shape; ranks = rounded "
+                           "mean rank of the true object with the reference's tolerance band (rtol 1e-4, atol 1e-5)"})
+    return out
+
+
 def other_configs(engine, torch, dev, flush, peaks):
     """BASELINE.json configs 3-5 on one GPU: kernel ms, rate, roofline fraction, parity vs the live reference."""
     from kge_b200 import synthetic
@@ -796,6 +822,11 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if world == 1 and _have_kge():
+        try:
+            line["parity"] = headline_parity(engine, torch, dev, ent_c, rel_c)
+        except Exception as ex:
+            line["parity"] = {"error": repr(ex)}
     if sharded is not None:
         line["sharded"] = sharded
     if world == 1 and not args.no_configs:

@@ -251,15 +251,20 @@ def test_fused_rank_equals_rank_of_own_scores(eng, model, D, prec):
                                        None if f is None else f.cuda(), precision=prec)
             assert torch.equal(r.cpu(), rr), (model, combine, (r.cpu() - rr).abs().max())
             assert torch.equal(t.cpu(), tt)
-    # end-to-end agreement with the oracle's own scores (tolerance-band flips allowed, reported)
-    ref = orc.score_sp(model, ent, rel, tri[:, S], tri[:, P])
-    rr, tt = orc.ranks_and_ties(ref, ref[torch.arange(n), tri[:, O]])
-    dense = eng.score_1vsN(model, "sp_", ce, cr, ce, s, p, precision=prec)
-    r, t = eng.rank_dense(dense, dense[torch.arange(n, device="cuda"), o])
+    # end-to-end agreement with the oracle's own scores over more rows: two correct fp32 implementations with
+    # different summation orders flip a few comparisons inside the isclose band (0-2 of 512 rows even for a
+    # plain fp32 reordering), never by more than one place; bench.py reports the measured rate at the headline shape
+    n2 = 400
+    tri2 = orc.make_triples(E, R, n2, seed=9)
+    ct2 = tri2.cuda()
+    ref = orc.score_sp(model, ent, rel, tri2[:, S], tri2[:, P])
+    rr, tt = orc.ranks_and_ties(ref, ref[torch.arange(n2), tri2[:, O]])
+    dense = eng.score_1vsN(model, "sp_", ce, cr, ce, ct2[:, S].contiguous(), ct2[:, P].contiguous(), precision=prec)
+    r, t = eng.rank_dense(dense, dense[torch.arange(n2, device="cuda"), ct2[:, O]])
     final = orc.final_ranks(r.cpu(), t.cpu())
     agree = float((final == orc.final_ranks(rr, tt)).float().mean())
-    assert agree >= 0.98, agree
-    assert int((final - orc.final_ranks(rr, tt)).abs().max()) <= 2
+    assert agree >= 0.99, agree
+    assert int((final - orc.final_ranks(rr, tt)).abs().max()) <= 1
 
 
 @pytest.mark.parametrize("model", ["complex", "rotate", "transe", "rescal"])
