@@ -53,6 +53,8 @@ struct Tc4Params {
                                    // last tile (width multiple of 32) — no quantisation to whole 256-column tiles
   const float* q_scale;            // [nq]
   const float* t_scale;            // [m + 32], zero beyond m
+  int dbg;                         // B200KGE_DBG ablations (measurement only; results are garbage): 1 = epilogue releases
+                                   // the accumulator without reading it, 2 = no MMAs are issued, 4 = no TMA loads
   EpiParams epi;
 };
 
@@ -140,9 +142,13 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
               uint8_t* sp = smem + s * SLOT_BYTES;
               // completion of BOTH CTAs' boxes is counted on the leader's barrier
               const uint32_t bar = ptx::mapa(ptx::smem_u32(&full[s]), 0);
-              if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * SLOT_BYTES);
-              ptx::tma_load_2d_cluster_bar(sp, h ? &tmQl : &tmQh, bar, kc * TKH, q_row);
-              ptx::tma_load_2d_cluster_bar(sp + A_BYTES, h ? &tmTl : &tmTh, bar, kc * TKH, e_row);
+              if (prm.dbg & 4) {
+                if (rank == 0) ptx::mbar_arrive(&full[s]);
+              } else {
+                if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * SLOT_BYTES);
+                ptx::tma_load_2d_cluster_bar(sp, h ? &tmQl : &tmQh, bar, kc * TKH, q_row);
+                ptx::tma_load_2d_cluster_bar(sp + A_BYTES, h ? &tmTl : &tmTh, bar, kc * TKH, e_row);
+              }
             }
           }
         }
@@ -169,16 +175,20 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
             const uint32_t a_lo = ptx::smem_u32(smem + sl * SLOT_BYTES), b_lo = a_lo + A_BYTES;
             ptx::mbar_wait_cluster_bounded(&full[sh], ph);
             ptx::tc_fence_after();
+            if (!(prm.dbg & 2)) {
 #pragma unroll
-            for (int k = 0; k < TKH / 16; ++k)
-              ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
-                                  (kc > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < TKH / 16; ++k)
+                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
+                                    (kc > 0 || k > 0) ? 1u : 0u);
+            }
             ptx::mbar_wait_cluster_bounded(&full[sl], ph);
             ptx::tc_fence_after();
+            if (!(prm.dbg & 2)) {
 #pragma unroll
-            for (int k = 0; k < TKH / 16; ++k) {
-              ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_lo + k * 32), idesc, 1u);
-              ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_lo + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+              for (int k = 0; k < TKH / 16; ++k) {
+                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_lo + k * 32), idesc, 1u);
+                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_lo + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+              }
             }
             ptx::umma_commit_2cta(&empty[sh], 0b11);
             ptx::umma_commit_2cta(&empty[sl], 0b11);
@@ -212,6 +222,7 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
         ptx::tc_fence_after();
         const int64_t tile_lo = c_lo + (int64_t)t * TN;
         const int64_t tile_end = tile_lo + TN < c_hi ? tile_lo + TN : c_hi;     // valid columns only (<= m)
+        if (!(prm.dbg & 1))
         tc::epilogue_tile<EPI, 4, true>(P, st, aux,
                                         tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TN + half * 128),
                                         row0, tile_lo + half * 128, prm.nq, tile_end, my_stg, lane, qs, prm.t_scale,
@@ -294,6 +305,7 @@ int launch_pairwise_tc4(int epi_kind, const SplitSet& Q, const SplitSet& T, cons
   if ((rc = tc::make_map_f16(&mTl, T.lo, m, T.Kp, T.Kp, TM))) return rc;
   prm.epi = P;
   prm.epi.nchunks = 2 * prm.echunks;   // two epilogue warps (column halves) per row
+  { const char* d = getenv("B200KGE_DBG"); prm.dbg = d ? atoi(d) : 0; }
   const char* e = getenv("B200KGE_TC4_DIRECT");
   const bool direct = e && atoi(e) == 1;
   const int total = prm.q_tiles * prm.echunks;
