@@ -255,6 +255,15 @@ class _B200ModelMixin:
     # -- helpers
     def b200_fusable(self):
         """True if the tables can be read in place: plain LookupEmbedders, one entity table, dropout inactive."""
+        key = self.training
+        cached = self.__dict__.get("_b200_fusable_cache")
+        if cached is not None and cached[0] == key:          # embedder types / dropout rates are fixed after creation
+            return cached[1]
+        ok = self._b200_fusable_now()
+        self.__dict__["_b200_fusable_cache"] = (key, ok)
+        return ok
+
+    def _b200_fusable_now(self):
         es, ep, eo = self.get_s_embedder(), self.get_p_embedder(), self.get_o_embedder()
         for e in (es, ep, eo):
             if type(e) is not LookupEmbedder:
@@ -263,7 +272,6 @@ class _B200ModelMixin:
                 return False
         return es is eo
 
-    _b200_direct = b200_fusable
 
     def b200_csr_labels_ok(self, label_smoothing):
         return label_smoothing == 0.0 or self._b200_name in ("complex", "distmult", "simple", "cp", "rescal")
