@@ -56,6 +56,7 @@ __device__ __forceinline__ uint64_t make_desc3(uint32_t addr) {
 struct Tc3Params {
   int64_t nq, m;
   int nk;           // K chunks of 64 halfs (planes are zero padded to nk * 64)
+  int last_ksteps;  // 16-element MMA steps of the LAST chunk that hold real data (1..4): zero padding is not multiplied
   int q_tiles, e_tiles, echunks;
   int tn;           // entities per tile (multiple of 16, <= TN)
   int ksplit;       // > 1: split-K GEMM mode (EPI_STORE only): the reduction is cut into `ksplit` segments of `kseg`
@@ -165,18 +166,22 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
             const uint32_t par = (c / NPAIR) & 1;
             const uint32_t a_hi = ptx::smem_u32(smem + sh * SLOT_BYTES), b_hi = a_hi + A_BYTES;
             const uint32_t a_lo = ptx::smem_u32(smem + sl * SLOT_BYTES), b_lo = a_lo + A_BYTES;
+            const int ksteps = (kc == nk - 1) ? prm.last_ksteps : TKH / 16;
             ptx::mbar_wait_bounded(&full[sh], par);
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TKH / 16; ++k)
-              ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc,
-                             (kc > k0 || k > 0) ? 1u : 0u);
+              if (k < ksteps)
+                ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc,
+                               (kc > k0 || k > 0) ? 1u : 0u);
             ptx::mbar_wait_bounded(&full[sl], par);
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TKH / 16; ++k) {
-              ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_lo + k * 32), idesc, 1u);
-              ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_lo + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc, 1u);
+              if (k < ksteps) {
+                ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_lo + k * 32), idesc, 1u);
+                ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_lo + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc, 1u);
+              }
             }
             ptx::umma_commit(&free_[sh]);
             ptx::umma_commit(&free_[sl]);
@@ -294,6 +299,8 @@ int launch_pairwise_tc3(int epi_kind, const SplitSet& Q, const SplitSet& T, cons
   prm.nq = nq; prm.m = m; prm.nk = Q.Kp / tkh;
   plan3(nq, m, prm.q_tiles, prm.e_tiles, prm.echunks, prm.tn);
   prm.ksplit = 1; prm.kseg = prm.nk;
+  { const int rem = Q.K - (prm.nk - 1) * tkh;            // real reduction elements in the last chunk
+    prm.last_ksteps = rem <= 0 ? 4 : (rem + 15) / 16; if (prm.last_ksteps > 4) prm.last_ksteps = 4; }
   if (P.accumulate_out) {
     // split-K GEMM: segments of 8 chunks (512 reduction elements) bound the tensor core's accumulator error, which
     // grows with the reduction length (2.4e-5 of rms at K=512, 2.8e-4 at K=14541: profiles/r2_summary.md); segment

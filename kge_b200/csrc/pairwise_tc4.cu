@@ -48,6 +48,7 @@ constexpr int TMEM_COLS = 512;
 struct Tc4Params {
   int64_t nq, m;
   int nk;                          // K chunks of 64 halfs
+  int last_ksteps;                 // 16-element MMA steps of the last chunk that hold real data (1..4)
   int q_tiles, echunks;            // q tiles of 256 rows; each q tile's columns are cut into `echunks` ranges
   int cols_per;                    // columns per range (multiple of 32): a range = full 256-column tiles + ONE narrower
                                    // last tile (width multiple of 32) — no quantisation to whole 256-column tiles
@@ -175,19 +176,23 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
             const uint32_t a_lo = ptx::smem_u32(smem + sl * SLOT_BYTES), b_lo = a_lo + A_BYTES;
             ptx::mbar_wait_cluster_bounded(&full[sh], ph);
             ptx::tc_fence_after();
+            const int ksteps = (kc == nk - 1) ? prm.last_ksteps : TKH / 16;
             if (!(prm.dbg & 2)) {
 #pragma unroll
               for (int k = 0; k < TKH / 16; ++k)
-                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
-                                    (kc > 0 || k > 0) ? 1u : 0u);
+                if (k < ksteps)
+                  ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
+                                      (kc > 0 || k > 0) ? 1u : 0u);
             }
             ptx::mbar_wait_cluster_bounded(&full[sl], ph);
             ptx::tc_fence_after();
             if (!(prm.dbg & 2)) {
 #pragma unroll
               for (int k = 0; k < TKH / 16; ++k) {
-                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_lo + k * 32), idesc, 1u);
-                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_lo + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+                if (k < ksteps) {
+                  ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_lo + k * 32), idesc, 1u);
+                  ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_lo + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+                }
               }
             }
             ptx::umma_commit_2cta(&empty[sh], 0b11);
@@ -296,6 +301,8 @@ int launch_pairwise_tc4(int epi_kind, const SplitSet& Q, const SplitSet& T, cons
   Tc4Params prm;
   prm.nq = nq; prm.m = m; prm.nk = Q.Kp / TKH;
   plan4(nq, m, prm.q_tiles, prm.echunks, prm.cols_per);
+  { const int rem = Q.K - (prm.nk - 1) * TKH;
+    prm.last_ksteps = rem <= 0 ? 4 : (rem + 15) / 16; if (prm.last_ksteps > 4) prm.last_ksteps = 4; }
   prm.q_scale = Q.inv_scale; prm.t_scale = T.inv_scale;
   CUtensorMap mQh, mQl, mTh, mTl;
   int rc;
