@@ -166,19 +166,29 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
             const uint32_t par = (c / NPAIR) & 1;
             const uint32_t a_hi = ptx::smem_u32(smem + sh * SLOT_BYTES), b_hi = a_hi + A_BYTES;
             const uint32_t a_lo = ptx::smem_u32(smem + sl * SLOT_BYTES), b_lo = a_lo + A_BYTES;
-            const int ksteps = (kc == nk - 1) ? prm.last_ksteps : TKH / 16;
+            const bool tail = (kc == nk - 1) && prm.last_ksteps < TKH / 16;      // zero-padded steps are not multiplied
             ptx::mbar_wait_bounded(&full[sh], par);
             ptx::tc_fence_after();
+            if (!tail) {
 #pragma unroll
-            for (int k = 0; k < TKH / 16; ++k)
-              if (k < ksteps)
+              for (int k = 0; k < TKH / 16; ++k)
                 ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc,
                                (kc > k0 || k > 0) ? 1u : 0u);
+            } else {
+              for (int k = 0; k < prm.last_ksteps; ++k)
+                ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc,
+                               (kc > k0 || k > 0) ? 1u : 0u);
+            }
             ptx::mbar_wait_bounded(&full[sl], par);
             ptx::tc_fence_after();
+            if (!tail) {
 #pragma unroll
-            for (int k = 0; k < TKH / 16; ++k) {
-              if (k < ksteps) {
+              for (int k = 0; k < TKH / 16; ++k) {
+                ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_lo + k * 32), idesc, 1u);
+                ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_lo + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc, 1u);
+              }
+            } else {
+              for (int k = 0; k < prm.last_ksteps; ++k) {
                 ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_lo + k * 32), idesc, 1u);
                 ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_lo + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc, 1u);
               }

@@ -176,23 +176,30 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
             const uint32_t a_lo = ptx::smem_u32(smem + sl * SLOT_BYTES), b_lo = a_lo + A_BYTES;
             ptx::mbar_wait_cluster_bounded(&full[sh], ph);
             ptx::tc_fence_after();
-            const int ksteps = (kc == nk - 1) ? prm.last_ksteps : TKH / 16;
-            if (!(prm.dbg & 2)) {
+            const bool tail = (kc == nk - 1) && prm.last_ksteps < TKH / 16;      // zero-padded steps are not multiplied
+            if (prm.dbg & 2) {
+              ptx::mbar_wait_cluster_bounded(&full[sl], ph);
+            } else if (!tail) {
 #pragma unroll
               for (int k = 0; k < TKH / 16; ++k)
-                if (k < ksteps)
-                  ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
-                                      (kc > 0 || k > 0) ? 1u : 0u);
-            }
-            ptx::mbar_wait_cluster_bounded(&full[sl], ph);
-            ptx::tc_fence_after();
-            if (!(prm.dbg & 2)) {
+                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
+                                    (kc > 0 || k > 0) ? 1u : 0u);
+              ptx::mbar_wait_cluster_bounded(&full[sl], ph);
+              ptx::tc_fence_after();
 #pragma unroll
               for (int k = 0; k < TKH / 16; ++k) {
-                if (k < ksteps) {
-                  ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_lo + k * 32), idesc, 1u);
-                  ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_lo + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc, 1u);
-                }
+                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_lo + k * 32), idesc, 1u);
+                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_lo + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+              }
+            } else {
+              for (int k = 0; k < prm.last_ksteps; ++k)
+                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
+                                    (kc > 0 || k > 0) ? 1u : 0u);
+              ptx::mbar_wait_cluster_bounded(&full[sl], ph);
+              ptx::tc_fence_after();
+              for (int k = 0; k < prm.last_ksteps; ++k) {
+                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_lo + k * 32), idesc, 1u);
+                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_lo + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc, 1u);
               }
             }
             ptx::umma_commit_2cta(&empty[sh], 0b11);
