@@ -126,7 +126,10 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
 
   if (warp == 0) {
     // ================================ TMA producer =========================================
-    if (lane == 0) {
+    // the whole warp walks the loops (uniform control flow, operands in uniform registers), one elected lane issues —
+    // see pairwise_tc4.cu: inside `if (lane == 0)` ptxas wraps every UTMALDG / UTCHMMA in a register-broadcast loop
+    {
+      const bool issuer = ptx::elect_one();
       const uint32_t tx = (uint32_t)(A_BYTES + prm.tn * TKH * 2);
       uint32_t c = 0;      // K-chunk counter
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -140,9 +143,12 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
               const int s = 2 * (int)(c % NPAIR) + h;
               ptx::mbar_wait_bounded(&free_[s], par);
               uint8_t* sp = smem + s * SLOT_BYTES;
-              ptx::mbar_arrive_expect_tx(&full[s], tx);
-              ptx::tma_load_2d(sp, h ? &tmQl : &tmQh, &full[s], kc * TKH, qt * TM);
-              ptx::tma_load_2d(sp + A_BYTES, h ? &tmTl : &tmTh, &full[s], kc * TKH, et * prm.tn);
+              if (issuer) {
+                ptx::mbar_arrive_expect_tx(&full[s], tx);
+                ptx::tma_load_2d(sp, h ? &tmQl : &tmQh, &full[s], kc * TKH, qt * TM);
+                ptx::tma_load_2d(sp + A_BYTES, h ? &tmTl : &tmTh, &full[s], kc * TKH, et * prm.tn);
+              }
+              __syncwarp();
             }
           }
         }
@@ -150,7 +156,8 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ============================================
-    if (lane == 0) {
+    {
+      const bool issuer = ptx::elect_one();
       const uint32_t idesc = ptx::umma_idesc_f16(TM, prm.tn);
       uint32_t c = 0, it = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -169,34 +176,40 @@ pairwise_tc3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
             const bool tail = (kc == nk - 1) && prm.last_ksteps < TKH / 16;      // zero-padded steps are not multiplied
             ptx::mbar_wait_bounded(&full[sh], par);
             ptx::tc_fence_after();
-            if (!tail) {
+            if (issuer) {
+              if (!tail) {
 #pragma unroll
-              for (int k = 0; k < TKH / 16; ++k)
-                ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc,
-                               (kc > k0 || k > 0) ? 1u : 0u);
-            } else {
-              for (int k = 0; k < prm.last_ksteps; ++k)
-                ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc,
-                               (kc > k0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < TKH / 16; ++k)
+                  ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc,
+                                 (kc > k0 || k > 0) ? 1u : 0u);
+              } else {
+                for (int k = 0; k < prm.last_ksteps; ++k)
+                  ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc,
+                                 (kc > k0 || k > 0) ? 1u : 0u);
+              }
             }
             ptx::mbar_wait_bounded(&full[sl], par);
             ptx::tc_fence_after();
-            if (!tail) {
+            if (issuer) {
+              if (!tail) {
 #pragma unroll
-              for (int k = 0; k < TKH / 16; ++k) {
-                ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_lo + k * 32), idesc, 1u);
-                ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_lo + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc, 1u);
+                for (int k = 0; k < TKH / 16; ++k) {
+                  ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_lo + k * 32), idesc, 1u);
+                  ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_lo + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc, 1u);
+                }
+              } else {
+                for (int k = 0; k < prm.last_ksteps; ++k) {
+                  ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_lo + k * 32), idesc, 1u);
+                  ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_lo + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc, 1u);
+                }
               }
-            } else {
-              for (int k = 0; k < prm.last_ksteps; ++k) {
-                ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_hi + k * 32), make_desc3<TKH>(b_lo + k * 32), idesc, 1u);
-                ptx::umma_bf16(d_tmem, make_desc3<TKH>(a_lo + k * 32), make_desc3<TKH>(b_hi + k * 32), idesc, 1u);
-              }
+              ptx::umma_commit(&free_[sh]);
+              ptx::umma_commit(&free_[sl]);
             }
-            ptx::umma_commit(&free_[sh]);
-            ptx::umma_commit(&free_[sl]);
+            __syncwarp();
           }
-          ptx::umma_commit(&tfull[b]);             // accumulator complete
+          if (issuer) ptx::umma_commit(&tfull[b]);             // accumulator complete
+          __syncwarp();
         }
       }
     }

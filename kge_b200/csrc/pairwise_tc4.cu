@@ -122,7 +122,12 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
 
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ==============================
-    if (lane == 0) {
+    // The WHOLE warp walks the loops (uniform control flow, loop state in uniform registers) and one elected lane
+    // issues: with the loops inside `if (lane == 0)` every operand of UTMALDG / UTCHMMA / UTCBAR lives in per-thread
+    // registers and ptxas wraps each instruction in an ELECT / R2UR.BROADCAST x7 / BRA.U.ANY "waterfall" (~24 SASS
+    // instructions per MMA): the issuing thread, not the tensor pipe, then paces the kernel.
+    {
+      const bool issuer = ptx::elect_one();
       uint32_t c = 0;
       for (int w = cluster_id; w < total_work; w += nclusters) {
         int qt, ec, ntiles;
@@ -143,13 +148,16 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
               uint8_t* sp = smem + s * SLOT_BYTES;
               // completion of BOTH CTAs' boxes is counted on the leader's barrier
               const uint32_t bar = ptx::mapa(ptx::smem_u32(&full[s]), 0);
-              if (prm.dbg & 4) {
-                if (rank == 0) ptx::mbar_arrive(&full[s]);
-              } else {
-                if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * SLOT_BYTES);
-                ptx::tma_load_2d_cluster_bar(sp, h ? &tmQl : &tmQh, bar, kc * TKH, q_row);
-                ptx::tma_load_2d_cluster_bar(sp + A_BYTES, h ? &tmTl : &tmTh, bar, kc * TKH, e_row);
+              if (issuer) {
+                if (prm.dbg & 4) {
+                  if (rank == 0) ptx::mbar_arrive(&full[s]);
+                } else {
+                  if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * SLOT_BYTES);
+                  ptx::tma_load_2d_cluster_bar(sp, h ? &tmQl : &tmQh, bar, kc * TKH, q_row);
+                  ptx::tma_load_2d_cluster_bar(sp + A_BYTES, h ? &tmTl : &tmTh, bar, kc * TKH, e_row);
+                }
               }
+              __syncwarp();
             }
           }
         }
@@ -157,7 +165,8 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA only) ===========================
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
+      const bool issuer = ptx::elect_one();
       uint32_t c = 0, it = 0;
       for (int w = cluster_id; w < total_work; w += nclusters) {
         int qt, ec, ntiles;
@@ -180,32 +189,44 @@ pairwise_tc4_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
             if (prm.dbg & 2) {
               ptx::mbar_wait_cluster_bounded(&full[sl], ph);
             } else if (!tail) {
+              if (issuer) {
 #pragma unroll
-              for (int k = 0; k < TKH / 16; ++k)
-                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
-                                    (kc > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < TKH / 16; ++k)
+                  ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
+                                      (kc > 0 || k > 0) ? 1u : 0u);
+              }
               ptx::mbar_wait_cluster_bounded(&full[sl], ph);
               ptx::tc_fence_after();
+              if (issuer) {
 #pragma unroll
-              for (int k = 0; k < TKH / 16; ++k) {
-                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_lo + k * 32), idesc, 1u);
-                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_lo + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+                for (int k = 0; k < TKH / 16; ++k) {
+                  ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_lo + k * 32), idesc, 1u);
+                  ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_lo + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+                }
               }
             } else {
-              for (int k = 0; k < prm.last_ksteps; ++k)
-                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
-                                    (kc > 0 || k > 0) ? 1u : 0u);
+              if (issuer) {
+                for (int k = 0; k < prm.last_ksteps; ++k)
+                  ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc,
+                                      (kc > 0 || k > 0) ? 1u : 0u);
+              }
               ptx::mbar_wait_cluster_bounded(&full[sl], ph);
               ptx::tc_fence_after();
-              for (int k = 0; k < prm.last_ksteps; ++k) {
-                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_lo + k * 32), idesc, 1u);
-                ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_lo + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+              if (issuer) {
+                for (int k = 0; k < prm.last_ksteps; ++k) {
+                  ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_hi + k * 32), ptx::umma_desc_sw128(b_lo + k * 32), idesc, 1u);
+                  ptx::umma_bf16_2cta(d_tmem, ptx::umma_desc_sw128(a_lo + k * 32), ptx::umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+                }
               }
             }
-            ptx::umma_commit_2cta(&empty[sh], 0b11);
-            ptx::umma_commit_2cta(&empty[sl], 0b11);
+            if (issuer) {
+              ptx::umma_commit_2cta(&empty[sh], 0b11);
+              ptx::umma_commit_2cta(&empty[sl], 0b11);
+            }
+            __syncwarp();
           }
-          ptx::umma_commit_2cta(&tfull[b], 0b11);
+          if (issuer) ptx::umma_commit_2cta(&tfull[b], 0b11);
+          __syncwarp();
         }
       }
     }
