@@ -126,45 +126,6 @@ loss_finalize_kernel(FinalizeArgs A) {
   }
 }
 
-// Single-block finaliser for the fused training step (no per-row output, n <= 8192): one launch, no ticket round
-// trip.  Thread t owns rows t, t + 1024, ...; all chunk partials of a row are loaded before any is used (an in-order
-// warp otherwise pays an L2 round trip per chunk); rows, warps and the final 32 values are combined in a fixed order.
-template <int LOSS>
-__global__ void __launch_bounds__(1024)
-loss_finalize_small_kernel(FinalizeArgs A) {
-  __shared__ float wsum[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int F = (LOSS == B200KGE_LOSS_BCE) ? 2 : 5;
-  float acc = 0.f;
-  for (int64_t r = threadIdx.x; r < A.n; r += 1024) {
-    const float* __restrict__ p = A.part + r * A.nchunks * F;
-    if constexpr (LOSS == B200KGE_LOSS_BCE) {
-      float a = 0.f, b = 0.f;
-      for (int c0 = 0; c0 < A.nchunks; c0 += 16) {
-        float2 v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          v[j] = (c0 + j < A.nchunks) ? __ldcg(reinterpret_cast<const float2*>(p) + c0 + j) : make_float2(0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { a += v[j].x; b += v[j].y; }
-      }
-      acc += a - b;
-    } else {
-      acc += finalize_row<LOSS>(A.part, A.nchunks, r);
-    }
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (lane == 0) wsum[warp] = acc;
-  __syncthreads();
-  if (warp == 0) {
-    float t = wsum[lane];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-    if (lane == 0) A.loss_out[0] = (A.accumulate ? A.loss_out[0] : 0.f) + A.scale * t;
-  }
-}
-
 }  // namespace
 
 int loss_dense_nchunks(int64_t m) { return (int)((m + DN_CHUNK - 1) / DN_CHUNK); }
@@ -194,12 +155,6 @@ int launch_rank_dense(const float* scores, int64_t lds, int64_t n, int64_t m, co
 int launch_loss_finalize(int loss_kind, const float* part, int nchunks, int64_t n, float* loss_out,
                          float* row_loss_out, float scale, int accumulate, void* scratch,
                          int ticket_zeroed, cudaStream_t st) {
-  if (!row_loss_out && n <= 8192 && loss_kind == B200KGE_LOSS_BCE) {
-    FinalizeArgs S{part, nchunks, n, loss_out, nullptr, scale, accumulate, nullptr, nullptr};
-    loss_finalize_small_kernel<B200KGE_LOSS_BCE><<<1, 1024, 0, st>>>(S);
-    B2K_LAUNCH_CHECK("loss_finalize_small_kernel");
-    return 0;
-  }
   float* block_sums = reinterpret_cast<float*>(scratch);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(scratch) + 512);
   if (!ticket_zeroed) B2K_CUDA(cudaMemsetAsync(ticket, 0, 4, st));
