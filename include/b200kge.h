@@ -335,6 +335,17 @@ int b200kge_score_1vsN_backward(int model, int combine, const b200kge_rows_t* en
                                 int64_t ldg, float* d_ent, int64_t lde, float* d_rel, int64_t ldr, void* workspace,
                                 size_t workspace_bytes, b200kge_stream_t stream);
 
+/* Backward of b200kge_score_1vsN_loss_csr / batch_size (loss_value.backward() at kge/job/train_KvsAll.py:294) for the
+ * dot family: dense gradients d_ent [E, lde], d_rel [R, ldr] (OVERWRITTEN) of  sum_i loss(score row i, y_i) / batch_size
+ * with y = (1 - eps) * count + (eps > 0 ? 1/E : 0) from the CSR labels — recompute, G planes written with the label-free
+ * value everywhere and patched at the nnz listed entries, two split-K tensor-core GEMMs, unfold.  Workspace:
+ * b200kge_score_1vsN_backward_workspace_bytes. */
+int b200kge_score_1vsN_loss_csr_backward(int model, int combine, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+                                         const int64_t* q_idx, const int64_t* p_idx, int64_t n, const int64_t* csr_off,
+                                         const int64_t* csr_col, float label_smoothing, int loss_kind, float offset,
+                                         int64_t batch_size, float* d_ent, int64_t lde, float* d_rel, int64_t ldr,
+                                         void* workspace, size_t workspace_bytes, b200kge_stream_t stream);
+
 /* KvsAll loss with CSR multi-hot labels (kge/job/train_KvsAll.py:242-300 without the densified label matrix):
  * row i's labels are the columns csr_col[csr_off[i] .. csr_off[i+1]) (sorted; a repeated column counts as often
  * as it appears, like duplicate triples in the reference), optionally smoothed: y = (1 - eps) * count + 1/m.

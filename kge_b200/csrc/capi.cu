@@ -744,7 +744,8 @@ int gemm_planes(const SplitSet& A, const SplitSet& B, float* C, int64_t ldc, cud
 int backward_block(int model, const Rows& E, const Rows& R, const int64_t* triples, int64_t n, int dir,
                    const float* Q, int64_t ldq, const int64_t* lab, int col_off, int K, int loss_kind, float offset,
                    float* d_ent, int64_t lde, float* dQ, Arena ws, cudaStream_t st,
-                   const float* Gdense = nullptr, int64_t ldg = 0) {
+                   const float* Gdense = nullptr, int64_t ldg = 0, const int64_t* csr_off = nullptr,
+                   const int64_t* csr_col = nullptr, float csr_a = 1.f, float csr_b = 0.f, float inv_batch = 0.f) {
   const int64_t nq = dir < 0 ? 2 * n : n, m = E.rows;
   const int64_t ldz = round_up(m, 4), Ep = round_up(m, 64), Np = round_up(nq, 64);
   const int64_t ldE = round_up(m, 4), ldN = round_up(nq, 4);
@@ -780,6 +781,11 @@ int backward_block(int model, const Rows& E, const Rows& R, const int64_t* tripl
     row_stat = (float*)ws.take((size_t)nq * 2 * 4);
     if (!row_stat) { set_error("workspace too small for the row statistics"); return B200KGE_ERR_WORKSPACE; }
   }
+  if (csr_off) {
+    if ((rc = launch_grad_planes_csr(z, ldz, nq, m, csr_off, csr_col, csr_a, csr_b, row_stat,
+                                     loss_kind == B200KGE_LOSS_KL ? 0.f : offset, inv_batch, SG.hi, SG.lo, Ep, SGT.hi,
+                                     SGT.lo, Np, SG.inv_scale, SGT.inv_scale, st))) return rc;
+  } else
   if ((rc = launch_grad_planes(z, ldz, nq, m, lab, nullptr, 0, row_stat, loss_kind == B200KGE_LOSS_KL ? 0.f : offset,
                                1.0f / (float)n, SG.hi, SG.lo, Ep, SGT.hi, SGT.lo, Np, SG.inv_scale, SGT.inv_scale,
                                st))) return rc;
@@ -930,6 +936,42 @@ int b200kge_score_1vsN_backward(int model, int combine, const b200kge_rows_t* en
   if ((rc = launch_fold_queries(model, combine, A, Pr, n, 0, Q, ldq, st))) return rc;
   if ((rc = backward_block(model, E, R, tri, n, combine, Q, ldq, nullptr, f.col_off, f.K, B200KGE_LOSS_BCE, 0.f, d_ent, lde, dQ,
                            ws, st, grad_scores, ldg))) return rc;
+  return launch_unfold(model, E, R, tri, n, combine, dQ, ldq, d_ent, lde, d_rel, ldr, st);
+}
+
+int b200kge_score_1vsN_loss_csr_backward(int model, int combine, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+                                         const int64_t* q_idx, const int64_t* p_idx, int64_t n, const int64_t* csr_off,
+                                         const int64_t* csr_col, float label_smoothing, int loss_kind, float offset,
+                                         int64_t batch_size, float* d_ent, int64_t lde, float* d_rel, int64_t ldr,
+                                         void* workspace, size_t workspace_bytes, b200kge_stream_t stream) {
+  if (!ent || !rel || !q_idx || !p_idx || !csr_off || !d_ent || !d_rel) { set_error("null operand"); return B200KGE_ERR_INVALID; }
+  if (ent->idx || rel->idx) { set_error("ent/rel must be plain tables"); return B200KGE_ERR_INVALID; }
+  if (combine != B200KGE_SP_ && combine != B200KGE__PO) { set_error("cannot handle combine=%d", combine); return B200KGE_ERR_INVALID; }
+  int rc = validate_model(model, to_rows(ent), to_rows(rel)); if (rc) return rc;
+  if (model > B200KGE_RESCAL) { set_error("the tensor-core backward covers the dot family only (model %d)", model); return B200KGE_ERR_UNSUPPORTED; }
+  if (loss_kind != B200KGE_LOSS_BCE && loss_kind != B200KGE_LOSS_KL) { set_error("unknown loss kind %d", loss_kind); return B200KGE_ERR_INVALID; }
+  if (batch_size <= 0 || !(label_smoothing >= 0.f && label_smoothing < 1.f)) { set_error("bad batch_size / label_smoothing"); return B200KGE_ERR_INVALID; }
+  if (lde < ent->dim || ldr < rel->dim) { set_error("leading dimensions too small"); return B200KGE_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Rows E = to_rows(ent), R = to_rows(rel);
+  B2K_CUDA(cudaMemsetAsync(d_rel, 0, (size_t)R.rows * ldr * 4, st));
+  B2K_CUDA(cudaMemsetAsync(d_ent, 0, (size_t)E.rows * lde * 4, st));
+  if (n <= 0) return 0;
+  Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  Folded f = folded_problem(model, combine, E.dim, 1.0f);
+  const int64_t ldq = round_up(f.K, 32);
+  float* Q = (float*)ws.take((size_t)n * ldq * 4);
+  float* dQ = (float*)ws.take((size_t)n * ldq * 4);
+  int64_t* tri = (int64_t*)ws.take((size_t)n * 3 * 8);
+  if (!Q || !dQ || !tri) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+  pack_triples_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q_idx, p_idx, n, combine, tri);
+  B2K_LAUNCH_CHECK("pack_triples_kernel");
+  Rows A = E; A.idx = q_idx; A.rows = n;
+  Rows Pr = R; Pr.idx = p_idx; Pr.rows = n;
+  if ((rc = launch_fold_queries(model, combine, A, Pr, n, 0, Q, ldq, st))) return rc;
+  const float a = 1.0f - label_smoothing, b = label_smoothing > 0.f ? 1.0f / (float)E.rows : 0.f;
+  if ((rc = backward_block(model, E, R, tri, n, combine, Q, ldq, q_idx /* placeholder index vector */, f.col_off, f.K, loss_kind,
+                           offset, d_ent, lde, dQ, ws, st, nullptr, 0, csr_off, csr_col, a, b, 1.0f / (float)batch_size))) return rc;
   return launch_unfold(model, E, R, tri, n, combine, dQ, ldq, d_ent, lde, d_rel, ldr, st);
 }
 

@@ -96,7 +96,7 @@ row_lse_kernel(const float* __restrict__ z, int64_t ldz, int64_t E, const int64_
 __global__ void __launch_bounds__(256)
 grad_planes_kernel(const float* __restrict__ z, int64_t ldz, int64_t nq, int64_t E,
                    const int64_t* __restrict__ label_idx, const float* __restrict__ label_dense, int64_t ldl,
-                   const float* __restrict__ row_stat,
+                   const float* __restrict__ row_stat, float y_base,
                    float offset, float inv_n, __half* __restrict__ g_hi, __half* __restrict__ g_lo, int64_t Ep,
                    __half* __restrict__ gt_hi, __half* __restrict__ gt_lo, int64_t Np,
                    float* __restrict__ g_scale, float* __restrict__ gt_scale) {
@@ -110,7 +110,8 @@ grad_planes_kernel(const float* __restrict__ z, int64_t ldz, int64_t nq, int64_t
     float g = 0.f;
     if (i < nq && e < E) {
       const float x = __ldg(z + i * ldz + e) + offset;
-      const float y = label_idx ? ((label_idx[i] == e) ? 1.f : 0.f) : __ldg(label_dense + i * ldl + e);
+      const float y = label_idx ? ((label_idx[i] == e) ? 1.f : 0.f)
+                                : (label_dense ? __ldg(label_dense + i * ldl + e) : y_base);   // CSR labels: fixed up below
       if (row_stat) {   // labels are normalised by their row sum first (loss.py:209-213)
         const float ys = row_stat[2 * i + 1], yc = fmaxf(ys, 1e-12f);
         g = (ys / yc) * expf(x - row_stat[2 * i]) - y / yc;
@@ -131,6 +132,44 @@ grad_planes_kernel(const float* __restrict__ z, int64_t ldz, int64_t nq, int64_t
       split_store(gt_hi, gt_lo, e * Np + i, tile[tx][ty + 8 * k]);   // i < Np by construction of the grid
       if (blockIdx.y == 0 && tx == 0) gt_scale[e] = inv;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSR multi-hot labels (train_KvsAll.py:242-266): y_ij = a * count_ij + b.  The planes are first written with y = b
+// everywhere (grad_planes_kernel, y_base), then the nnz listed entries are recomputed with their labels and patched
+// into both layouts — no [n, E] label matrix.  KL needs the row label mass a * nnz_i + b * E in row_stat first.
+__global__ void __launch_bounds__(256)
+csr_row_mass_kernel(const int64_t* __restrict__ off, int64_t n, float a, float b, float E, float* __restrict__ row_stat) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) row_stat[2 * i + 1] = a * (float)(off[i + 1] - off[i]) + b * E;
+}
+
+__global__ void __launch_bounds__(256)
+csr_grad_fix_kernel(const float* __restrict__ z, int64_t ldz, int64_t n, const int64_t* __restrict__ off,
+                    const int64_t* __restrict__ col, const float* __restrict__ row_stat, float a, float b, float offset,
+                    __half* __restrict__ g_hi, __half* __restrict__ g_lo, int64_t Ep, __half* __restrict__ gt_hi,
+                    __half* __restrict__ gt_lo, int64_t Np) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // one warp per row
+  if (i >= n) return;
+  const int64_t t0 = off[i], t1 = off[i + 1];
+  for (int64_t t = t0 + lane; t < t1; t += 32) {
+    if (t > t0 && col[t] == col[t - 1]) continue;             // a run of equal columns is handled by its first entry
+    int64_t c = 1;
+    while (t + c < t1 && col[t + c] == col[t]) ++c;
+    const int64_t e = col[t];
+    const float y = a * (float)c + b;
+    const float x = z[i * ldz + e] + offset;
+    float g;
+    if (row_stat) {
+      const float ys = row_stat[2 * i + 1], yc = fmaxf(ys, 1e-12f);
+      g = (ys / yc) * expf(x - row_stat[2 * i]) - y / yc;
+    } else {
+      g = 1.0f / (1.0f + expf(-x)) - y;
+    }
+    split_store(g_hi, g_lo, i * Ep + e, g);
+    split_store(gt_hi, gt_lo, e * Np + i, g);
   }
 }
 
@@ -534,10 +573,32 @@ int launch_grad_planes(const float* z, int64_t ldz, int64_t nq, int64_t E, const
     B2K_LAUNCH_CHECK("row_lse_kernel");
   }
   dim3 grid((unsigned)(Ep / 32), (unsigned)(Np / 32));
-  grad_planes_kernel<<<grid, 256, 0, st>>>(z, ldz, nq, E, label_idx, label_dense, ldl, row_stat, offset, inv_n,
+  grad_planes_kernel<<<grid, 256, 0, st>>>(z, ldz, nq, E, label_idx, label_dense, ldl, row_stat, 0.f, offset, inv_n,
                                             (__half*)g_hi, (__half*)g_lo, Ep, (__half*)gt_hi, (__half*)gt_lo, Np,
                                             g_scale, gt_scale);
   B2K_LAUNCH_CHECK("grad_planes_kernel");
+  return 0;
+}
+
+int launch_grad_planes_csr(const float* z, int64_t ldz, int64_t nq, int64_t E, const int64_t* csr_off,
+                           const int64_t* csr_col, float a, float b, float* row_stat /* KL scratch [2nq] or null */,
+                           float offset, float inv_n, void* g_hi, void* g_lo, int64_t Ep, void* gt_hi, void* gt_lo,
+                           int64_t Np, float* g_scale, float* gt_scale, cudaStream_t st) {
+  if (nq == 0 || E == 0) return 0;
+  if (row_stat) {
+    row_lse_kernel<<<(unsigned)nq, 256, 0, st>>>(z, ldz, E, nullptr, nullptr, 0, row_stat);
+    B2K_LAUNCH_CHECK("row_lse_kernel");
+    csr_row_mass_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(csr_off, nq, a, b, (float)E, row_stat);
+    B2K_LAUNCH_CHECK("csr_row_mass_kernel");
+  }
+  dim3 grid((unsigned)(Ep / 32), (unsigned)(Np / 32));
+  grad_planes_kernel<<<grid, 256, 0, st>>>(z, ldz, nq, E, nullptr, nullptr, 0, row_stat, b, offset, inv_n, (__half*)g_hi,
+                                            (__half*)g_lo, Ep, (__half*)gt_hi, (__half*)gt_lo, Np, g_scale, gt_scale);
+  B2K_LAUNCH_CHECK("grad_planes_kernel");
+  csr_grad_fix_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(z, ldz, nq, csr_off, csr_col, row_stat, a, b, offset,
+                                                               (__half*)g_hi, (__half*)g_lo, Ep, (__half*)gt_hi,
+                                                               (__half*)gt_lo, Np);
+  B2K_LAUNCH_CHECK("csr_grad_fix_kernel");
   return 0;
 }
 

@@ -452,7 +452,11 @@ int launch_grad_planes(const float* z, int64_t ldz, int64_t nq, int64_t E, const
                        const float* label_dense, int64_t ldl, float* row_stat, float offset, float inv_n, void* g_hi, void* g_lo,
                        int64_t Ep, void* gt_hi, void* gt_lo, int64_t Np, float* g_scale, float* gt_scale,
                        cudaStream_t st);
-// CSR-label losses (csr_loss.cu), experimental.
+int launch_grad_planes_csr(const float* z, int64_t ldz, int64_t nq, int64_t E, const int64_t* csr_off,
+                           const int64_t* csr_col, float a, float b, float* row_stat, float offset, float inv_n,
+                           void* g_hi, void* g_lo, int64_t Ep, void* gt_hi, void* gt_lo, int64_t Np, float* g_scale,
+                           float* gt_scale, cudaStream_t st);
+// CSR-label losses (csr_loss.cu).
 int launch_csr_expand(const int64_t* off, const int64_t* col, int64_t n, int64_t nnz, int extra, const int64_t* q_idx,
                       const int64_t* p_idx, int64_t* qsel, int64_t* psel, int64_t* esel, cudaStream_t st);
 int launch_csr_rows(int loss_kind, const int64_t* off, const int64_t* col, const float* zpos, int64_t n, int64_t nnz,

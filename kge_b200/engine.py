@@ -515,6 +515,27 @@ def score_1vsN_backward(model: str, combine: str, ent, rel, q, p, grad_scores):
     return d_ent, d_rel
 
 
+def score_1vsN_loss_csr_backward(model: str, combine: str, ent, rel, q, p, csr_offsets, csr_cols, loss: str = "kl",
+                                 offset: float = 0.0, label_smoothing: float = 0.0, batch_size: Optional[int] = None):
+    """(d_ent, d_rel) of score_1vsN_loss_csr(...) / batch_size over the whole entity table (dot family)."""
+    _require_cuda(ent, rel, csr_offsets, csr_cols)
+    lib, k = _lib.load(), _Keep()
+    re_, rr = k.rows(ent), k.rows(rel)
+    qi, pi, offs, cols = _i64(q), _i64(p), _i64(csr_offsets), _i64(csr_cols)
+    n = qi.numel()
+    dev = ent.device
+    d_ent = torch.empty_like(_f32(ent))
+    d_rel = torch.empty_like(_f32(rel))
+    ws = torch.empty(lib.b200kge_score_1vsN_backward_workspace_bytes(MODELS[model], n, ent.shape[0], ent.shape[1]),
+                     dtype=torch.uint8, device=dev)
+    _lib.check(lib.b200kge_score_1vsN_loss_csr_backward(
+        MODELS[model], SP_ if combine == "sp_" else _PO, C.byref(re_), C.byref(rr), qi.data_ptr(), pi.data_ptr(), n,
+        offs.data_ptr(), cols.data_ptr() if cols.numel() else None, label_smoothing, LOSS[loss], offset,
+        batch_size or n, d_ent.data_ptr(), d_ent.stride(0), d_rel.data_ptr(), d_rel.stride(0), ws.data_ptr(), ws.numel(),
+        _stream(dev)))
+    return d_ent, d_rel
+
+
 def lookup_penalty(weight: torch.Tensor, regularize: str = "lp", regularize_weight: float = 0.0, p: float = 2.0,
                      weighted: bool = False, indexes: Optional[torch.Tensor] = None, space: str = "euclidean"):
     """LookupEmbedder.penalty (lookup_embedder.py:123-177) as a 0-d tensor."""

@@ -210,6 +210,27 @@ def _install_embedder_kernels(emb):
     emb._b200_patched = True
 
 
+class _KvsAllLossFn(torch.autograd.Function):
+    """KvsAll loss of one query type with CSR labels / batch_size: forward = fused score + loss with the CSR consumed in
+    the epilogue; backward = the gradient kernels (b200kge_score_1vsN_loss_csr_backward)."""
+
+    @staticmethod
+    def forward(ctx, ent_w, rel_w, model, combine, a, p, offs, cols, loss, offset, smoothing, batch_size):
+        ctx.args = (model, combine, loss, offset, smoothing, batch_size)
+        ctx.save_for_backward(ent_w, rel_w, a, p, offs, cols)
+        ln, prec = model._b200_args()
+        return engine.score_1vsN_loss_csr(model._b200_name, combine, ent_w.detach(), rel_w.detach(), ent_w.detach(), offs,
+                                          cols, a, p, loss, offset, smoothing, ln, prec) / batch_size
+
+    @staticmethod
+    def backward(ctx, g):
+        ent_w, rel_w, a, p, offs, cols = ctx.saved_tensors
+        model, combine, loss, offset, smoothing, batch_size = ctx.args
+        d_ent, d_rel = engine.score_1vsN_loss_csr_backward(model._b200_name, combine, ent_w.detach(), rel_w.detach(), a, p,
+                                                           offs, cols, loss, offset, smoothing, batch_size)
+        return (d_ent * g, d_rel * g) + (None,) * 10
+
+
 class _NsSlotLossFn(torch.autograd.Function):
     """One slot of a negative-sampling batch with BCE: forward = fused gather+score [n, 1+K] and the dense-loss kernel;
     backward = the fused NS gradient kernel (b200kge_ns_backward: per-row fold, per-column recompute, scatter)."""
@@ -404,6 +425,15 @@ class _B200ModelMixin:
         ln, prec = self._b200_args()
         return engine.score_1vsN_loss_csr(self._b200_name, combine, ent, rel, ent, csr_offsets, csr_cols, a, p,
                                           loss, offset, label_smoothing, ln, prec)
+
+    def b200_kvsall_native_backward_ok(self):
+        return self.b200_backward == "native" and self._b200_name in ("complex", "distmult", "simple", "cp", "rescal")
+
+    def loss_kvsall_train(self, combine, a, p, csr_offsets, csr_cols, loss, offset, label_smoothing, batch_size):
+        """loss_kvsall / batch_size as a differentiable scalar (train_KvsAll.py:286-294)."""
+        ent_w, rel_w = self._b200_weights()
+        return _KvsAllLossFn.apply(ent_w, rel_w, self, combine, a.long().contiguous(), p.long().contiguous(),
+                                   csr_offsets, csr_cols, loss, float(offset), float(label_smoothing), int(batch_size))
 
     def score_negatives(self, triples, negatives, slot):
         """[n, 1+K]: the positive triple's score in column 0, its K corrupted versions after it

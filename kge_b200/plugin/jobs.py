@@ -96,8 +96,8 @@ class B200TrainingJobKvsAll(TrainingJobKvsAll):
     def _process_subbatch(self, batch_index, batch, subbatch_slice, result):
         model, kind = _fused_model(self.model), _fused_loss_kind(self.loss)
         qtypes = [q for q in self.query_types]
-        if (model is None or kind is None or not self.is_forward_only or "s_o" in qtypes
-                or not model.b200_csr_labels_ok(self.label_smoothing)):
+        if (model is None or kind is None or "s_o" in qtypes or not model.b200_csr_labels_ok(self.label_smoothing)
+                or (not self.is_forward_only and not model.b200_kvsall_native_backward_ok())):
             return super()._process_subbatch(batch_index, batch, subbatch_slice, result)
         batch_size = result.size
 
@@ -137,10 +137,18 @@ class B200TrainingJobKvsAll(TrainingJobKvsAll):
                 combine, ent_idx, rel_idx = "sp_", queries[examples, 0], queries[examples, 1]
             else:
                 combine, ent_idx, rel_idx = "_po", queries[examples, 1], queries[examples, 0]
-            loss_value = model.loss_kvsall(combine, ent_idx, rel_idx, offsets, ccols, kind[0], kind[1],
-                                           self.label_smoothing) / batch_size
+            if self.is_forward_only:
+                loss_value = model.loss_kvsall(combine, ent_idx, rel_idx, offsets, ccols, kind[0], kind[1],
+                                               self.label_smoothing) / batch_size
+            else:
+                loss_value = model.loss_kvsall_train(combine, ent_idx, rel_idx, offsets, ccols, kind[0], kind[1],
+                                                     self.label_smoothing, batch_size)
             result.avg_loss += loss_value.item()
             result.forward_time += time.time()
+            result.backward_time -= time.time()
+            if not self.is_forward_only:
+                loss_value.backward()
+            result.backward_time += time.time()
 
 
 class B200TrainingJobNegativeSampling(TrainingJobNegativeSampling):

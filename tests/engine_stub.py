@@ -77,6 +77,14 @@ def score_1vsN_backward(model, combine, ent, rel, q, p, grad_scores):
         return torch.autograd.grad(x, (e, r), grad_scores)
 
 
+def score_1vsN_loss_csr_backward(model, combine, ent, rel, q, p, csr_offsets, csr_cols, loss="kl", offset=0.0,
+                                 label_smoothing=0.0, batch_size=None):
+    e, r = ent.detach().clone().requires_grad_(True), rel.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        val = score_1vsN_loss_csr(model, combine, e, r, e, csr_offsets, csr_cols, q, p, loss, offset, label_smoothing)
+        return torch.autograd.grad(val / (batch_size or q.numel()), (e, r))
+
+
 class Step1vsAll:
     """Stand-in of engine.Step1vsAll (prepared fused step)."""
 
@@ -108,7 +116,7 @@ def installed():
     from kge_b200 import engine
 
     names = ["score_spo", "score_1vsN", "score_sp_po", "train_1vsall_forward", "score_1vsN_loss",
-             "score_1vsN_loss_csr", "ns_score", "loss_dense", "train_1vsall_backward", "score_1vsN_backward", "launch_count"]
+             "score_1vsN_loss_csr", "ns_score", "loss_dense", "train_1vsall_backward", "score_1vsN_backward", "score_1vsN_loss_csr_backward", "launch_count"]
     saved = {k: getattr(engine, k) for k in names}
     g = globals()
 

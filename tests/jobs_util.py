@@ -21,7 +21,7 @@ def synthetic_splits(E, R, n_train, n_valid=40, n_test=40, seed=1):
 
 
 def make_job(model, E, R, D, splits, device="cpu", train_type="1vsAll", loss="bce", batch_size=16, extra=None,
-             job_class=None, forward_only=True):
+             job_class=None, forward_only=True, imports=()):
     """A reference TrainingJob (with its validation EntityRankingJob) over an in-memory dataset."""
     hostenv.import_kge()
     from kge import Config, Dataset
@@ -33,6 +33,8 @@ def make_job(model, E, R, D, splits, device="cpu", train_type="1vsAll", loss="bc
     config.set("modules", MODULES)
     config.set("model", model)
     config._import(model)
+    for extra_model in imports:           # e.g. the base model of reciprocal_relations_model
+        config._import(extra_model)
     config.set("dataset.name", "synthetic")
     config.set("dataset.num_entities", E)
     config.set("dataset.num_relations", R)

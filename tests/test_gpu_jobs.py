@@ -238,3 +238,63 @@ def test_negative_sampling_training_native_backward(model, splits):
     assert losses["ref"][1] < losses["ref"][0]
     assert losses["native"][0] == pytest.approx(losses["ref"][0], rel=REL)
     assert losses["native"][1] == pytest.approx(losses["ref"][1], rel=1e-3)
+
+
+@pytest.mark.parametrize("base", ["distmult", "complex"])
+def test_reciprocal_relations_model_through_plugin(base, splits):
+    """The reference's own ReciprocalRelationsModel wrapper (reciprocal_relations_model.py:85-124: score_po as sp_ with a
+    relation offset; it calls the scorer's score_emb directly) over a b200 base model: two 1vsAll training epochs and
+    the entity-ranking job agree with the same wrapper over the reference base model."""
+    def make(bm, dev):
+        return ju.make_job("reciprocal_relations_model", E, R, D, splits, device=dev, train_type="1vsAll", loss="kl",
+                           batch_size=64, forward_only=False, imports=(bm,),
+                           extra={"reciprocal_relations_model.base_model.type": bm})
+    torch.manual_seed(0)
+    init = make(base, "cpu")
+    out = {}
+    for tag, dev, bm in (("ref", "cpu", base), ("plugin", "cuda", "b200_" + base)):
+        job = make(bm, dev)
+        with torch.no_grad():
+            for a, b in zip(init.model.parameters(), job.model.parameters()):
+                b.copy_(a.to(b.device))
+        if tag == "plugin":
+            assert type(job.model._base_model.get_scorer()).__name__.startswith("B200")
+        losses = []
+        for ep in range(2):
+            job.epoch += 1
+            if job.loader is None:
+                job._prepare()
+            ju.seed_all(20 + ep)
+            losses.append(job.run_epoch()["avg_loss"])
+        out[tag] = (losses, ju.run_valid(job))
+    assert out["plugin"][0][0] == pytest.approx(out["ref"][0][0], rel=REL)
+    assert out["plugin"][0][1] == pytest.approx(out["ref"][0][1], rel=1e-3)
+    for k in ("mean_reciprocal_rank_filtered", "hits_at_10_filtered", "mean_rank"):
+        assert out["plugin"][1][k] == pytest.approx(out["ref"][1][k], rel=1e-2, abs=1e-2)
+
+
+@pytest.mark.parametrize("model", ["complex", "rescal"])
+@pytest.mark.parametrize("loss,eps", [("kl", 0.0), ("kl", 0.2), ("bce", 0.1)])
+def test_kvsall_training_native_backward(model, loss, eps, splits):
+    """B200TrainingJobKvsAll in TRAINING mode: CSR labels in the forward epilogue and in the gradient planes
+    (b200kge_score_1vsN_loss_csr_backward); two epochs (forward, backward, Adagrad) track the reference job."""
+    extra = {"KvsAll.label_smoothing": eps}
+    torch.manual_seed(0)
+    init = ju.make_job(model, E, R, D, splits, device="cpu", train_type="KvsAll", loss=loss, batch_size=32, extra=extra)
+    losses = {}
+    for tag, dev in (("ref", "cpu"), ("native", "cuda")):
+        name = model if tag == "ref" else "b200_" + model
+        kw = {"job_class": "B200TrainingJobKvsAll"} if tag == "native" else {}
+        job = ju.make_job(name, E, R, D, splits, device=dev, train_type="KvsAll", loss=loss, batch_size=32,
+                          forward_only=False, extra=extra, **kw)
+        ju.copy_tables(init, job)
+        out = []
+        for ep in range(2):
+            job.epoch += 1
+            if job.loader is None:
+                job._prepare()
+            ju.seed_all(10 + ep)
+            out.append(job.run_epoch()["avg_loss"])
+        losses[tag] = out
+    assert losses["native"][0] == pytest.approx(losses["ref"][0], rel=REL)
+    assert losses["native"][1] == pytest.approx(losses["ref"][1], rel=1e-3)

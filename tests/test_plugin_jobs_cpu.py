@@ -118,3 +118,25 @@ def test_job_plugins_fall_through_for_reference_models(splits):
     ju.copy_tables(ref, plug)
     assert type(plug).__name__ == "B200TrainingJob1vsAll"
     assert ju.run_forward_epoch(plug)["avg_loss"] == pytest.approx(ju.run_forward_epoch(ref)["avg_loss"], rel=1e-7)
+
+
+def test_kvsall_training_through_the_job_plugin(splits, stub):
+    """B200TrainingJobKvsAll in training mode (autograd node per query type over the CSR labels) tracks the reference."""
+    out = {}
+    torch.manual_seed(0)
+    init = ju.make_job("distmult", E, R, D, splits, train_type="KvsAll", loss="kl", batch_size=16,
+                       extra={"KvsAll.label_smoothing": 0.1})
+    for tag in ("ref", "plugin"):
+        kw = {"job_class": "B200TrainingJobKvsAll"} if tag == "plugin" else {}
+        job = ju.make_job("distmult" if tag == "ref" else "b200_distmult", E, R, D, splits, train_type="KvsAll", loss="kl",
+                          batch_size=16, forward_only=False, extra={"KvsAll.label_smoothing": 0.1}, **kw)
+        ju.copy_tables(init, job)
+        losses = []
+        for ep in range(2):
+            job.epoch += 1
+            if job.loader is None:
+                job._prepare()
+            ju.seed_all(10 + ep)
+            losses.append(job.run_epoch()["avg_loss"])
+        out[tag] = losses
+    assert out["plugin"] == pytest.approx(out["ref"], rel=1e-5)
