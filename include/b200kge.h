@@ -313,13 +313,14 @@ int b200kge_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, in
                       int64_t K, float* C, int64_t ldc, void* workspace, size_t workspace_bytes,
                       b200kge_stream_t stream);
 
-/* Backward of b200kge_train_1vsall_forward (loss.backward() at kge/job/train_1vsAll.py:70,81) for the
- * dot family with BCE or KL: dense gradients of the entity table d_ent [E, lde] and of the relation table d_rel
+/* Backward of b200kge_train_1vsall_forward (loss.backward() at kge/job/train_1vsAll.py:70,81) with BCE or KL, for the
+ * dot family (tensor-core GEMMs, below) and for TransE (l_norm 1, 2) / RotatE (l_norm 1) (CUDA-core row-gradient passes,
+ * grad_distance.cu: dQ_i = sum_j G_ij s'(Q_i - T_j), dT_j = sum_i G_ij s'(T_j - Q_i)): dense gradients of the entity table d_ent [E, lde] and of the relation table d_rel
  * [R, ldr] of  (loss(score_sp, o) + loss(score_po, s)) / n.  Both buffers are overwritten (the reference
  * accumulates into .grad; add them there).  Recompute-based: scores, G = n dL/dz (sigmoid(z+off) - y | softmax(z) - y), two tensor-core
  * GEMMs (dT = G^T Q, dQ = G T), row-wise unfold of dQ through the relation fold (grad.cu). */
 size_t b200kge_train_1vsall_backward_workspace_bytes(int model, int64_t n, int64_t E, int32_t D);
-int b200kge_train_1vsall_backward(int model, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+int b200kge_train_1vsall_backward(int model, float l_norm, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
                                     const int64_t* triples, int64_t n, int loss_kind, float offset,
                                     float* d_ent, int64_t lde, float* d_rel, int64_t ldr,
                                     void* workspace, size_t workspace_bytes, b200kge_stream_t stream);

@@ -83,7 +83,7 @@ SIGNATURES = {
     "b200kge_gemm_nt": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200kge_train_1vsall_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int64, C.c_int32]),
-    "b200kge_train_1vsall_backward": (C.c_int, [C.c_int, _RP, _RP, C.c_void_p, C.c_int64, C.c_int, C.c_float,
+    "b200kge_train_1vsall_backward": (C.c_int, [C.c_int, C.c_float, _RP, _RP, C.c_void_p, C.c_int64, C.c_int, C.c_float,
                                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                                   C.c_size_t, C.c_void_p]),
     "b200kge_score_1vsN_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int64, C.c_int32]),

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200kge.so")
-SOURCES = ["capi.cu", "fold.cu", "pairwise_simt.cu", "pairwise_tc.cu", "presplit.cu", "pairwise_tc3.cu", "pairwise_tc4.cu", "rowwise.cu", "epilogue_dense.cu", "hostindex.cu", "grad.cu", "csr_loss.cu"]
+SOURCES = ["capi.cu", "fold.cu", "pairwise_simt.cu", "pairwise_tc.cu", "presplit.cu", "pairwise_tc3.cu", "pairwise_tc4.cu", "rowwise.cu", "epilogue_dense.cu", "hostindex.cu", "grad.cu", "grad_distance.cu", "csr_loss.cu"]
 HEADERS = ["common.cuh", "fold.cuh", "ptx.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "b200kge.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -844,17 +844,20 @@ int b200kge_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, in
 size_t b200kge_train_1vsall_backward_workspace_bytes(int model, int64_t n, int64_t E, int32_t D) {
   const int64_t K = (model == B200KGE_CP) ? D / 2 : D;
   const int64_t nq = 2 * n, ldq = round_up(K, 32);
+  if (model == B200KGE_TRANSE || model == B200KGE_ROTATE)   // Q, dQ, labels, z, G, G^T, z^T, row stats + scorer workspace
+    return 2 * (size_t)nq * ldq * 4 + (size_t)nq * 8 + 2 * (size_t)nq * round_up(E, 4) * 4 + 2 * (size_t)E * round_up(nq, 4) * 4 +
+           (size_t)nq * 8 + 16 * 256 + b200kge_workspace_bytes(model, n, E, D, 0);
   return (size_t)nq * ldq * 4 + (size_t)n * 5 * 8 + 4096 + backward_block_bytes(nq, E, K, ldq);
 }
 
-int b200kge_train_1vsall_backward(int model, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+int b200kge_train_1vsall_backward(int model, float l_norm, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
                                     const int64_t* triples, int64_t n, int loss_kind, float offset, float* d_ent,
                                     int64_t lde, float* d_rel, int64_t ldr, void* workspace, size_t workspace_bytes,
                                     b200kge_stream_t stream) {
   if (!ent || !rel || !triples || !d_ent || !d_rel) { set_error("null operand"); return B200KGE_ERR_INVALID; }
   if (ent->idx || rel->idx) { set_error("ent/rel must be plain tables"); return B200KGE_ERR_INVALID; }
   int rc = validate_model(model, to_rows(ent), to_rows(rel)); if (rc) return rc;
-  if (model > B200KGE_RESCAL) { set_error("the analytic backward covers the dot family only (model %d)", model); return B200KGE_ERR_UNSUPPORTED; }
+  if ((rc = validate_norm(model, l_norm))) return rc;
   if (loss_kind != B200KGE_LOSS_BCE && loss_kind != B200KGE_LOSS_KL) { set_error("unknown loss kind %d", loss_kind); return B200KGE_ERR_INVALID; }
   if (lde < ent->dim || ldr < rel->dim) { set_error("gradient leading dimensions are smaller than the table widths"); return B200KGE_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -862,6 +865,45 @@ int b200kge_train_1vsall_backward(int model, const b200kge_rows_t* ent, const b2
   B2K_CUDA(cudaMemsetAsync(d_rel, 0, (size_t)R.rows * ldr * 4, st));
   if (n <= 0) { B2K_CUDA(cudaMemsetAsync(d_ent, 0, (size_t)E.rows * lde * 4, st)); return 0; }
   Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
+  if (model == B200KGE_TRANSE || model == B200KGE_ROTATE) {
+    // distance family (grad_distance.cu): scores by the CUDA-core scorer, dense G, two row-gradient passes, unfold
+    Folded f = folded_problem(model, B200KGE_SP_, E.dim, l_norm);
+    if (f.pair_op != PAIR_L1 && f.pair_op != PAIR_L2 && f.pair_op != PAIR_CMOD_L1) {
+      set_error("the distance-family backward covers l_norm 1 and 2 (TransE) and 1 (RotatE)");
+      return B200KGE_ERR_UNSUPPORTED;
+    }
+    const int64_t nq = 2 * n, m = E.rows, ldq = round_up(f.K, 32), ldz = round_up(m, 4), ldN = round_up(nq, 4);
+    float* Q = (float*)ws.take((size_t)nq * ldq * 4);
+    float* dQ = (float*)ws.take((size_t)nq * ldq * 4);
+    int64_t* lab = (int64_t*)ws.take((size_t)nq * 8);
+    float* z = (float*)ws.take((size_t)nq * ldz * 4);
+    float* G = (float*)ws.take((size_t)nq * ldz * 4);
+    float* Gt = (float*)ws.take((size_t)m * ldN * 4);
+    float* Zt = f.pair_op == PAIR_L2 ? (float*)ws.take((size_t)m * ldN * 4) : nullptr;
+    float* row_stat = loss_kind == B200KGE_LOSS_KL ? (float*)ws.take((size_t)nq * 2 * 4) : nullptr;
+    if (!Q || !dQ || !lab || !z || !G || !Gt || (f.pair_op == PAIR_L2 && !Zt) || (loss_kind == B200KGE_LOSS_KL && !row_stat)) {
+      set_error("workspace too small");
+      return B200KGE_ERR_WORKSPACE;
+    }
+    if ((rc = launch_prep_1vsall(model, E, R, triples, n, Q, ldq, lab, nullptr, st))) return rc;
+    {
+      Rows S = E; S.idx = lab; S.rows = n;      // placeholders: operands are pre-folded
+      Rows Pr = R; Pr.idx = lab; Pr.rows = n;
+      EpiParams P = empty_epi();
+      P.out = z; P.ldo = ldz;
+      Block B{model, B200KGE_SP_, &S, &S, &Pr, &E, n};
+      B.Qpre = Q;
+      if ((rc = run_block(B, l_norm, B200KGE_PREC_AUTO, EPI_STORE, P, ws, st, nullptr))) return rc;
+    }
+    if (row_stat && (rc = launch_row_lse(z, ldz, nq, m, lab, row_stat, st))) return rc;
+    if ((rc = launch_grad_dense(z, ldz, nq, m, lab, row_stat, loss_kind == B200KGE_LOSS_KL ? 0.f : offset, 1.0f / (float)n,
+                                G, ldz, st))) return rc;
+    if ((rc = launch_transpose(G, ldz, nq, m, Gt, ldN, st))) return rc;
+    if (Zt && (rc = launch_transpose(z, ldz, nq, m, Zt, ldN, st))) return rc;
+    if ((rc = launch_pair_rowgrad(f.pair_op, Q, ldq, nq, E.base, E.ld, m, f.K, G, ldz, z, ldz, dQ, ldq, st))) return rc;
+    if ((rc = launch_pair_rowgrad(f.pair_op, E.base, E.ld, m, Q, ldq, nq, f.K, Gt, ldN, Zt, ldN, d_ent, lde, st))) return rc;
+    return launch_unfold_distance(model, E, R, triples, n, -1, dQ, ldq, d_ent, lde, d_rel, ldr, st);
+  }
   Folded f0 = folded_problem(model, B200KGE_SP_, E.dim, 1.0f), f1 = folded_problem(model, B200KGE__PO, E.dim, 1.0f);
   const int64_t ldq = round_up(f0.K, 32);
   if (f0.col_off == f1.col_off) {

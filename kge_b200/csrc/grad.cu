@@ -534,6 +534,28 @@ int launch_ns_backward(int model, float l_norm, const Rows& ent, const Rows& rel
   return launch_unfold(model, ent, rel, triples, n, dir, dQ, ldq, d_ent, lde, d_rel, ldr, st);
 }
 
+int launch_unfold_distance(int model, const Rows& ent, const Rows& rel, const int64_t* triples, int64_t n, int dir,
+                           const float* dQ, int64_t ldq, float* d_ent, int64_t lde, float* d_rel, int64_t ldr,
+                           cudaStream_t st) {
+  if (n == 0) return 0;
+  dim3 g2((unsigned)(dir < 0 ? 2 * n : n)), b2(128);
+  if (model == B200KGE_TRANSE)
+    unfold_distance_kernel<B200KGE_TRANSE><<<g2, b2, 0, st>>>(ent, rel, triples, n, dir, dQ, ldq, d_ent, lde, d_rel, ldr);
+  else if (model == B200KGE_ROTATE)
+    unfold_distance_kernel<B200KGE_ROTATE><<<g2, b2, 0, st>>>(ent, rel, triples, n, dir, dQ, ldq, d_ent, lde, d_rel, ldr);
+  else { set_error("not a distance-family model (%d)", model); return B200KGE_ERR_INVALID; }
+  B2K_LAUNCH_CHECK("unfold_distance_kernel");
+  return 0;
+}
+
+int launch_row_lse(const float* z, int64_t ldz, int64_t nq, int64_t E, const int64_t* label_idx, float* row_stat,
+                   cudaStream_t st) {
+  if (nq == 0) return 0;
+  row_lse_kernel<<<(unsigned)nq, 256, 0, st>>>(z, ldz, E, label_idx, nullptr, 0, row_stat);
+  B2K_LAUNCH_CHECK("row_lse_kernel");
+  return 0;
+}
+
 int launch_penalty(const Rows& tab, const float* counts, float p, int complex_abs, float scale, float* scratch,
                    size_t scratch_floats, float* out, cudaStream_t st) {
   const int64_t blocks = (tab.rows + PEN_ROWS - 1) / PEN_ROWS;

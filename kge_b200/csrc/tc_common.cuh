@@ -452,6 +452,16 @@ int launch_grad_planes(const float* z, int64_t ldz, int64_t nq, int64_t E, const
                        const float* label_dense, int64_t ldl, float* row_stat, float offset, float inv_n, void* g_hi, void* g_lo,
                        int64_t Ep, void* gt_hi, void* gt_lo, int64_t Np, float* g_scale, float* gt_scale,
                        cudaStream_t st);
+// distance-family backward (grad_distance.cu, grad.cu)
+int launch_pair_rowgrad(int pair_op, const float* A, int64_t lda, int64_t ra, const float* B, int64_t ldb, int64_t rb, int K,
+                        const float* W, int64_t ldw, const float* Z, int64_t ldz, float* dA, int64_t ldda, cudaStream_t st);
+int launch_grad_dense(const float* z, int64_t ldz, int64_t nq, int64_t E, const int64_t* label_idx, const float* row_stat,
+                      float offset, float inv_n, float* G, int64_t ldg, cudaStream_t st);
+int launch_row_lse(const float* z, int64_t ldz, int64_t nq, int64_t E, const int64_t* label_idx, float* row_stat,
+                   cudaStream_t st);
+int launch_unfold_distance(int model, const Rows& ent, const Rows& rel, const int64_t* triples, int64_t n, int dir,
+                           const float* dQ, int64_t ldq, float* d_ent, int64_t lde, float* d_rel, int64_t ldr,
+                           cudaStream_t st);
 int launch_grad_planes_csr(const float* z, int64_t ldz, int64_t nq, int64_t E, const int64_t* csr_off,
                            const int64_t* csr_col, float a, float b, float* row_stat, float offset, float inv_n,
                            void* g_hi, void* g_lo, int64_t Ep, void* gt_hi, void* gt_lo, int64_t Np, float* g_scale,

@@ -477,8 +477,8 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def train_1vsall_backward(model: str, ent, rel, triples, loss: str = "bce", offset: float = 0.0):
-    """(d_ent, d_rel): dense table gradients of train_1vsall_forward's loss (dot family, BCE)."""
+def train_1vsall_backward(model: str, ent, rel, triples, loss: str = "bce", offset: float = 0.0, l_norm: float = 1.0):
+    """(d_ent, d_rel): dense table gradients of train_1vsall_forward's loss (dot family; TransE L1/L2; RotatE L1)."""
     _require_cuda(ent, rel, triples)
     lib, k = _lib.load(), _Keep()
     re_, rr = k.rows(ent), k.rows(rel)
@@ -490,7 +490,7 @@ def train_1vsall_backward(model: str, ent, rel, triples, loss: str = "bce", offs
     nbytes = lib.b200kge_train_1vsall_backward_workspace_bytes(MODELS[model], n, ent.shape[0], ent.shape[1])
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     _lib.check(lib.b200kge_train_1vsall_backward(
-        MODELS[model], C.byref(re_), C.byref(rr), tri.data_ptr(), n, LOSS[loss], offset, d_ent.data_ptr(),
+        MODELS[model], l_norm, C.byref(re_), C.byref(rr), tri.data_ptr(), n, LOSS[loss], offset, d_ent.data_ptr(),
         d_ent.stride(0), d_rel.data_ptr(), d_rel.stride(0), ws.data_ptr(), ws.numel(), _stream(dev)))
     return d_ent, d_rel
 

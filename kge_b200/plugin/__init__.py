@@ -358,8 +358,11 @@ class _B200ModelMixin:
 
     def _b200_loss_1vsall_backward(self, ent_w, rel_w, triples, loss, offset):
         name = self._b200_name
-        if self.b200_backward == "native" and name in ("complex", "distmult", "simple", "cp", "rescal"):
-            return engine.train_1vsall_backward(name, ent_w.detach(), rel_w.detach(), triples, loss, offset)
+        ln = self._b200_args()[0]
+        native = name in ("complex", "distmult", "simple", "cp", "rescal") or \
+            (name == "transe" and ln in (1.0, 2.0)) or (name == "rotate" and ln == 1.0)
+        if self.b200_backward == "native" and native:
+            return engine.train_1vsall_backward(name, ent_w.detach(), rel_w.detach(), triples, loss, offset, ln)
         e, r = ent_w.detach().requires_grad_(True), rel_w.detach().requires_grad_(True)
         n = triples.shape[0]
         s, p, o = triples[:, 0], triples[:, 1], triples[:, 2]

@@ -64,10 +64,10 @@ def loss_dense(scores, labels, loss="bce", offset=0.0, return_rows=False):
     return orc.bce_loss(scores, labels, offset) if loss == "bce" else orc.kl_loss(scores, labels)
 
 
-def train_1vsall_backward(model, ent, rel, triples, loss="bce", offset=0.0):
+def train_1vsall_backward(model, ent, rel, triples, loss="bce", offset=0.0, l_norm=1.0):
     from oracle import kge_fold as kf
 
-    return kf.train_1vsall_backward(model, ent.detach(), rel.detach(), triples.long(), loss, offset)
+    return kf.train_1vsall_backward(model, ent.detach(), rel.detach(), triples.long(), loss, offset, l_norm)
 
 
 def score_1vsN_backward(model, combine, ent, rel, q, p, grad_scores):

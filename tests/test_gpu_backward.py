@@ -83,6 +83,32 @@ def test_backward_medium(eng, model, D, loss):
     _assert_close(d_rel, ref_r, f"{model} d_rel")
 
 
+@pytest.mark.parametrize("loss", ["bce", "kl"])
+@pytest.mark.parametrize("model,D,ln", [("transe", 100, 1.0), ("transe", 72, 2.0), ("rotate", 72, 1.0)])
+def test_backward_distance_family(eng, model, D, ln, loss):
+    """The 1vsAll backward of TransE (L1, L2) and RotatE (L1): CUDA-core scores, dense G and the two row-gradient passes
+    of grad_distance.cu, against the analytic CPU assembly; ragged sizes (E, 2n not multiples of the 128 / 16 tiles, D not
+    a multiple of the 64-element chunk) and a duplicate triple."""
+    from oracle import kge_fold as kf
+
+    E, R, n = 1201, 7, 139
+    ent, rel = orc.make_tables(model, E, R, D, sigma=0.5)
+    tri = orc.make_triples(E, R, n)
+    tri[5] = tri[4]
+    off = 0.5 if loss == "bce" else 0.0
+    ref_e, ref_r = kf.train_1vsall_backward(model, ent.double(), rel.double(), tri, loss, off, ln)
+    d_ent, d_rel = eng.train_1vsall_backward(model, ent.cuda(), rel.cuda(), tri.cuda(), loss, off, ln)
+    _assert_close(d_ent, ref_e, f"{model} d_ent")
+    _assert_close(d_rel, ref_r, f"{model} d_rel")
+
+
+def test_backward_distance_family_refuses_other_norms(eng):
+    ent, rel = orc.make_tables("rotate", 50, 3, 16, sigma=0.5)
+    tri = orc.make_triples(50, 3, 8)
+    with pytest.raises(NotImplementedError):
+        eng.train_1vsall_backward("rotate", ent.cuda(), rel.cuda(), tri.cuda(), "bce", 0.0, 2.0)
+
+
 @pytest.mark.parametrize("model,D,ln", [("complex", 64, 1.0), ("distmult", 32, 1.0), ("simple", 64, 1.0), ("cp", 64, 1.0),
                                         ("rescal", 16, 1.0), ("transe", 64, 1.0), ("transe", 64, 2.0), ("rotate", 64, 1.0)])
 def test_ns_backward(eng, model, D, ln):

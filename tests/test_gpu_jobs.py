@@ -141,11 +141,12 @@ def test_training_epoch_through_plugin(model, splits):
         assert losses[tag][1] == pytest.approx(losses["ref"][1], rel=1e-3)
 
 
-@pytest.mark.parametrize("model", ["complex", "distmult", "simple", "cp", "rescal"])
+@pytest.mark.parametrize("model", ["complex", "distmult", "simple", "cp", "rescal", "transe", "rotate"])
 @pytest.mark.parametrize("loss", ["kl", "bce"])
 def test_training_epoch_native_backward(model, loss, splits):
     """The fused job with the gradient kernels of libb200kge (b200kge_train_1vsall_backward: recompute, G planes,
-    two split-K tensor-core GEMMs, unfold) instead of the reference's autograd: two epochs track the reference."""
+    two split-K tensor-core GEMMs, unfold; TransE / RotatE: the row-gradient passes of grad_distance.cu) instead of the
+    reference's autograd: two epochs track the reference."""
     torch.manual_seed(0)
     init = ju.make_job(model, E, R, D, splits, device="cpu", train_type="1vsAll", loss=loss, batch_size=64)
     losses = {}
