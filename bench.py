@@ -490,6 +490,61 @@ def train_step_bench(torch, local, ent_c, rel_c, batches_host, flush, iters=10):
             "grad_finite": bool(g is not None and bool(_t.isfinite(g).all()))}
 
 
+def batch_split_train_bench(torch, dist, local, rank, world, ent_c, rel_c, flush, iters=10):
+    """SURVEY 8e "small tables": replicas + batch split as a TRAINING step.  Every rank holds the whole ComplEx tables
+    and runs B200TrainingJob1vsAll._process_batch with `user.b200_batch_split` on the SAME global batch of
+    N_BATCH * world triples: fused forward + native backward on its N_BATCH rows, then ncclAllReduce of the dense table
+    gradients (and of the batch loss).  Weak scaling; wall clock between device synchronisations, max over ranks."""
+    if not _have_kge():
+        return {"skipped": "reference not installed"}
+    from kge_b200 import hostenv, synthetic
+
+    hostenv.import_kge()
+    nb = N_BATCH * world
+    dev = torch.device("cuda", local)
+    out = {}
+    for tag, split in (("batch_split", True), ("one_rank_own_batch", False)):
+        job = make_job("b200_" + MODEL, f"cuda:{local}", job_class="B200TrainingJob1vsAll", tables=(ent_c, rel_c),
+                       n_batch=nb if split else N_BATCH, extra={"user.b200_batch_split": split})
+        job.is_forward_only = False
+        batches = [{"triples": synthetic.make_triples(E, R, nb if split else N_BATCH, seed=50 + i).contiguous().pin_memory()}
+                   for i in range(4)]
+        for i in range(3):
+            job.model.zero_grad(set_to_none=False)
+            job._process_batch(i, batches[i % 4])
+        torch.cuda.synchronize()
+        dist.barrier()
+        ts = []
+        for i in range(iters):
+            flush.fill_(i & 0xFF)
+            job.model.zero_grad(set_to_none=False)
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            res = job._process_batch(i, batches[i % 4])
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        t = torch.tensor([sum(ts) / len(ts)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[tag] = {"ms_per_step": float(t) * 1e3, "loss": float(res.avg_loss)}
+        if split:       # replicas must hold identical gradients after the all-reduce
+            g = job.model.get_s_embedder()._embeddings.weight.grad
+            ck = torch.stack([g.double().sum(), g.double().abs().sum()])
+            lo, hi = ck.clone(), ck.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            out[tag]["replica_gradients_identical"] = bool(torch.equal(lo, hi))
+            out[tag]["grad_bytes_all_reduced"] = int(sum(p.numel() * 4 for p in job.model.parameters()))
+        del job
+    per = out["batch_split"]["ms_per_step"] * 1e-3
+    return {"workload": f"ComplEx d={D} 1vsAll+{LOSS.upper()} training step, global batch {nb} = {N_BATCH} rows per GPU, tables "
+                        f"replicated x{world}: fused forward + native backward per rank, dense-gradient ncclAllReduce "
+                        "(B200TrainingJob1vsAll, user.b200_batch_split)",
+            "parallelism": f"replicas + batch split x{world} (NCCL all-reduce of gradients)", "scaling": "weak",
+            "ms_per_step": per * 1e3, "value": nb / per, "unit": "train triples/s",
+            "same_step_without_collective_ms": out["one_rank_own_batch"]["ms_per_step"], "detail": out}
+
+
 def transe_shard_bench(engine, torch, dev, flush, peaks, have_ref, fma_peak):
     rows, D5, n5, R5 = 600000, 512, 128, 822
     g = torch.Generator(device=dev).manual_seed(1234)
@@ -777,6 +832,11 @@ def run_ours(args):
             sharded = sharded_bench(engine, torch, dist, dev, rank, world, flush, _peaks())
         except Exception as ex:
             sharded = {"error": repr(ex)}
+        barrier()
+        try:
+            sharded["batch_split_training"] = batch_split_train_bench(torch, dist, local, rank, world, ent_c, rel_c, flush)
+        except Exception as ex:
+            sharded["batch_split_training"] = {"error": repr(ex)}
         barrier()
 
     if rank != 0:

@@ -879,9 +879,8 @@ int b200kge_train_1vsall_backward(int model, float l_norm, const b200kge_rows_t*
     float* z = (float*)ws.take((size_t)nq * ldz * 4);
     float* G = (float*)ws.take((size_t)nq * ldz * 4);
     float* Gt = (float*)ws.take((size_t)m * ldN * 4);
-    float* Zt = f.pair_op == PAIR_L2 ? (float*)ws.take((size_t)m * ldN * 4) : nullptr;
     float* row_stat = loss_kind == B200KGE_LOSS_KL ? (float*)ws.take((size_t)nq * 2 * 4) : nullptr;
-    if (!Q || !dQ || !lab || !z || !G || !Gt || (f.pair_op == PAIR_L2 && !Zt) || (loss_kind == B200KGE_LOSS_KL && !row_stat)) {
+    if (!Q || !dQ || !lab || !z || !G || !Gt || (loss_kind == B200KGE_LOSS_KL && !row_stat)) {
       set_error("workspace too small");
       return B200KGE_ERR_WORKSPACE;
     }
@@ -897,11 +896,11 @@ int b200kge_train_1vsall_backward(int model, float l_norm, const b200kge_rows_t*
     }
     if (row_stat && (rc = launch_row_lse(z, ldz, nq, m, lab, row_stat, st))) return rc;
     if ((rc = launch_grad_dense(z, ldz, nq, m, lab, row_stat, loss_kind == B200KGE_LOSS_KL ? 0.f : offset, 1.0f / (float)n,
-                                G, ldz, st))) return rc;
+                                f.pair_op == PAIR_L2, G, ldz, st))) return rc;
     if ((rc = launch_transpose(G, ldz, nq, m, Gt, ldN, st))) return rc;
-    if (Zt && (rc = launch_transpose(z, ldz, nq, m, Zt, ldN, st))) return rc;
-    if ((rc = launch_pair_rowgrad(f.pair_op, Q, ldq, nq, E.base, E.ld, m, f.K, G, ldz, z, ldz, dQ, ldq, st))) return rc;
-    if ((rc = launch_pair_rowgrad(f.pair_op, E.base, E.ld, m, Q, ldq, nq, f.K, Gt, ldN, Zt, ldN, d_ent, lde, st))) return rc;
+    // each pass reads its weights transposed ([column, row]): the other pass's orientation
+    if ((rc = launch_pair_rowgrad(f.pair_op, Q, ldq, nq, E.base, E.ld, m, f.K, Gt, ldN, dQ, ldq, st))) return rc;
+    if ((rc = launch_pair_rowgrad(f.pair_op, E.base, E.ld, m, Q, ldq, nq, f.K, G, ldz, d_ent, lde, st))) return rc;
     return launch_unfold_distance(model, E, R, triples, n, -1, dQ, ldq, d_ent, lde, d_rel, ldr, st);
   }
   Folded f0 = folded_problem(model, B200KGE_SP_, E.dim, 1.0f), f1 = folded_problem(model, B200KGE__PO, E.dim, 1.0f);

@@ -93,6 +93,57 @@ presplit_kernel(const SplitSet A, const SplitSet B, const int blocks_a) {
   else presplit_row(B, (int64_t)(blockIdx.x - blocks_a) * PS_WARPS + warp, lane);
 }
 
+// Long rows (the transposed operands of the backward GEMMs: K = E or 2n elements per row, only ~1000 rows): one warp per
+// row leaves most SMs idle and walks 114 strides per pass (83.6 us for 2 x 30 MB at E = 14 541).  One CTA per row instead.
+__global__ void __launch_bounds__(PS_WARPS * 32)
+presplit_longrow_kernel(const SplitSet A, const SplitSet B, const int rows_a) {
+  __shared__ float red[PS_WARPS];
+  __shared__ int bad_any;
+  const bool first = (int)blockIdx.x < rows_a;
+  const SplitSet& S = first ? A : B;
+  const int64_t r = first ? blockIdx.x : blockIdx.x - rows_a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (r >= S.rows) {
+    if (threadIdx.x == 0) S.inv_scale[r] = 0.f;
+    return;
+  }
+  const int64_t src_row = S.idx ? S.idx[r] : r;
+  const float* __restrict__ x = S.src + src_row * S.ld + S.col_off;
+  const int K = S.K, Kp = S.Kp;
+  if (threadIdx.x == 0) bad_any = 0;
+  float amax = 0.f;
+  bool bad = false;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float v = __ldg(x + k);
+    amax = fmaxf(amax, fabsf(v));
+    bad |= !isfinite(v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  __syncthreads();
+  if (__any_sync(0xffffffffu, bad) && lane == 0) bad_any = 1;
+  if (lane == 0) red[warp] = amax;
+  __syncthreads();
+  amax = red[0];
+#pragma unroll
+  for (int w = 1; w < PS_WARPS; ++w) amax = fmaxf(amax, red[w]);
+  int e = 13;                                    // same scaling rule as presplit_row
+  if (amax > 0.f && !bad_any) {
+    e = ilogbf(amax);
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+  }
+  const float mul = scalbnf(1.f, 13 - e);
+  __half2* __restrict__ hi = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(S.hi) + r * Kp);
+  __half2* __restrict__ lo = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(S.lo) + r * Kp);
+  for (int k = threadIdx.x * 2; k < Kp; k += blockDim.x * 2) {        // Kp is even; second read hits L1 / L2
+    const float s0 = (k < K) ? __ldg(x + k) * mul : 0.f, s1 = (k + 1 < K) ? __ldg(x + k + 1) * mul : 0.f;
+    const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
+    hi[k >> 1] = __halves2half2(h0, h1);
+    lo[k >> 1] = __halves2half2(__float2half_rn(s0 - __half2float(h0)), __float2half_rn(s1 - __half2float(h1)));
+  }
+  if (threadIdx.x == 0) S.inv_scale[r] = scalbnf(1.f, e - 13);
+}
+
 // ---------------------------------------------------------------------------------------------
 // The whole prologue of a fused 1vsAll step in ONE launch (train_1vsAll.py:59-65,75-76 up to the scorer):
 //   blocks [0, 2n)   : query row b — gather + relation fold of (s_b, p_b) for the sp_ direction (b < n) or of
@@ -203,6 +254,11 @@ int launch_presplit(const SplitSet& A, const SplitSet& B, cudaStream_t st) {
   const int64_t ba = (A.rows_pad + PS_WARPS - 1) / PS_WARPS, bb = (B.rows_pad + PS_WARPS - 1) / PS_WARPS;
   if (ba + bb == 0) return 0;
   if (ba + bb >= (1ll << 31)) { set_error("too many rows for the operand split"); return B200KGE_ERR_INVALID; }
+  if ((A.K >= 4096 || (B.rows_pad > 0 && B.K >= 4096)) && A.rows_pad + B.rows_pad < (1ll << 31)) {
+    presplit_longrow_kernel<<<(unsigned)(A.rows_pad + B.rows_pad), PS_WARPS * 32, 0, st>>>(A, B, (int)A.rows_pad);
+    B2K_LAUNCH_CHECK("presplit_longrow_kernel");
+    return 0;
+  }
   presplit_kernel<<<(unsigned)(ba + bb), PS_WARPS * 32, 0, st>>>(A, B, (int)ba);
   B2K_LAUNCH_CHECK("presplit_kernel");
   return 0;

@@ -47,7 +47,70 @@ def _fused_model(model):
     return model if model.b200_fusable() else None
 
 
-class B200TrainingJob1vsAll(TrainingJob1vsAll):
+def _user_option(config, key, default=None):
+    try:
+        return config.get("user." + key)
+    except KeyError:
+        return default
+
+
+class _BatchSplit:
+    """Replicas + batch split over the processes of a torch.distributed group ("small tables": every GPU
+    holds the whole tables, scores its share of the batch's rows against them, and the dense table gradients are
+    all-reduced before the optimizer step; no collective on the forward data path).
+
+    Enabled by `user.b200_batch_split: true` when a process group with more than one rank is initialised (one process
+    per GPU, `job.device: cuda:<LOCAL_RANK>`, one output folder per rank, the same random seed on every rank so that
+    all ranks draw the same batches).  Rank r takes rows [r*B/W, (r+1)*B/W) of every batch; the per-row losses are
+    divided by the size of the WHOLE batch (as for sub-batches, train_1vsAll.py:65), so the all-reduced gradients and
+    avg_loss are those of the single-process job.  Penalties and the optimizer step run identically on every rank
+    (kge/job/train.py:411-470), which keeps the replicas in step without a broadcast."""
+
+    def _b200_ranks(self):
+        r = getattr(self, "_b200_rank_world", None)
+        if r is None:
+            r = (0, 1)
+            if _user_option(self.config, "b200_batch_split", False):
+                import torch.distributed as dist
+
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                    r = (dist.get_rank(), dist.get_world_size())
+            self._b200_rank_world = r
+        return r
+
+    def _b200_my_rows(self, subbatch_slice, batch_size):
+        """This rank's part of a sub-batch slice, or None if it has none."""
+        rank, world = self._b200_ranks()
+        if world == 1:
+            return subbatch_slice
+        lo, hi = rank * batch_size // world, (rank + 1) * batch_size // world
+        start = max(subbatch_slice.start or 0, lo)
+        stop = min(batch_size if subbatch_slice.stop is None else subbatch_slice.stop, hi)
+        return slice(start, stop) if stop > start else None
+
+    def _process_batch(self, batch_index, batch):
+        result = super()._process_batch(batch_index, batch)
+        rank, world = self._b200_ranks()
+        if world == 1:
+            return result
+        import torch.distributed as dist
+
+        if not self.is_forward_only:
+            for p in self.model.parameters():
+                if not p.requires_grad:
+                    continue
+                if p.grad is None:                      # a rank without rows (batch smaller than the group)
+                    p.grad = torch.zeros_like(p)
+                if p.grad.is_sparse:
+                    raise NotImplementedError("user.b200_batch_split all-reduces dense gradients (sparse: False)")
+                dist.all_reduce(p.grad)
+        total = torch.tensor([result.avg_loss], dtype=torch.float64, device=self.device)
+        dist.all_reduce(total)
+        result.avg_loss = float(total.item())
+        return result
+
+
+class B200TrainingJob1vsAll(_BatchSplit, TrainingJob1vsAll):
     """`TrainingJob1vsAll` (train_1vsAll.py:10-82) with the sub-batch step as ONE fused call:
     (loss(score_sp, o) + loss(score_po, s)) / batch_size, both directions stacked into one problem."""
 
@@ -58,6 +121,9 @@ class B200TrainingJob1vsAll(TrainingJob1vsAll):
                 f(self)
 
     def _process_subbatch(self, batch_index, batch, subbatch_slice, result):
+        subbatch_slice = self._b200_my_rows(subbatch_slice, result.size)
+        if subbatch_slice is None:
+            return
         model, kind = _fused_model(self.model), _fused_loss_kind(self.loss)
         if model is None or kind is None:
             return super()._process_subbatch(batch_index, batch, subbatch_slice, result)
@@ -82,7 +148,7 @@ class B200TrainingJob1vsAll(TrainingJob1vsAll):
         result.backward_time += time.time()
 
 
-class B200TrainingJobKvsAll(TrainingJobKvsAll):
+class B200TrainingJobKvsAll(_BatchSplit, TrainingJobKvsAll):
     """`TrainingJobKvsAll` (train_KvsAll.py:205-294): per query type one fused score+loss call that consumes the
     batch's label coordinates as CSR (no dense [n, E] label matrix: job/util.py:32-60 + `.to_dense()`,
     train_KvsAll.py:242-266 are not executed)."""
@@ -94,6 +160,9 @@ class B200TrainingJobKvsAll(TrainingJobKvsAll):
                 f(self)
 
     def _process_subbatch(self, batch_index, batch, subbatch_slice, result):
+        subbatch_slice = self._b200_my_rows(subbatch_slice, result.size)
+        if subbatch_slice is None:
+            return
         model, kind = _fused_model(self.model), _fused_loss_kind(self.loss)
         qtypes = [q for q in self.query_types]
         if (model is None or kind is None or "s_o" in qtypes or not model.b200_csr_labels_ok(self.label_smoothing)
@@ -151,7 +220,7 @@ class B200TrainingJobKvsAll(TrainingJobKvsAll):
             result.backward_time += time.time()
 
 
-class B200TrainingJobNegativeSampling(TrainingJobNegativeSampling):
+class B200TrainingJobNegativeSampling(_BatchSplit, TrainingJobNegativeSampling):
     """`TrainingJobNegativeSampling` (train_negative_sampling.py:103-164): per slot ONE kernel gathers the sampled
     rows and scores them, with the positive triple in column 0 — neither `[n*K, D]` gathers (`triple`
     implementation, sampler.py:294-305) nor scoring against all unique targets (`batch`, :306-339).
@@ -194,6 +263,9 @@ class B200TrainingJobNegativeSampling(TrainingJobNegativeSampling):
                                      torch.initial_seed(), offset, self.device)
 
     def _process_subbatch(self, batch_index, batch, subbatch_slice, result):
+        subbatch_slice = self._b200_my_rows(subbatch_slice, result.size)
+        if subbatch_slice is None:
+            return
         model = _fused_model(self.model)
         kind = _fused_loss_kind(self.loss)
         slots = [sl for sl in (S, P, O) if self._sampler.num_samples[sl] > 0]

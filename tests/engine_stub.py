@@ -70,6 +70,14 @@ def train_1vsall_backward(model, ent, rel, triples, loss="bce", offset=0.0, l_no
     return kf.train_1vsall_backward(model, ent.detach(), rel.detach(), triples.long(), loss, offset, l_norm)
 
 
+def ns_backward(model, ent, rel, triples, negatives, offset=0.0, l_norm=1.0, batch_size=None):
+    from oracle import kge_fold as kf
+
+    d_ent, d_rel = kf.ns_backward(model, ent.detach(), rel.detach(), triples.long(), negatives, offset, l_norm)
+    scale = triples.shape[0] / float(batch_size or triples.shape[0])     # the oracle divides by n, the job by the batch
+    return d_ent * scale, d_rel * scale
+
+
 def score_1vsN_backward(model, combine, ent, rel, q, p, grad_scores):
     e, r = ent.detach().clone().requires_grad_(True), rel.detach().clone().requires_grad_(True)
     with torch.enable_grad():
@@ -116,7 +124,7 @@ def installed():
     from kge_b200 import engine
 
     names = ["score_spo", "score_1vsN", "score_sp_po", "train_1vsall_forward", "score_1vsN_loss",
-             "score_1vsN_loss_csr", "ns_score", "loss_dense", "train_1vsall_backward", "score_1vsN_backward", "score_1vsN_loss_csr_backward", "launch_count"]
+             "score_1vsN_loss_csr", "ns_score", "loss_dense", "train_1vsall_backward", "ns_backward", "score_1vsN_backward", "score_1vsN_loss_csr_backward", "launch_count"]
     saved = {k: getattr(engine, k) for k in names}
     g = globals()
 
