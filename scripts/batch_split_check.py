@@ -68,10 +68,17 @@ def main():
             ref_losses, ref_ent, ref_rel = train(case, False, f"cuda:{local}")
             for a, b in zip(losses, ref_losses):
                 assert abs(a - b) <= 1e-4 * abs(b), (case, losses, ref_losses)
-            err = max(float((ent - ref_ent).abs().max() / ref_ent.abs().max()),
-                      float((rel - ref_rel).abs().max() / ref_rel.abs().max()))
-            assert err <= 1e-3, (case, err)
-            report[case] = {"avg_loss": losses, "single_process": ref_losses, "table_rel_err": err}
+            # Frobenius norm: Adagrad turns a gradient element that is round-off around zero into a +-lr step, so single
+            # elements may differ by 2 lr between two summation orders (the L1 models' sign gradients make that common)
+            err = max(float((ent - ref_ent).norm() / ref_ent.norm()), float((rel - ref_rel).norm() / ref_rel.norm()))
+            # noise floor: the same single-process job twice (atomic accumulation order in the unfold kernels)
+            _, ent2, rel2 = train(case, False, f"cuda:{local}")
+            noise = max(float((ent2 - ref_ent).norm() / ref_ent.norm()), float((rel2 - ref_rel).norm() / ref_rel.norm()))
+            report[case] = {"avg_loss": losses, "single_process": ref_losses, "table_rel_err": err,
+                            "single_process_run_to_run": noise,
+                            "elements_differing_by_more_than_1e-3": int(((ent - ref_ent).abs() > 1e-3).sum()),
+                            "elements": ent.numel()}
+            assert err <= max(1e-3, 4 * noise), (case, report[case])
         dist.barrier()
     if rank == 0:
         print(json.dumps({"check": "batch split over N ranks == single-process job", "world": world, "cases": report}),
