@@ -257,7 +257,7 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -898,12 +898,34 @@ def run_ours(args):
             line["configs"]["cfg2_train_fwd_bwd"] = train_step_bench(torch, local, ent_c, rel_c, batches_host, flush)
         except Exception as ex:
             line["configs"]["cfg2_train_fwd_bwd"] = {"error": repr(ex)}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_OUT_FD = None
+
+
+def _stdout_for_the_json_line_only():
+    """Libraries print to stdout too (NCCL's version banner under NCCL_DEBUG=VERSION): route fd 1 to stderr for the whole
+    run and keep the original for the ONE json line the contract asks for."""
+    global _OUT_FD
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _OUT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_OUT_FD, data)
+
+
 def main():
+    _stdout_for_the_json_line_only()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -73,7 +73,9 @@ __device__ __forceinline__ void fetch8(const float* __restrict__ rowp, bool row_
   for (int c = 0; c < 8; ++c) r[c] = (row_ok && k + c < kmax) ? __ldg(rowp + k + c) : 0.f;
 }
 
-template <int PAIR, int EPI, bool VEC>
+// CSR: the ranking epilogue with a CSR filter is its own instantiation — its 16 cursor registers would otherwise cost the
+// plain rank kernel its second resident CTA (168 vs <= 128 registers: 5.83 -> 6.59 ms on the cfg5 shard).
+template <int PAIR, int EPI, bool VEC, bool CSR = false>
 __global__ void __launch_bounds__(NT)   // (NT, 2) was measured: spills in the fused epilogues, no net gain
 pairwise_simt_kernel(const float* __restrict__ Q, int64_t ldq, int64_t nq, Rows cand, int col_off,
                      int K, float p_norm, int col_tiles, EpiParams P) {
@@ -116,15 +118,15 @@ pairwise_simt_kernel(const float* __restrict__ Q, int64_t ldq, int64_t nq, Rows 
   // CSR ranking filter: per owned row a cursor into its sorted segment of known answers; the CTA visits
   // its column tiles in increasing order, so each cursor only moves forward (one binary search at the first tile, then
   // ~one L1-resident load per row and tile)
-  int64_t ccur[8], cend[8];
-  if constexpr (EPI == EPI_RANK) {
+  int ccur[CSR ? 8 : 1], cend[CSR ? 8 : 1];          // nnz < 2^31 (checked by the launcher)
+  if constexpr (CSR) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int64_t row = row0 + ty * 4 + 64 * (i >> 2) + (i & 3);
       ccur[i] = 0; cend[i] = 0;
-      if (P.csr_off && row < nq) {
-        cend[i] = __ldg(P.csr_off + row + 1);
-        ccur[i] = csr_lower_bound(P.csr_col, __ldg(P.csr_off + row), cend[i], (int64_t)t0 * BN);
+      if (row < nq) {
+        cend[i] = (int)__ldg(P.csr_off + row + 1);
+        ccur[i] = (int)csr_lower_bound(P.csr_col, __ldg(P.csr_off + row), (int64_t)cend[i], (int64_t)t0 * BN);
       }
     }
   }
@@ -220,7 +222,7 @@ pairwise_simt_kernel(const float* __restrict__ Q, int64_t ldq, int64_t nq, Rows 
       const int64_t row = row0 + ty * 4 + 64 * (i >> 2) + (i & 3);
       const bool row_ok = row < nq;
       unsigned filtered = 0u;          // bit j: element (i, j) is a known answer of this row (rank filter)
-      if constexpr (EPI == EPI_RANK) {
+      if constexpr (CSR) {
         if (ccur[i] < cend[i]) {
           const int64_t own = P.csr_skip ? __ldg(P.csr_skip + row) : -1;
           int64_t cj = __ldg(P.csr_col + ccur[i]);
@@ -236,7 +238,7 @@ pairwise_simt_kernel(const float* __restrict__ Q, int64_t ldq, int64_t nq, Rows 
       for (int j = 0; j < 8; ++j) {
         const int64_t col = col0 + tx * 4 + 64 * (j >> 2) + (j & 3);
         float x = pair_finish<PAIR>(acc[i][j], p_norm);
-        if constexpr (EPI == EPI_RANK) {
+        if constexpr (CSR) {
           if (filtered & (1u << j)) x = -INFINITY;       // eval_entity_ranking.py:561-566: score - inf
         }
         if (row_ok && col < m) epi_elem<EPI>(P, st[i], row, col, x, aux[i]);
@@ -258,6 +260,17 @@ template <int PAIR, int EPI>
 int launch_pe(bool vec, dim3 grid, cudaStream_t st, const float* Q, int64_t ldq, int64_t nq,
               const Rows& cand, int col_off, int K, float p, const EpiParams& P) {
   const int col_tiles = (int)((cand.rows + BN - 1) / BN);
+  if constexpr (EPI == EPI_RANK) {
+    if (P.csr_off) {
+      if (P.csr_nnz >= (1ll << 31)) { set_error("CSR filter too long for the CUDA-core rank epilogue"); return B200KGE_ERR_UNSUPPORTED; }
+      profile_begin(st);
+      if (vec) pairwise_simt_kernel<PAIR, EPI, true, true><<<grid, NT, 0, st>>>(Q, ldq, nq, cand, col_off, K, p, col_tiles, P);
+      else     pairwise_simt_kernel<PAIR, EPI, false, true><<<grid, NT, 0, st>>>(Q, ldq, nq, cand, col_off, K, p, col_tiles, P);
+      profile_end(st);
+      B2K_LAUNCH_CHECK("pairwise_simt_kernel");
+      return 0;
+    }
+  }
   profile_begin(st);
   if (vec) pairwise_simt_kernel<PAIR, EPI, true><<<grid, NT, 0, st>>>(Q, ldq, nq, cand, col_off, K, p, col_tiles, P);
   else     pairwise_simt_kernel<PAIR, EPI, false><<<grid, NT, 0, st>>>(Q, ldq, nq, cand, col_off, K, p, col_tiles, P);
