@@ -490,6 +490,33 @@ def train_step_bench(torch, local, ent_c, rel_c, batches_host, flush, iters=10):
             "grad_finite": bool(g is not None and bool(_t.isfinite(g).all()))}
 
 
+def reference_on_gpu_bench(torch, local, ent_c, rel_c, batches_host, flush, iters=20):
+    """SURVEY 8d "PyTorch-on-B200" bar: the UNMODIFIED reference job and model (`model: complex`, no plugin module on the
+    path) with job.device cuda — torch's own kernels (cuBLAS sgemm, elementwise, BCEWithLogits) on the same GPU, same
+    batches, same harness as `e2e` (host batch in, .item() out, wall clock between synchronisations)."""
+    if not _have_kge():
+        return {"skipped": "reference not installed"}
+    job = make_job(MODEL, f"cuda:{local}", tables=(ent_c, rel_c))
+    assert type(job).__name__ == "TrainingJob1vsAll" and type(job.model).__name__ == "ComplEx"
+    for i in range(3):
+        loss = job._process_batch(i, {"triples": batches_host[i % 4]}).avg_loss
+    torch.cuda.synchronize()
+    ts = []
+    for i in range(iters):
+        flush.fill_(i & 0xFF)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        loss = job._process_batch(i, {"triples": batches_host[i % 4]}).avg_loss
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    per = sum(ts) / len(ts)
+    return {"workload": "the headline step through the unmodified reference TrainingJob1vsAll._process_batch (forward only) "
+                        "with the reference's own ComplEx model on job.device cuda (torch eager: fp32 cuBLAS GEMMs with "
+                        f"torch.backends.cuda.matmul.allow_tf32={torch.backends.cuda.matmul.allow_tf32}, embed_all copy, "
+                        "[n,E] logits and BCE through HBM)",
+            "ms_per_step": per * 1e3, "value": 2.0 * N_BATCH * E / per, "unit": UNIT, "loss_last": float(loss)}
+
+
 def batch_split_train_bench(torch, dist, local, rank, world, ent_c, rel_c, flush, iters=10):
     """SURVEY 8e "small tables": replicas + batch split as a TRAINING step.  Every rank holds the whole ComplEx tables
     and runs B200TrainingJob1vsAll._process_batch with `user.b200_batch_split` on the SAME global batch of
@@ -798,7 +825,8 @@ def run_ours(args):
             def step(i):
                 return job._process_batch(i, {"triples": batches_host[i % 4]}).avg_loss
             e2e_api = ("kge.job.TrainingJob._process_batch of B200TrainingJob1vsAll (1vsAll.class_name) with model "
-                       "b200_complex on job.device cuda: pinned host batch -> .to(device) -> fused step -> .item()")
+                       "b200_complex on job.device cuda: pinned host batch -> one library call (H2D copy, fused step, "
+                       "4-byte read-back, stream sync) -> float")
             d2h = 4
         except Exception as ex:
             step, e2e_api = None, f"job plugin unavailable ({ex!r}); "
@@ -898,6 +926,10 @@ def run_ours(args):
             line["configs"]["cfg2_train_fwd_bwd"] = train_step_bench(torch, local, ent_c, rel_c, batches_host, flush)
         except Exception as ex:
             line["configs"]["cfg2_train_fwd_bwd"] = {"error": repr(ex)}
+        try:
+            line["reference_on_b200"] = reference_on_gpu_bench(torch, local, ent_c, rel_c, batches_host, flush)
+        except Exception as ex:
+            line["reference_on_b200"] = {"error": repr(ex)}
     _emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -413,8 +413,11 @@ class Step1vsAll:
         self.k = _Keep()
         self.re, self.rr = self.k.rows(self.ent), self.k.rows(self.rel)
         self.max_n = int(max_n)
-        self.ws = _workspace(MODELS[model], self.max_n, ent.shape[0], ent.shape[1], False, ent.device)
+        nbytes = self.lib.b200kge_workspace_bytes(MODELS[model], self.max_n, ent.shape[0], ent.shape[1], 0)
+        self.ws = torch.empty(nbytes + self.max_n * 24 + 1024, dtype=torch.uint8, device=ent.device)   # + staged batch (host form)
         self.out = torch.zeros((), dtype=torch.float32, device=ent.device)
+        self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.loss_np = self.loss_host.numpy()
         self.key = (self.ent.data_ptr(), self.rel.data_ptr(), tuple(ent.shape), tuple(rel.shape))
         self.args = (MODELS[model], C.c_float(l_norm), PREC[precision], C.byref(self.re), C.byref(self.rr))
         self.tail = (LOSS[loss], C.c_float(offset), C.c_void_p(self.out.data_ptr()), C.c_void_p(self.ws.data_ptr()),
@@ -432,6 +435,17 @@ class Step1vsAll:
         if rc:
             _lib.check(rc)
         return self.out
+
+    def call_host(self, triples_host: torch.Tensor) -> float:
+        """The same step from a HOST batch (contiguous int64 [n,3], ideally pinned): host->device copy, kernels, the
+        4-byte read-back and the stream synchronisation inside ONE library call (triples.to(device) ... .item(),
+        train_1vsAll.py:59-77)."""
+        rc = self.lib.b200kge_train_1vsall_forward_host(
+            *self.args, C.c_void_p(triples_host.data_ptr()), triples_host.shape[0], self.tail[0], self.tail[1],
+            C.c_void_p(self.loss_host.data_ptr()), self.tail[3], self.ws.numel(), _stream(self.dev))
+        if rc:
+            _lib.check(rc)
+        return float(self.loss_np[0])
 
 
 class HostStep:

@@ -412,15 +412,23 @@ class _B200ModelMixin:
             need_grad = self._b200_needs_grad()
         if need_grad and self._b200_needs_grad():
             return _Loss1vsAllFn.apply(ent_w, rel_w, self, triples, loss, offset)
-        # forward only: a prepared step (table views, workspace, output scalar set up once per table storage)
+        return self._b200_prepared_step(ent_w, rel_w, triples.shape[0], loss, offset)(triples)
+
+    def _b200_prepared_step(self, ent_w, rel_w, n, loss, offset):
+        """forward only: a prepared step (table views, workspace, output scalar set up once per table storage)"""
         st = self.__dict__.get("_b200_step")
-        n = triples.shape[0]
         if st is None or st.cfg != (loss, offset) or not st.matches(ent_w, rel_w, n):
             ln, prec = self._b200_args()
             st = engine.Step1vsAll(self._b200_name, ent_w.detach(), rel_w.detach(), max(n, 1024), loss, offset, ln, prec)
             st.cfg = (loss, offset)
             self.__dict__["_b200_step"] = st
-        return st(triples)
+        return st
+
+    def loss_1vsall_host(self, triples_host, loss="bce", offset=0.0) -> float:
+        """loss_1vsall for a HOST batch (contiguous int64 [n,3]) as a Python float, forward only: the copy to the
+        device, the kernels and the read-back of the scalar are one library call (train_1vsAll.py:59-77)."""
+        ent_w, rel_w = self._b200_weights()
+        return self._b200_prepared_step(ent_w, rel_w, triples_host.shape[0], loss, offset).call_host(triples_host)
 
     def loss_kvsall(self, combine, a, p, csr_offsets, csr_cols, loss="kl", offset=0.0, label_smoothing=0.0):
         """Sum over rows of the KvsAll loss with CSR multi-hot labels (train_KvsAll.py:242-294); forward only."""

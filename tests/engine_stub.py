@@ -107,6 +107,9 @@ class Step1vsAll:
         _counter["n"] += 1
         return orc.train_1vsall_forward(self.model, self.ent, self.rel, triples.long(), self.loss, self.offset, self.l_norm)
 
+    def call_host(self, triples_host):
+        return float(self(triples_host))
+
 
 _counter = {"n": 0}
 

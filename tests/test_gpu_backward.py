@@ -84,7 +84,8 @@ def test_backward_medium(eng, model, D, loss):
 
 
 @pytest.mark.parametrize("loss", ["bce", "kl"])
-@pytest.mark.parametrize("model,D,ln", [("transe", 100, 1.0), ("transe", 72, 2.0), ("rotate", 72, 1.0)])
+@pytest.mark.parametrize("model,D,ln", [("transe", 100, 1.0), ("transe", 72, 2.0), ("rotate", 72, 1.0), ("transe", 3, 1.0),
+                                        ("transe", 130, 2.0), ("rotate", 66, 1.0)])
 def test_backward_distance_family(eng, model, D, ln, loss):
     """The 1vsAll backward of TransE (L1, L2) and RotatE (L1): CUDA-core scores, dense G and the two row-gradient passes
     of grad_distance.cu, against the analytic CPU assembly; ragged sizes (E, 2n not multiples of the 128 / 16 tiles, D not
@@ -100,6 +101,18 @@ def test_backward_distance_family(eng, model, D, ln, loss):
     d_ent, d_rel = eng.train_1vsall_backward(model, ent.cuda(), rel.cuda(), tri.cuda(), loss, off, ln)
     _assert_close(d_ent, ref_e, f"{model} d_ent")
     _assert_close(d_rel, ref_r, f"{model} d_rel")
+
+
+def test_backward_distance_family_tiny_batch(eng):
+    """One triple, five entities: every tile of the row-gradient passes is ragged."""
+    from oracle import kge_fold as kf
+
+    ent, rel = orc.make_tables("transe", 5, 2, 8, sigma=0.5)
+    tri = torch.tensor([[1, 0, 3]])
+    ref_e, ref_r = kf.train_1vsall_backward("transe", ent.double(), rel.double(), tri, "kl", 0.0, 1.0)
+    d_ent, d_rel = eng.train_1vsall_backward("transe", ent.cuda(), rel.cuda(), tri.cuda(), "kl", 0.0, 1.0)
+    _assert_close(d_ent, ref_e, "d_ent")
+    _assert_close(d_rel, ref_r, "d_rel")
 
 
 def test_backward_distance_family_refuses_other_norms(eng):
