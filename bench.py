@@ -880,7 +880,7 @@ def run_ours(args):
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": 34.1e6,
-        "traffic_from": "profiles/r2_raw_tc4.csv / r2_raw_tc3.csv (ncu --set full of this command: dram__bytes_read.sum 34.10 MB + "
+        "traffic_from": "profiles/r2c_raw_tc4.csv / r2_raw_tc3.csv (ncu --set full of this command: dram__bytes_read.sum 34.11 MB + "
                         "dram__bytes_write.sum 0 per launch) — NOT measured in this run; algorithmic bytes = table "
                         "planes 29.8 MB + query planes 4.2 MB",
         "kernel": "pairwise_tc4_kernel<BCE> (CTA pair)" if pair else "pairwise_tc3_kernel<BCE>",
