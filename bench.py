@@ -242,6 +242,14 @@ def cpu_reference(steps, warmup, budget_s):
     return _time_oracle_port(steps, warmup, budget_s)
 
 
+def _config(world):
+    """The SAME config object in both arms (the driver compares them): the workload, and how the device arm times it."""
+    return {"workload": WORKLOAD, "global_batch": N_BATCH * world,
+            "parallelism": f"replicas x{world} (batch split, no data-path collective)",
+            "l2": "device arm: flushed before every timed step (256 MiB write)",
+            "precision": "device arm: f16x3 split (parity mode); reference arm: torch fp32 on the host"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -252,7 +260,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": done, "warmup": W, "ms_per_step": base["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD},
+        "config": _config(max(1, args.gpus)),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -899,10 +907,7 @@ def run_ours(args):
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (fp16 hi/lo split products hi*hi + hi*lo + lo*hi on tcgen05, fp32 accumulate; ~2.5e-5 of score rms vs fp64)",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "global_batch": N_BATCH * world, "parallelism": f"replicas x{world} (batch split, no "
-                   "data-path collective)", "l2": "flushed before every timed step (256 MiB write)",
-                   "precision": "f16x3 split (parity mode)"},
+        "config": _config(world),
         "roofline": roofline,
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
