@@ -331,7 +331,7 @@ int b200kge_train_1vsall_backward(int model, float l_norm, const b200kge_rows_t*
  * fp16 hi/lo planes of grad_scores and of its transpose, two split-K tensor-core GEMMs (dT = G^T Q, dQ = G T) and the
  * row-wise unfold — no cuBLAS, no [n, E, D] intermediate. */
 size_t b200kge_score_1vsN_backward_workspace_bytes(int model, int64_t n, int64_t E, int32_t D);
-int b200kge_score_1vsN_backward(int model, int combine, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+int b200kge_score_1vsN_backward(int model, int combine, float l_norm, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
                                 const int64_t* q_idx, const int64_t* p_idx, int64_t n, const float* grad_scores,
                                 int64_t ldg, float* d_ent, int64_t lde, float* d_rel, int64_t ldr, void* workspace,
                                 size_t workspace_bytes, b200kge_stream_t stream);

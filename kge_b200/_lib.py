@@ -87,7 +87,7 @@ SIGNATURES = {
                                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                                   C.c_size_t, C.c_void_p]),
     "b200kge_score_1vsN_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int64, C.c_int32]),
-    "b200kge_score_1vsN_backward": (C.c_int, [C.c_int, C.c_int, _RP, _RP, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+    "b200kge_score_1vsN_backward": (C.c_int, [C.c_int, C.c_int, C.c_float, _RP, _RP, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                               C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                               C.c_size_t, C.c_void_p]),
     "b200kge_score_1vsN_loss_csr_backward": (C.c_int, [C.c_int, C.c_int, _RP, _RP, C.c_void_p, C.c_void_p, C.c_int64,

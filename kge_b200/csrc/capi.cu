@@ -944,10 +944,13 @@ int b200kge_train_1vsall_backward(int model, float l_norm, const b200kge_rows_t*
 size_t b200kge_score_1vsN_backward_workspace_bytes(int model, int64_t n, int64_t E, int32_t D) {
   const int64_t K = (model == B200KGE_CP) ? D / 2 : D;
   const int64_t ldq = round_up(K, 32);
+  if (model == B200KGE_TRANSE || model == B200KGE_ROTATE)   // Q, dQ, triples, z + W (L2), W^T, scorer workspace
+    return 2 * (size_t)n * ldq * 4 + (size_t)n * 4 * 8 + 2 * (size_t)n * round_up(E, 4) * 4 + (size_t)E * round_up(n, 4) * 4 +
+           16 * 256 + b200kge_workspace_bytes(model, n, E, D, 0);
   return 2 * (size_t)n * ldq * 4 + (size_t)n * 4 * 8 + (size_t)E * round_up(n, 4) * 4 + 8192 + backward_block_bytes(n, E, K, ldq);
 }
 
-int b200kge_score_1vsN_backward(int model, int combine, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
+int b200kge_score_1vsN_backward(int model, int combine, float l_norm, const b200kge_rows_t* ent, const b200kge_rows_t* rel,
                                 const int64_t* q_idx, const int64_t* p_idx, int64_t n, const float* grad_scores,
                                 int64_t ldg, float* d_ent, int64_t lde, float* d_rel, int64_t ldr, void* workspace,
                                 size_t workspace_bytes, b200kge_stream_t stream) {
@@ -955,15 +958,20 @@ int b200kge_score_1vsN_backward(int model, int combine, const b200kge_rows_t* en
   if (ent->idx || rel->idx) { set_error("ent/rel must be plain tables"); return B200KGE_ERR_INVALID; }
   if (combine != B200KGE_SP_ && combine != B200KGE__PO) { set_error("cannot handle combine=%d", combine); return B200KGE_ERR_INVALID; }
   int rc = validate_model(model, to_rows(ent), to_rows(rel)); if (rc) return rc;
-  if (model > B200KGE_RESCAL) { set_error("the tensor-core backward covers the dot family only (model %d)", model); return B200KGE_ERR_UNSUPPORTED; }
+  if ((rc = validate_norm(model, l_norm))) return rc;
   if (lde < ent->dim || ldr < rel->dim || ldg < ent->rows) { set_error("leading dimensions too small"); return B200KGE_ERR_INVALID; }
+  const bool distance = (model == B200KGE_TRANSE || model == B200KGE_ROTATE);
   cudaStream_t st = (cudaStream_t)stream;
   Rows E = to_rows(ent), R = to_rows(rel);
+  Folded f = folded_problem(model, combine, E.dim, l_norm);
+  if (distance && f.pair_op != PAIR_L1 && f.pair_op != PAIR_L2 && f.pair_op != PAIR_CMOD_L1) {
+    set_error("the distance-family backward covers l_norm 1 and 2 (TransE) and 1 (RotatE)");
+    return B200KGE_ERR_UNSUPPORTED;
+  }
   B2K_CUDA(cudaMemsetAsync(d_rel, 0, (size_t)R.rows * ldr * 4, st));
   B2K_CUDA(cudaMemsetAsync(d_ent, 0, (size_t)E.rows * lde * 4, st));
   if (n <= 0) return 0;
   Arena ws{(uint8_t*)workspace, workspace_bytes, 0};
-  Folded f = folded_problem(model, combine, E.dim, 1.0f);
   const int64_t ldq = round_up(f.K, 32);
   float* Q = (float*)ws.take((size_t)n * ldq * 4);
   float* dQ = (float*)ws.take((size_t)n * ldq * 4);
@@ -975,6 +983,30 @@ int b200kge_score_1vsN_backward(int model, int combine, const b200kge_rows_t* en
   Rows A = E; A.idx = q_idx; A.rows = n;
   Rows Pr = R; Pr.idx = p_idx; Pr.rows = n;
   if ((rc = launch_fold_queries(model, combine, A, Pr, n, 0, Q, ldq, st))) return rc;
+  if (distance) {
+    // grad_distance.cu: W = dL/dscores (L2: divided by the recomputed scores), then the two row-gradient passes
+    const int64_t m = E.rows, ldz = round_up(m, 4), ldN = round_up(n, 4);
+    const float* W = grad_scores;
+    int64_t ldw = ldg;
+    if (f.pair_op == PAIR_L2) {
+      float* z = (float*)ws.take((size_t)n * ldz * 4);
+      float* Wd = (float*)ws.take((size_t)n * ldz * 4);
+      if (!z || !Wd) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+      EpiParams P = empty_epi();
+      P.out = z; P.ldo = ldz;
+      Block B{model, combine, &A, nullptr, &Pr, &E, n};
+      B.Qpre = Q;
+      if ((rc = run_block(B, l_norm, B200KGE_PREC_AUTO, EPI_STORE, P, ws, st, nullptr))) return rc;
+      if ((rc = launch_div_scores(grad_scores, ldg, z, ldz, n, m, Wd, ldz, st))) return rc;
+      W = Wd; ldw = ldz;
+    }
+    float* Wt = (float*)ws.take((size_t)m * ldN * 4);
+    if (!Wt) { set_error("workspace too small"); return B200KGE_ERR_WORKSPACE; }
+    if ((rc = launch_transpose(W, ldw, n, m, Wt, ldN, st))) return rc;
+    if ((rc = launch_pair_rowgrad(f.pair_op, Q, ldq, n, E.base, E.ld, m, f.K, Wt, ldN, dQ, ldq, st))) return rc;
+    if ((rc = launch_pair_rowgrad(f.pair_op, E.base, E.ld, m, Q, ldq, n, f.K, W, ldw, d_ent, lde, st))) return rc;
+    return launch_unfold_distance(model, E, R, tri, n, combine, dQ, ldq, d_ent, lde, d_rel, ldr, st);
+  }
   if ((rc = backward_block(model, E, R, tri, n, combine, Q, ldq, nullptr, f.col_off, f.K, B200KGE_LOSS_BCE, 0.f, d_ent, lde, dQ,
                            ws, st, grad_scores, ldg))) return rc;
   return launch_unfold(model, E, R, tri, n, combine, dQ, ldq, d_ent, lde, d_rel, ldr, st);

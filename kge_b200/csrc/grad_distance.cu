@@ -137,6 +137,16 @@ grad_dense_kernel(const float* __restrict__ z, int64_t ldz, int64_t E, const int
   G[i * ldg + e] = g;
 }
 
+// W[i, e] = g[i, e] / z[i, e] (0 where z = 0): the L2 pair op's chain factor for a given dL/dscores.  grid = (ceil(E/256), n)
+__global__ void __launch_bounds__(256)
+div_scores_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ z, int64_t ldz, int64_t E,
+                  float* __restrict__ W, int64_t ldw) {
+  const int64_t i = blockIdx.y, e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const float zv = z[i * ldz + e];
+  W[i * ldw + e] = (zv != 0.f) ? g[i * ldg + e] / zv : 0.f;
+}
+
 template <int PAIR>
 int launch_rowgrad_t(const float* A, int64_t lda, int64_t ra, const float* B, int64_t ldb, int64_t rb, int K, const float* Wt,
                      int64_t ldwt, float* dA, int64_t ldda, cudaStream_t st) {
@@ -159,6 +169,16 @@ int launch_pair_rowgrad(int pair_op, const float* A, int64_t lda, int64_t ra, co
   }
   set_error("the distance-family backward covers L1, L2 (TransE) and the L1 of complex moduli (RotatE)");
   return B200KGE_ERR_UNSUPPORTED;
+}
+
+int launch_div_scores(const float* g, int64_t ldg, const float* z, int64_t ldz, int64_t n, int64_t E, float* W, int64_t ldw,
+                      cudaStream_t st) {
+  if (n == 0 || E == 0) return 0;
+  if (n > 65535) { set_error("too many rows for one launch (%lld)", (long long)n); return B200KGE_ERR_UNSUPPORTED; }
+  dim3 grid((unsigned)((E + 255) / 256), (unsigned)n);
+  div_scores_kernel<<<grid, 256, 0, st>>>(g, ldg, z, ldz, E, W, ldw);
+  B2K_LAUNCH_CHECK("div_scores_kernel");
+  return 0;
 }
 
 int launch_grad_dense(const float* z, int64_t ldz, int64_t nq, int64_t E, const int64_t* label_idx, const float* row_stat,

@@ -457,6 +457,8 @@ int launch_pair_rowgrad(int pair_op, const float* A, int64_t lda, int64_t ra, co
                         const float* Wt, int64_t ldwt, float* dA, int64_t ldda, cudaStream_t st);   // Wt: [rb, >= ra]
 int launch_grad_dense(const float* z, int64_t ldz, int64_t nq, int64_t E, const int64_t* label_idx, const float* row_stat,
                       float offset, float inv_n, int div_z, float* G, int64_t ldg, cudaStream_t st);
+int launch_div_scores(const float* g, int64_t ldg, const float* z, int64_t ldz, int64_t n, int64_t E, float* W, int64_t ldw,
+                      cudaStream_t st);
 int launch_row_lse(const float* z, int64_t ldz, int64_t nq, int64_t E, const int64_t* label_idx, float* row_stat,
                    cudaStream_t st);
 int launch_unfold_distance(int model, const Rows& ent, const Rows& rel, const int64_t* triples, int64_t n, int dir,

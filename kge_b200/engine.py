@@ -509,8 +509,9 @@ def train_1vsall_backward(model: str, ent, rel, triples, loss: str = "bce", offs
     return d_ent, d_rel
 
 
-def score_1vsN_backward(model: str, combine: str, ent, rel, q, p, grad_scores):
-    """(d_ent, d_rel) of a dense [n, E] score block of the dot family given dL/dscores (fresh tensors)."""
+def score_1vsN_backward(model: str, combine: str, ent, rel, q, p, grad_scores, l_norm: float = 1.0):
+    """(d_ent, d_rel) of a dense [n, E] score block given dL/dscores (fresh tensors): dot family (tensor cores), TransE
+    L1 / L2 and RotatE L1 (row-gradient kernel)."""
     _require_cuda(ent, rel, grad_scores)
     lib, k = _lib.load(), _Keep()
     re_, rr = k.rows(ent), k.rows(rel)
@@ -523,7 +524,7 @@ def score_1vsN_backward(model: str, combine: str, ent, rel, q, p, grad_scores):
     ws = torch.empty(lib.b200kge_score_1vsN_backward_workspace_bytes(MODELS[model], n, ent.shape[0], ent.shape[1]),
                      dtype=torch.uint8, device=dev)
     _lib.check(lib.b200kge_score_1vsN_backward(
-        MODELS[model], SP_ if combine == "sp_" else _PO, C.byref(re_), C.byref(rr), qi.data_ptr(), pi.data_ptr(), n,
+        MODELS[model], SP_ if combine == "sp_" else _PO, l_norm, C.byref(re_), C.byref(rr), qi.data_ptr(), pi.data_ptr(), n,
         g.data_ptr(), g.stride(0), d_ent.data_ptr(), d_ent.stride(0), d_rel.data_ptr(), d_rel.stride(0), ws.data_ptr(),
         ws.numel(), _stream(dev)))
     return d_ent, d_rel

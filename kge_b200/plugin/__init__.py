@@ -339,17 +339,24 @@ class _B200ModelMixin:
         n = p.numel()
         return torch.cat((ref(ent[a[:n]], rel[p], cand, "sp_"), ref(cand, rel[p], ent[a[n:]], "_po")), dim=1)
 
+    def _b200_native_family(self):
+        """Models / norms whose 1-vs-N gradients the library computes itself."""
+        name, ln = self._b200_name, self._b200_args()[0]
+        return (name in ("complex", "distmult", "simple", "cp", "rescal")
+                or (name == "transe" and ln in (1.0, 2.0)) or (name == "rotate" and ln == 1.0))
+
     def _b200_score_backward(self, ent_w, rel_w, kind, a, p, b, grad_out):
         name = self._b200_name
-        if (self.b200_backward == "native" and b is None and kind in ("sp_", "_po", "sp_po")
-                and name in ("complex", "distmult", "simple", "cp", "rescal")):
-            # dense [n, E] (or [n, 2E]) scores over the whole table: tensor-core gradient GEMMs + unfold
+        if self.b200_backward == "native" and b is None and kind in ("sp_", "_po", "sp_po") and self._b200_native_family():
+            # dense [n, E] (or [n, 2E]) scores over the whole table: tensor-core gradient GEMMs (dot family) or the
+            # row-gradient passes (TransE L1 / L2, RotatE L1) + unfold
             E_ = ent_w.shape[0]
+            ln = self._b200_args()[0]
             if kind != "sp_po":
-                return engine.score_1vsN_backward(name, kind, ent_w.detach(), rel_w.detach(), a, p, grad_out)
+                return engine.score_1vsN_backward(name, kind, ent_w.detach(), rel_w.detach(), a, p, grad_out, ln)
             n = p.numel()
-            de1, dr1 = engine.score_1vsN_backward(name, "sp_", ent_w.detach(), rel_w.detach(), a[:n], p, grad_out[:, :E_])
-            de2, dr2 = engine.score_1vsN_backward(name, "_po", ent_w.detach(), rel_w.detach(), a[n:], p, grad_out[:, E_:])
+            de1, dr1 = engine.score_1vsN_backward(name, "sp_", ent_w.detach(), rel_w.detach(), a[:n], p, grad_out[:, :E_], ln)
+            de2, dr2 = engine.score_1vsN_backward(name, "_po", ent_w.detach(), rel_w.detach(), a[n:], p, grad_out[:, E_:], ln)
             return de1 + de2, dr1 + dr2
         e, r = ent_w.detach().requires_grad_(True), rel_w.detach().requires_grad_(True)
         with torch.enable_grad():
@@ -359,9 +366,7 @@ class _B200ModelMixin:
     def _b200_loss_1vsall_backward(self, ent_w, rel_w, triples, loss, offset):
         name = self._b200_name
         ln = self._b200_args()[0]
-        native = name in ("complex", "distmult", "simple", "cp", "rescal") or \
-            (name == "transe" and ln in (1.0, 2.0)) or (name == "rotate" and ln == 1.0)
-        if self.b200_backward == "native" and native:
+        if self.b200_backward == "native" and self._b200_native_family():
             return engine.train_1vsall_backward(name, ent_w.detach(), rel_w.detach(), triples, loss, offset, ln)
         e, r = ent_w.detach().requires_grad_(True), rel_w.detach().requires_grad_(True)
         n = triples.shape[0]

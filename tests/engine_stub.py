@@ -78,10 +78,10 @@ def ns_backward(model, ent, rel, triples, negatives, offset=0.0, l_norm=1.0, bat
     return d_ent * scale, d_rel * scale
 
 
-def score_1vsN_backward(model, combine, ent, rel, q, p, grad_scores):
+def score_1vsN_backward(model, combine, ent, rel, q, p, grad_scores, l_norm=1.0):
     e, r = ent.detach().clone().requires_grad_(True), rel.detach().clone().requires_grad_(True)
     with torch.enable_grad():
-        x = score_1vsN(model, combine, e, r, e, q, p, None)
+        x = score_1vsN(model, combine, e, r, e, q, p, None, l_norm)
         return torch.autograd.grad(x, (e, r), grad_scores)
 
 

@@ -141,9 +141,10 @@ def test_ns_backward(eng, model, D, ln):
     _assert_close(d_rel, ref_r, f"{model} d_rel")
 
 
-@pytest.mark.parametrize("model,D", [("complex", 128), ("distmult", 64), ("simple", 128), ("cp", 64), ("rescal", 24)])
+@pytest.mark.parametrize("model,D,ln", [("complex", 128, 1.0), ("distmult", 64, 1.0), ("simple", 128, 1.0), ("cp", 64, 1.0),
+                                        ("rescal", 24, 1.0), ("transe", 72, 1.0), ("transe", 72, 2.0), ("rotate", 72, 1.0)])
 @pytest.mark.parametrize("combine", ["sp_", "_po"])
-def test_score_1vsN_backward_vs_autograd(eng, model, D, combine):
+def test_score_1vsN_backward_vs_autograd(eng, model, D, ln, combine):
     """Backward of a dense [n, E] score block given dL/dscores (the unfused route of a job: score_sp -> KgeLoss ->
     autograd) against torch autograd of the oracle's expression in fp64."""
     E, R, n = 3001, 5, 150
@@ -153,10 +154,10 @@ def test_score_1vsN_backward_vs_autograd(eng, model, D, combine):
     g = torch.randn((n, E), generator=torch.Generator().manual_seed(2)) * 0.1
     e64, r64 = ent.double().requires_grad_(True), rel.double().requires_grad_(True)
     if combine == "sp_":
-        x = orc.score_emb(model, e64[q], r64[tri[:, 1]], e64, "sp_")
+        x = orc.score_emb(model, e64[q], r64[tri[:, 1]], e64, "sp_", ln)
     else:
-        x = orc.score_emb(model, e64, r64[tri[:, 1]], e64[q], "_po")
+        x = orc.score_emb(model, e64, r64[tri[:, 1]], e64[q], "_po", ln)
     ref_e, ref_r = torch.autograd.grad(x, (e64, r64), g.double())
-    d_ent, d_rel = eng.score_1vsN_backward(model, combine, ent.cuda(), rel.cuda(), q.cuda(), tri[:, 1].cuda(), g.cuda())
+    d_ent, d_rel = eng.score_1vsN_backward(model, combine, ent.cuda(), rel.cuda(), q.cuda(), tri[:, 1].cuda(), g.cuda(), ln)
     _assert_close(d_ent, ref_e, f"{model} {combine} d_ent")
     _assert_close(d_rel, ref_r, f"{model} {combine} d_rel")

@@ -114,7 +114,7 @@ def test_unmodified_entity_ranking_job(model, splits):
     assert b["mean_reciprocal_rank_filtered"] == pytest.approx(a["mean_reciprocal_rank_filtered"], rel=2e-3)
 
 
-@pytest.mark.parametrize("model", ["complex", "transe"])
+@pytest.mark.parametrize("model", ["complex", "transe", "rotate"])
 def test_training_epoch_through_plugin(model, splits):
     """Two full training epochs (forward, backward, Adagrad step) of the unmodified job and of the fused job move
     the tables as the reference does: same avg_loss in epoch 1 AND in epoch 2 (i.e. after the updates)."""
