@@ -94,3 +94,26 @@ def test_option_without_process_group_is_single_process():
     losses, _, _ = _train("1vsAll", True)          # no group initialised: the whole batch stays on this process
     ref, _, _ = _train("1vsAll", False)
     assert losses == ref
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("batch_size", [1, 7, 30, 64])
+def test_rank_slices_partition_every_subbatch(world, batch_size):
+    """The ranks' row ranges tile [0, B) exactly — also inside sub-batches and when B < world."""
+    hostenv.import_kge()
+    from kge_b200.plugin.jobs import _BatchSplit
+
+    class Probe(_BatchSplit):
+        def __init__(self, rank):
+            self._b200_rank_world = (rank, world)
+
+    for sub in (batch_size, 5, 16):
+        seen = []
+        for start in range(0, batch_size, sub):
+            sl = slice(start, min(start + sub, batch_size))
+            for rank in range(world):
+                mine = Probe(rank)._b200_my_rows(sl, batch_size)
+                if mine is not None:
+                    assert sl.start <= mine.start < mine.stop <= sl.stop
+                    seen.extend(range(mine.start, mine.stop))
+        assert sorted(seen) == list(range(batch_size))
