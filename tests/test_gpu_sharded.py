@@ -39,3 +39,18 @@ def test_sharded_world1_matches_oracle(model, D):
     v, i = m.topk_sp(s, p, 5)
     order = torch.sort(-full[:, :E], dim=1, stable=True).indices[:, :5]
     assert torch.equal(i.cpu(), order)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_operands_on_a_non_current_device():
+    """`job.device: cuda:1` without set_device (LibKGE never calls it): the engine follows its operands."""
+    from kge_b200 import engine
+
+    torch.cuda.set_device(0)
+    ent, rel = orc.make_tables("complex", 501, 5, 64, sigma=0.5)
+    tri = orc.make_triples(501, 5, 40)
+    dev = torch.device("cuda", 1)
+    x = engine.score_sp_po("complex", ent.to(dev), rel.to(dev), tri[:, 0].to(dev), tri[:, 1].to(dev), tri[:, 2].to(dev))
+    ref = orc.score_sp_po("complex", ent, rel, tri[:, 0], tri[:, 1], tri[:, 2])
+    assert x.device == dev
+    assert float((x.cpu() - ref).abs().max()) <= 1e-4 * float(ref.pow(2).mean().sqrt())
