@@ -68,7 +68,7 @@ def _stream(dev) -> C.c_void_p:
     """The operands' current stream.  The library launches on the CURRENT device, so follow the operands when they live
     elsewhere (`job.device: cuda:1` in a process that never called set_device, e.g. LibKGE's search workers,
     kge/job/search.py:36-40); a no-op when the devices already agree."""
-    idx = getattr(dev, "index", None)
+    idx = dev.index if isinstance(dev, torch.device) else torch.device(dev).index
     if idx is not None and idx != torch.cuda.current_device():
         torch.cuda.set_device(idx)
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
