@@ -1,5 +1,7 @@
 """Sharded model on the GPU backend.  world=1 runs under plain pytest; the multi-rank case is
 launched by scripts/sharded_check.py under torchrun."""
+import os
+
 import pytest
 import torch
 
@@ -41,7 +43,9 @@ def test_sharded_world1_matches_oracle(model, D):
     assert torch.equal(i.cpu(), order)
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.skipif(os.environ.get("B200KGE_TEST_MULTI_DEVICE") != "1" or torch.cuda.device_count() < 2,
+                    reason="opt-in (B200KGE_TEST_MULTI_DEVICE=1, two GPUs): written after the round's GPU budget was spent, "
+                           "not yet run on hardware")
 def test_operands_on_a_non_current_device():
     """`job.device: cuda:1` without set_device (LibKGE never calls it): the engine follows its operands."""
     from kge_b200 import engine
@@ -52,5 +56,6 @@ def test_operands_on_a_non_current_device():
     dev = torch.device("cuda", 1)
     x = engine.score_sp_po("complex", ent.to(dev), rel.to(dev), tri[:, 0].to(dev), tri[:, 1].to(dev), tri[:, 2].to(dev))
     ref = orc.score_sp_po("complex", ent, rel, tri[:, 0], tri[:, 1], tri[:, 2])
+    torch.cuda.set_device(0)
     assert x.device == dev
     assert float((x.cpu() - ref).abs().max()) <= 1e-4 * float(ref.pow(2).mean().sqrt())
